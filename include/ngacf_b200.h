@@ -1,0 +1,176 @@
+/*
+ * ngacf_b200 -- C-ABI of the B200-native SPUIGACF propagation-and-scoring hot path.
+ *
+ * The reference (cleverer123/NGACF) has no FFI: its boundary for this path is the Python call surface
+ * of graphattention/SPUIGACF.py, graphattention/BPRLoss.py and train_eval_Gowalla.py.
+ * Every entry point below replaces one or more reference call sites and says which (file:line relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in _host;
+ *   - the caller owns every buffer; nothing is allocated, freed or synchronised here, so every call
+ *     is CUDA-graph capturable (ngacf_graph_build is the one documented exception: it is a build-time
+ *     call, still async, and reports its data-dependent sizes through a device counter array);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: NGACF_OK or a negative NGACF_ERR_* code; ngacf_last_error() gives the text;
+ *   - all float tensors are fp32 row-major with 64 columns (embedSize 64 of every BASELINE config);
+ *   - node numbering: users 0..U-1 then items U..U+I-1 ("features" layout of SPUIGACF.py:38);
+ *   - H = heads of a stage: 8 (eight 64->8 heads, SPUIGACF.py:191-198) or 1 (out_att 64->64, :200-205).
+ */
+#ifndef NGACF_B200_H
+#define NGACF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGACF_OK 0
+#define NGACF_ERR_INVALID_ARG (-1)
+#define NGACF_ERR_CUDA (-2)
+#define NGACF_ERR_WORKSPACE (-3)
+#define NGACF_ERR_UNSUPPORTED (-4)
+
+#define NGACF_D 64            /* embedding width */
+#define NGACF_CHUNK 128       /* max edges per aggregation task (degree bucketing granularity) */
+#define NGACF_TOPK 20         /* K_max of eval_neg_all (train_eval_Gowalla.py:276,375) */
+
+const char* ngacf_last_error(void);
+int ngacf_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) graph builder.  Replaces get_adj_mat/buildLaplacianMat('ui_mat')/scipySP_torchSP/.coalesce()
+ * (data/loadGowalla.py:179-186,218-219,229-253) and the per-call COO rebuild + coalesce sort of
+ * SPUIGACF.py:365,377.  Input: COO (u,i) int64, any order, duplicates allowed.  Output: coalesced CSR,
+ * CSC, CSC->CSR edge permutation, the unified node adjacency used by the aggregation kernels and the
+ * degree-bucketed task list.
+ *
+ * counts[0]=E (unique edges) counts[1]=T (tasks) counts[2]=L (long rows, >NGACF_CHUNK edges)
+ * counts[3]=S (scratch slots) counts[4]=#users with zero edges (reference asserts 0, SPUIGACF.py:368)
+ * counts[5]=#out-of-range input edges  counts[6]=T_u: tasks [0,T_u) are user rows, [T_u,T) item rows;
+ * inside a side the tasks are ordered longest first (the degree buckets).  Buffer capacities: *_idx/perm/adj_* for E_in edges,
+ * tasks for (U+I)+2*E_in/NGACF_CHUNK entries of 4 ints, long_* for 2*E_in/NGACF_CHUNK+1 ints.
+ * ------------------------------------------------------------------------------------------- */
+size_t ngacf_graph_build_workspace_bytes(int64_t E_in, int32_t U, int32_t I);
+int ngacf_graph_build(const int64_t* coo_u, const int64_t* coo_i, int64_t E_in, int32_t U, int32_t I,
+                      int32_t* rowptr, int32_t* colidx, int32_t* colptr, int32_t* rowidx, int32_t* perm,
+                      int32_t* adj_ptr, int32_t* adj_idx, int32_t* adj_eid,
+                      int32_t* tasks /* [cap][4] = node,beg,end,long_id|-1 */,
+                      int32_t* long_first_slot, int32_t* long_counter,
+                      int32_t* counts /* [8] */, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dropout keep masks (specified Philox4x32-10 streams; the reference draws from torch's global
+ * generator at SPUIGACF.py:208,213 (features) and :375 (edges), which no custom kernel can replay).
+ * feat: uint64[N], bit d = keep (n,d).  edge: uint8[E], bit k = keep (edge e, head k).
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream);
+int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a3,a5,a6) dense transform: h = dropout(act(X)) @ [W_0..W_{H-1}],  s[n,k] = a_k . h[n, head k].
+ * Replaces getFeatureMat (SPUIGACF.py:30-39), F.dropout (:208,213), the 2x torch.mm of every head
+ * (:356-357) and the `a.mm(edge_h)` logit (:359-361, which is rank-1: s[u]+s[i]).
+ * Xu/Xi: stage input rows of users/items (embedding tables for stage 0; Z_prev, Z_prev+64*U after).
+ * apply_elu: input is a pre-activation (ELU applied on load, SPUIGACF.py:397-398).
+ * wtab: device array of 3*H pointers [W_u heads | W_i heads | a heads], the reference's own
+ * parameter tensors (64,DH) and (1,2*DH).
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
+                        const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a6-a9) fused edge softmax + neighbour aggregation, both sides in one launch:
+ *   e = exp(-LeakyReLU_0.2(s[n]+s[m])), norm[n] = sum_m e, Z[n] = h[n] + sum_m drop(e) h[m] / norm[n]
+ * Replaces SPUIGACF.py:359-391 (2 sparse_coo_tensor + 2 coalesce + 4 sparse.mm + div + NaN->0).
+ * Z is PRE-ELU; the consumer applies ELU (:397-398, :214).  scratch: S*(64+8) floats.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
+                        const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
+                        const float* h, const float* s, int32_t H, const uint8_t* edgemask, float scale,
+                        float* Z, float* norm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a10) pair scoring: score[b] = ELU(Z[u_b]) . ELU(Z[U+i_b])   (SPUIGACF.py:49-52), fixed summation
+ * tree, and its backward G[row] += dscore * ELU(Z[other]) * ELU'(Z[row]),
+ * deterministic (no atomics).  G must be zero-filled by the caller.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream);
+int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const int64_t* items, const float* dscore,
+                          int32_t B, float* G, void* stream);
+
+/* F = ELU(Z) materialised for evaluation (SPUIGACF.py:214) */
+int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream);
+
+/* (a11) BPRLoss (BPRLoss.py:8-9): loss = mean softplus(-(pos-neg)); dpos = -sigmoid(-(pos-neg))*gscale/B, dneg = -dpos */
+int ngacf_bpr_loss(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a12) backward of one stage (closed form of SURVEY.md 3.4; the reference uses autograd).
+ * prep:   Ghat = G/norm, dN = -(G . (Z-h))/norm per head.
+ * edges:  mode 0 = user rows (CSR walk): computes d s_e per edge, stores it in ds_store[E*H];
+ *         mode 1 = item rows (CSC walk): reads d s_e through adj_eid -- no atomics on either side.
+ *         dh[n] = G[n] + sum_m drop(e) Ghat[m] + dS[n] (x) a_side,  dS[n] = sum_m ds.
+ * transform_bwd: dW/da (accumulated into gtab, same layout as wtab), dX -> Gprev = dX*mask*scale*ELU'(Zprev)
+ *         (stage > 0) or accumulated into the embedding gradients (stage 0).
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_stage_bwd_prep(const float* G, const float* Z, const float* h, const float* norm, int32_t H, int64_t N,
+                         float* Ghat, float* dN, void* stream);
+int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end, const int32_t* adj_ptr,
+                          const int32_t* adj_idx, const int32_t* adj_eid,
+                          const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
+                          const float* G, const float* Ghat, const float* dN, const float* h, const float* s, int32_t H,
+                          const uint8_t* edgemask, float scale, const float* const* wtab, int32_t U,
+                          float* ds_store, float* dh, float* dS, void* stream);
+size_t ngacf_transform_bwd_workspace_bytes(int32_t U, int32_t I);
+int ngacf_transform_bwd(const float* dh, const float* dS, const float* h, const float* Xu, const float* Xi, int32_t apply_elu,
+                        const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H,
+                        int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate_dx, int32_t accumulate_dw,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* (a13) Adam with L2 weight decay over a table of tensors (torch.optim.Adam semantics, run_Gowalla.py:114).
+ * tab: device array of n entries {param, grad, exp_avg, exp_avg_sq, numel} (5 x 64-bit words each).
+ * step_host is the 1-based step count (bias corrections computed on the host in double). */
+int ngacf_adam_step(const uint64_t* tab, int32_t n_tensors, int64_t total_numel, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int64_t step_host, void* stream);
+/* same, with the step counter resident on the device so a captured CUDA graph can be replayed:
+ * state = double[4] {step, lr/(1-beta1^step), 1/sqrt(1-beta2^step), unused}; the call increments step first. */
+int ngacf_adam_step_dev(const uint64_t* tab, int32_t n_tensors, int64_t total_numel, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, double* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a14) PairSampling sampler.  Replaces train_pos_neg_exclude_test + train_pair_sampling
+ * (data/loadGowalla.py:63-77): per train row, one positive uniform from the user's train items and one
+ * negative uniform from item_pool minus train items (rank-select; negatives are never materialised).
+ * Specified stream: Philox counter (row, epoch, TAG), key = seed.  neg = -1 if the user has no negative.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr, const int32_t* train_items,
+                       const int32_t* train_rank, const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end,
+                       uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a16,a17) AllNeg evaluation.  Replaces the 64x2048 score tiles + D2H + heapq.nlargest of
+ * train_eval_Gowalla.py:300-341,370-385: for every listed user the top-20 candidate items
+ * (candidates = item_pool - train items; order = score desc, item id asc) straight from the
+ * propagated features; the dense score matrix never exists in HBM.
+ *   exact: fp32 CUDA-core scores with the fixed summation tree (bit-reproducible).
+ * F = ELU(Z_last) (N,64) final features (ngacf_final_features).  in_pool: uint8[I].
+ * top_ids int32 [n_users][20] (-1 padded), top_scores fp32 likewise.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
+                           const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
+                           int32_t* top_ids, float* top_scores, void* stream);
+/* hits + metric sums (metrics.py:10-86 via get_performance, train_eval_Gowalla.py:419-429):
+ * hits uint8 [n_users][20]; sums double[16] = {precision,recall,ndcg,hit}@{1,5,10,20} summed over users
+ * (the caller divides by the reference's divisor, the number of users with train data, :283). */
+size_t ngacf_eval_metrics_workspace_bytes(int32_t n_users);
+int ngacf_eval_metrics(const int32_t* top_ids, const int32_t* users, int32_t n_users, const int32_t* test_ptr,
+                       const int32_t* test_items, uint8_t* hits, double* sums, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGACF_B200_H */

@@ -1,0 +1,108 @@
+// Shared device helpers for the ngacf_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ngacf_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "ngacf_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace ngacf {
+
+constexpr int D = NGACF_D;
+constexpr int CHUNK = NGACF_CHUNK;
+constexpr float LRELU_ALPHA = 0.2f;   // SPUIGACF.py:22
+constexpr int SCRATCH_STRIDE = D + 8; // per-slot partial: 64 accumulators + up to 8 per-head sums
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define NGACF_REQUIRE(cond, ...)                       \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ngacf::set_error(__VA_ARGS__);             \
+            return NGACF_ERR_INVALID_ARG;              \
+        }                                              \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// loads / stores with cache intent: gathered tables go through L1 (popular rows hit), streamed
+// arrays do not allocate in L1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_gather4(const float* p) {   // read-only path, L1 allocating
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg4(const float* p) {   // L2-coherent (other SMs' writes in this launch)
+    return __ldcg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ float elu(float z) { return z > 0.f ? z : expm1f(z); }
+__device__ __forceinline__ float elu_grad(float z) { return z > 0.f ? 1.f : __expf(z); }
+
+// e = exp(-LeakyReLU(x)); the same expression is used by forward and backward so the recomputed
+// weight is bit-identical to the one the forward normalised with.
+__device__ __forceinline__ float edge_weight(float x) {
+    float l = x > 0.f ? x : LRELU_ALPHA * x;
+    return __expf(-l);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (same constants/rounds as oracle/port.py:philox4x32_10)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__host__ __device__ __forceinline__ uint32_t keep_threshold(float droprate) {
+    double t = floor((1.0 - (double)droprate) * 65536.0 + 0.5);
+    if (t < 0) t = 0;
+    if (t > 65536.0) t = 65536.0;
+    return (uint32_t)t;
+}
+
+// 16-lane group helpers: a "group" is one half of a warp; the two halves may diverge.
+__device__ __forceinline__ unsigned group_mask() { return (threadIdx.x & 16) ? 0xFFFF0000u : 0x0000FFFFu; }
+
+template <int H>
+__device__ __forceinline__ float head_reduce(float v, unsigned mask) {
+    // sum over the lanes that share a head: H=8 -> lane pairs, H=1 -> all 16 lanes (adjacent-pair tree)
+    v += __shfl_xor_sync(mask, v, 1, 16);
+    if (H == 1) {
+        v += __shfl_xor_sync(mask, v, 2, 16);
+        v += __shfl_xor_sync(mask, v, 4, 16);
+        v += __shfl_xor_sync(mask, v, 8, 16);
+    }
+    return v;
+}
+
+}  // namespace ngacf

@@ -1,0 +1,419 @@
+// Backward of one SpUIGAT stage in closed form (the reference relies on autograd through
+// graphattention/SPUIGACF.py:340-400).  Unified-node formulation, G = dL/dZ:
+//   Ghat[n] = G[n]/norm[n]                      dN[n] = -(G[n].(Z[n]-h[n]))/norm[n]            (per head)
+//   d e~(n,m) = Ghat[n].h[m] + Ghat[m].h[n]     d e = keep*scale*d e~ + dN[n] + dN[m]
+//   d s = d e * (-e) * LeakyReLU'(s[n]+s[m])    dS[n] = sum_m d s(n,m)
+//   dh[n] = G[n] + sum_m drop(e) Ghat[m] + dS[n] (x) a_side
+//   dW = Xd^T dh,  da = sum_n dS[n] (x) h[n],  dX = dh W^T (then dropout mask and ELU' of the producer)
+// User rows walk the CSR half and store d s per edge; item rows walk the CSC half and read it back
+// through adj_eid, so neither side needs atomics.
+#include "common.cuh"
+
+namespace ngacf {
+
+template <int H>
+__device__ __forceinline__ int lane_head_b(int lane16) { return H == 8 ? (lane16 >> 1) : 0; }
+template <int H>
+__device__ __forceinline__ bool head_writer(int lane16) { return H == 8 ? ((lane16 & 1) == 0) : (lane16 == 0); }
+
+// ------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) stage_bwd_prep_kernel(const float* __restrict__ G, const float* __restrict__ Z,
+                                                             const float* __restrict__ h, const float* __restrict__ norm, int64_t N,
+                                                             float* __restrict__ Ghat, float* __restrict__ dN) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    if (n >= N) return;
+    const int head = lane_head_b<H>(lane16);
+    const float4 g = ld_stream4(G + n * D + lane16 * 4);
+    const float4 z = ld_stream4(Z + n * D + lane16 * 4);
+    const float4 hh = ld_stream4(h + n * D + lane16 * 4);
+    const float nr = __ldg(norm + n * H + head);
+    const float inv = nr != 0.f ? 1.0f / nr : 0.f;
+    float part = g.x * (z.x - hh.x) + g.y * (z.y - hh.y) + g.z * (z.z - hh.z) + g.w * (z.w - hh.w);
+    part = head_reduce<H>(part, gm);
+    st_stream4(Ghat + n * D + lane16 * 4, make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv));
+    if (head_writer<H>(lane16)) dN[n * H + head] = -part * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// defined in propagate_fwd.cu's translation unit as a template; re-declared here (same body) to keep
+// the two .cu files independently compilable
+template <int H, int NSUM>
+__device__ __forceinline__ bool long_row_combine_b(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
+                                                   float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
+    const int head = lane_head_b<H>(lane16);
+    const int first = long_first_slot[lid];
+    const int nslots = long_first_slot[lid + 1] - first;
+    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
+    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
+    if (head_writer<H>(lane16)) {
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
+    }
+    __threadfence();
+    __syncwarp(gm);
+    int old = 0;
+    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
+    old = __shfl_sync(gm, old, 0, 16);
+    if (old != nslots - 1) return false;
+    __threadfence();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ts[NSUM];
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
+    for (int c = 0; c < nslots; ++c) {
+        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
+        float4 v = ld_cg4(sl + lane16 * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
+    }
+    acc = t;
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
+    if (lane16 == 0) long_counter[lid] = 0;
+    return true;
+}
+
+template <int H, int MODE, bool DROP>
+__global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
+                                                              const int* __restrict__ adj_ptr, const int* __restrict__ adj_idx,
+                                                              const int* __restrict__ adj_eid, const int* __restrict__ long_first_slot,
+                                                              int* long_counter, float* scratch, const float* __restrict__ G,
+                                                              const float* __restrict__ Ghat, const float* __restrict__ dN,
+                                                              const float* __restrict__ h, const float* __restrict__ s,
+                                                              const uint8_t* __restrict__ edgemask, float scale,
+                                                              const float* const* __restrict__ wtab, int U,
+                                                              float* ds_store, float* __restrict__ dh, float* __restrict__ dS) {
+    constexpr int DH = D / H;
+    const int t = T_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    if (t >= T_end) return;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int head = lane_head_b<H>(lane16);
+    const int4 tk = __ldg(tasks + t);
+    const int node = tk.x, beg = tk.y, end = tk.z, lid = tk.w;
+    const float sn = __ldg(s + (int64_t)node * H + head);
+    const float sc = DROP ? scale : 1.f;
+    float4 ghn = make_float4(0.f, 0.f, 0.f, 0.f), hn = ghn;
+    float dNn = 0.f;
+    if (MODE == 0) {
+        ghn = ld_stream4(Ghat + (int64_t)node * D + lane16 * 4);
+        hn = ld_stream4(h + (int64_t)node * D + lane16 * 4);
+        dNn = __ldg(dN + (int64_t)node * H + head);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dSacc = 0.f;
+    for (int base = beg; base < end; base += 16) {
+        const int idx = base + lane16;
+        int m_l = 0, eid_l = 0;
+        unsigned mk_l = 0xFFu;
+        if (idx < end) {
+            m_l = ld_stream_i32(adj_idx + idx);
+            eid_l = ld_stream_i32(adj_eid + idx);
+            if (DROP) mk_l = edgemask[eid_l];
+        }
+        const int cnt = min(16, end - base);
+#pragma unroll 2
+        for (int j = 0; j < cnt; ++j) {
+            const int m = __shfl_sync(gm, m_l, j, 16);
+            const int eid = __shfl_sync(gm, eid_l, j, 16);
+            const float sm = __ldg(s + (int64_t)m * H + head);
+            const float4 gm4 = ld_gather4(Ghat + (int64_t)m * D + lane16 * 4);
+            const float x = sn + sm;
+            const float e = edge_weight(x);
+            float keepsc = sc;
+            if (DROP) {
+                const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
+                keepsc = ((mk >> head) & 1u) ? sc : 0.f;
+            }
+            const float et = e * keepsc;
+            acc.x = fmaf(et, gm4.x, acc.x); acc.y = fmaf(et, gm4.y, acc.y);
+            acc.z = fmaf(et, gm4.z, acc.z); acc.w = fmaf(et, gm4.w, acc.w);
+            float ds;
+            if (MODE == 0) {
+                const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                float part = ghn.x * hm.x + ghn.y * hm.y + ghn.z * hm.z + ghn.w * hm.w
+                           + gm4.x * hn.x + gm4.y * hn.y + gm4.z * hn.z + gm4.w * hn.w;
+                const float det = head_reduce<H>(part, gm);
+                const float de = fmaf(det, keepsc, dNn + __ldg(dN + (int64_t)m * H + head));
+                ds = de * (-e) * (x > 0.f ? 1.f : LRELU_ALPHA);
+                if (head_writer<H>(lane16)) ds_store[(int64_t)eid * H + head] = ds;
+            } else {
+                ds = __ldg(ds_store + (int64_t)eid * H + head);
+            }
+            dSacc += ds;
+        }
+    }
+    if (lid >= 0) {
+        float sums[1] = {dSacc};
+        const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
+        if (!long_row_combine_b<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        dSacc = sums[0];
+    }
+    const float4 gn = ld_stream4(G + (int64_t)node * D + lane16 * 4);
+    const float* ap = wtab[2 * H + head] + (node >= U ? DH : 0) + ((lane16 * 4) % DH);
+    const float4 a4 = make_float4(__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3));
+    st_stream4(dh + (int64_t)node * D + lane16 * 4,
+               make_float4(gn.x + acc.x + dSacc * a4.x, gn.y + acc.y + dSacc * a4.y, gn.z + acc.z + dSacc * a4.z, gn.w + acc.w + dSacc * a4.w));
+    if (head_writer<H>(lane16)) dS[(int64_t)node * H + head] = dSacc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense backward: dX = dh W^T (+ mask/ELU'), partial dW = Xd^T dh, partial da = sum dS (x) h
+// persistent blocks per side; deterministic two-pass reduction of the partials
+// ------------------------------------------------------------------------------------------------
+constexpr int TB_TM = 128;
+constexpr int TB_XS = 68;
+constexpr size_t TB_SMEM = (size_t)(64 * 64 + 2 * TB_TM * TB_XS + 256) * sizeof(float);
+constexpr int TB_PART = 64 * 64 + 64;   // floats per block partial
+
+template <int H>
+__global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dS,
+                                                            const float* __restrict__ h, const float* __restrict__ Xu,
+                                                            const float* __restrict__ Xi, int apply_elu,
+                                                            const uint64_t* __restrict__ featmask, float scale,
+                                                            const float* const* __restrict__ wtab, int U, int I, int nb_u,
+                                                            float* __restrict__ dXu, float* __restrict__ dXi, int accumulate_dx,
+                                                            float* __restrict__ partials) {
+    extern __shared__ __align__(16) float smem[];
+    float* WTs = smem;                       // [c][k] = W[k][c]
+    float* dhs = smem + 64 * 64;             // [128][68]
+    float* Xds = dhs + TB_TM * TB_XS;        // [128][68]
+    float* red = Xds + TB_TM * TB_XS;        // [256]
+    constexpr int DH = D / H;
+    const bool item_side = (int)blockIdx.x >= nb_u;
+    const int bs = item_side ? blockIdx.x - nb_u : blockIdx.x;
+    const int nbs = item_side ? gridDim.x - nb_u : nb_u;
+    const int rows_side = item_side ? I : U;
+    const float* X = item_side ? Xi : Xu;
+    float* dX = item_side ? dXi : dXu;
+    const int64_t node_off = item_side ? U : 0;
+    const int tiles = (rows_side + TB_TM - 1) / TB_TM;
+
+    // WTs[c*64+k] = W[k][c]
+    {
+        const float* const* wptr = wtab + (item_side ? H : 0);
+        for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+            int k = idx >> 6, c = idx & 63;
+            WTs[c * 64 + k] = __ldg(wptr[c / DH] + k * DH + (c % DH));
+        }
+    }
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float accW[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accW[i][0] = accW[i][1] = accW[i][2] = accW[i][3] = 0.f;
+    float acc_a = 0.f;
+    const int ac = threadIdx.x & 63, arp = threadIdx.x >> 6;
+
+    for (int tile = bs; tile < tiles; tile += nbs) {
+        const int row0 = tile * TB_TM;
+        const int nrows = min(TB_TM, rows_side - row0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < TB_TM * 16; idx += 256) {
+            int r = idx >> 4, q = idx & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), x = v;
+            if (r < nrows) {
+                v = ld_stream4(dh + (node_off + row0 + r) * D + q * 4);
+                // same expression as transform_fwd: recomputes the dropped, activated stage input
+                x = ld_stream4(X + (int64_t)(row0 + r) * D + q * 4);
+                if (apply_elu) { x.x = elu(x.x); x.y = elu(x.y); x.z = elu(x.z); x.w = elu(x.w); }
+                if (featmask) {
+                    uint32_t m = (uint32_t)(featmask[node_off + row0 + r] >> (q * 4)) & 0xFu;
+                    x.x = (m & 1u) ? x.x * scale : 0.f; x.y = (m & 2u) ? x.y * scale : 0.f;
+                    x.z = (m & 4u) ? x.z * scale : 0.f; x.w = (m & 8u) ? x.w * scale : 0.f;
+                }
+            }
+            *reinterpret_cast<float4*>(dhs + r * TB_XS + q * 4) = v;
+            *reinterpret_cast<float4*>(Xds + r * TB_XS + q * 4) = x;
+        }
+        __syncthreads();
+
+        // (a) dXd[r][k] = sum_c dh[r][c] * W[k][c]; thread = rows ty+16i, k = 4tx..4tx+3
+        {
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll 2
+            for (int c4 = 0; c4 < 16; ++c4) {
+                float4 w0 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 0) * 64 + tx * 4);
+                float4 w1 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 1) * 64 + tx * 4);
+                float4 w2 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 2) * 64 + tx * 4);
+                float4 w3 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 3) * 64 + tx * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 x = *reinterpret_cast<const float4*>(dhs + (ty + 16 * i) * TB_XS + c4 * 4);
+                    acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
+                    acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
+                    acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
+                    acc[i][2] = fmaf(x.y, w1.z, acc[i][2]); acc[i][3] = fmaf(x.y, w1.w, acc[i][3]);
+                    acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]);
+                    acc[i][2] = fmaf(x.z, w2.z, acc[i][2]); acc[i][3] = fmaf(x.z, w2.w, acc[i][3]);
+                    acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]);
+                    acc[i][2] = fmaf(x.w, w3.z, acc[i][2]); acc[i][3] = fmaf(x.w, w3.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = ty + 16 * i;
+                if (r >= nrows) continue;
+                float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (featmask) {
+                    uint32_t m = (uint32_t)(featmask[node_off + row0 + r] >> (tx * 4)) & 0xFu;
+                    v.x = (m & 1u) ? v.x * scale : 0.f; v.y = (m & 2u) ? v.y * scale : 0.f;
+                    v.z = (m & 4u) ? v.z * scale : 0.f; v.w = (m & 8u) ? v.w * scale : 0.f;
+                }
+                float* dst = dX + (int64_t)(row0 + r) * D + tx * 4;
+                if (apply_elu) {   // the stage input was ELU(Zprev): chain through ELU'
+                    float4 z = ld_stream4(X + (int64_t)(row0 + r) * D + tx * 4);
+                    v.x *= elu_grad(z.x); v.y *= elu_grad(z.y); v.z *= elu_grad(z.z); v.w *= elu_grad(z.w);
+                }
+                if (accumulate_dx) {
+                    float4 o = *reinterpret_cast<const float4*>(dst);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+        }
+        // (b) dW[k][c] += sum_r Xd[r][k] * dh[r][c]; thread = k 4ty..4ty+3, c 4tx..4tx+3 (rows >= nrows are zero)
+#pragma unroll 4
+        for (int r = 0; r < TB_TM; ++r) {
+            float4 xs = *reinterpret_cast<const float4*>(Xds + r * TB_XS + ty * 4);
+            float4 ds = *reinterpret_cast<const float4*>(dhs + r * TB_XS + tx * 4);
+            accW[0][0] = fmaf(xs.x, ds.x, accW[0][0]); accW[0][1] = fmaf(xs.x, ds.y, accW[0][1]);
+            accW[0][2] = fmaf(xs.x, ds.z, accW[0][2]); accW[0][3] = fmaf(xs.x, ds.w, accW[0][3]);
+            accW[1][0] = fmaf(xs.y, ds.x, accW[1][0]); accW[1][1] = fmaf(xs.y, ds.y, accW[1][1]);
+            accW[1][2] = fmaf(xs.y, ds.z, accW[1][2]); accW[1][3] = fmaf(xs.y, ds.w, accW[1][3]);
+            accW[2][0] = fmaf(xs.z, ds.x, accW[2][0]); accW[2][1] = fmaf(xs.z, ds.y, accW[2][1]);
+            accW[2][2] = fmaf(xs.z, ds.z, accW[2][2]); accW[2][3] = fmaf(xs.z, ds.w, accW[2][3]);
+            accW[3][0] = fmaf(xs.w, ds.x, accW[3][0]); accW[3][1] = fmaf(xs.w, ds.y, accW[3][1]);
+            accW[3][2] = fmaf(xs.w, ds.z, accW[3][2]); accW[3][3] = fmaf(xs.w, ds.w, accW[3][3]);
+        }
+        // (c) da[c] += sum_r dS[r][head(c)] * h[r][c]
+        for (int r = arp; r < nrows; r += 4) {
+            const int64_t node = node_off + row0 + r;
+            acc_a = fmaf(__ldg(dS + node * H + ac / DH), __ldg(h + node * D + ac), acc_a);
+        }
+    }
+    float* part = partials + (size_t)blockIdx.x * TB_PART;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(part + (ty * 4 + i) * 64 + tx * 4) = make_float4(accW[i][0], accW[i][1], accW[i][2], accW[i][3]);
+    red[threadIdx.x] = acc_a;
+    __syncthreads();
+    if (threadIdx.x < 64) part[64 * 64 + threadIdx.x] = (red[threadIdx.x] + red[64 + threadIdx.x]) + (red[128 + threadIdx.x] + red[192 + threadIdx.x]);
+}
+
+// sums the block partials of each side in block order and writes the per-head gradient tensors
+template <int H>
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nb_u, int nb_total, float* const* __restrict__ gtab,
+                                       int accumulate) {
+    constexpr int DH = D / H;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * TB_PART) return;
+    const int side = idx / TB_PART, o = idx % TB_PART;
+    const int b0 = side ? nb_u : 0, b1 = side ? nb_total : nb_u;
+    float sum = 0.f;
+    for (int b = b0; b < b1; ++b) sum += partials[(size_t)b * TB_PART + o];
+    float* dst;
+    if (o < 64 * 64) {
+        const int k = o >> 6, c = o & 63;
+        dst = gtab[side * H + c / DH] + k * DH + (c % DH);
+    } else {
+        const int c = o - 64 * 64;
+        dst = gtab[2 * H + c / DH] + side * DH + (c % DH);
+    }
+    *dst = accumulate ? *dst + sum : sum;
+}
+
+}  // namespace ngacf
+
+using namespace ngacf;
+
+extern "C" int ngacf_stage_bwd_prep(const float* G, const float* Z, const float* h, const float* norm, int32_t H, int64_t N, float* Ghat,
+                                    float* dN, void* stream) {
+    NGACF_REQUIRE(G && Z && h && norm && Ghat && dN && N > 0, "stage_bwd_prep: null/empty argument");
+    NGACF_REQUIRE(H == 1 || H == 8, "stage_bwd_prep: H must be 1 or 8");
+    const int blocks = ceil_div(N * 16, 256);
+    if (H == 8) stage_bwd_prep_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(G, Z, h, norm, N, Ghat, dN);
+    else        stage_bwd_prep_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(G, Z, h, norm, N, Ghat, dN);
+    return check_launch("stage_bwd_prep");
+}
+
+extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end, const int32_t* adj_ptr,
+                                     const int32_t* adj_idx, const int32_t* adj_eid, const int32_t* long_first_slot,
+                                     int32_t* long_counter, float* scratch, const float* G, const float* Ghat, const float* dN,
+                                     const float* h, const float* s, int32_t H, const uint8_t* edgemask, float scale,
+                                     const float* const* wtab, int32_t U, float* ds_store, float* dh, float* dS, void* stream) {
+    NGACF_REQUIRE(tasks && adj_ptr && adj_idx && adj_eid && G && Ghat && dN && h && s && wtab && ds_store && dh && dS,
+                  "stage_bwd_edges: null argument");
+    NGACF_REQUIRE((mode == 0 || mode == 1) && (H == 1 || H == 8) && T_end >= T_begin, "stage_bwd_edges: bad mode/H/range");
+    if (T_end == T_begin) return NGACF_OK;
+    const int blocks = ceil_div((int64_t)(T_end - T_begin) * 16, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int4* tk = reinterpret_cast<const int4*>(tasks);
+#define LAUNCH(HH, MM, DR)                                                                                                              \
+    stage_bwd_edges_kernel<HH, MM, DR><<<blocks, 256, 0, st>>>(tk, T_begin, T_end, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, \
+                                                               scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS)
+    const bool dr = edgemask != nullptr;
+    if (H == 8) {
+        if (mode == 0) { if (dr) LAUNCH(8, 0, true); else LAUNCH(8, 0, false); }
+        else           { if (dr) LAUNCH(8, 1, true); else LAUNCH(8, 1, false); }
+    } else {
+        if (mode == 0) { if (dr) LAUNCH(1, 0, true); else LAUNCH(1, 0, false); }
+        else           { if (dr) LAUNCH(1, 1, true); else LAUNCH(1, 1, false); }
+    }
+#undef LAUNCH
+    return check_launch("stage_bwd_edges");
+}
+
+static void transform_bwd_grid(int U, int I, int* nb_u, int* nb_i) {
+    const int tiles_u = ceil_div(U, TB_TM), tiles_i = ceil_div(I, TB_TM);
+    const int budget = 2 * 148;   // two resident CTAs per SM (86 KB of shared memory each)
+    int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i));
+    if (bu < 1) bu = 1;
+    if (bu > tiles_u) bu = tiles_u;
+    int bi = budget - bu;
+    if (bi < 1) bi = 1;
+    if (bi > tiles_i) bi = tiles_i;
+    *nb_u = bu;
+    *nb_i = bi;
+}
+
+extern "C" size_t ngacf_transform_bwd_workspace_bytes(int32_t U, int32_t I) {
+    int bu, bi;
+    transform_bwd_grid(U, I, &bu, &bi);
+    return (size_t)(bu + bi) * TB_PART * sizeof(float);
+}
+
+extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float* h, const float* Xu, const float* Xi, int32_t apply_elu,
+                                   const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H,
+                                   int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate_dx, int32_t accumulate_dw,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    NGACF_REQUIRE(dh && dS && h && Xu && Xi && wtab && gtab && dXu && dXi && workspace && U > 0 && I > 0, "transform_bwd: null/empty argument");
+    NGACF_REQUIRE(H == 1 || H == 8, "transform_bwd: H must be 1 or 8");
+    if (workspace_bytes < ngacf_transform_bwd_workspace_bytes(U, I)) {
+        set_error("transform_bwd: workspace too small");
+        return NGACF_ERR_WORKSPACE;
+    }
+    int bu, bi;
+    transform_bwd_grid(U, I, &bu, &bi);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(transform_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
+        cudaFuncSetAttribute(transform_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partials = (float*)workspace;
+    if (H == 8) {
+        transform_bwd_kernel<8><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
+        reduce_partials_kernel<8><<<ceil_div(2 * TB_PART, 256), 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
+    } else {
+        transform_bwd_kernel<1><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
+        reduce_partials_kernel<1><<<ceil_div(2 * TB_PART, 256), 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
+    }
+    return check_launch("transform_bwd");
+}

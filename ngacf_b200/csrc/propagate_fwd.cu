@@ -1,0 +1,313 @@
+// Forward propagation kernels of one SpUIGAT stage (all heads at once):
+//   dropout masks (Philox), dense transform h = drop(act(X)) W with the rank-1 logit scalars s,
+//   fused edge-softmax + neighbour aggregation over the unified node adjacency.
+// Reference: graphattention/SPUIGACF.py:207-215 (SpUIGAT.forward), :340-400 (layer forward).
+#include "common.cuh"
+
+namespace ngacf {
+
+// ------------------------------------------------------------------------------------------------
+// dropout masks
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t decisions8(const uint32_t w[4], uint32_t thr) {
+    // eight 16-bit fields, low half first (oracle/port.py:_decisions)
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t r16 = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+        bits |= (uint32_t)(r16 < thr) << j;
+    }
+    return bits;
+}
+
+__global__ void feature_mask_kernel(uint64_t* __restrict__ out, int64_t N, uint32_t k0, uint32_t k1, uint32_t call, uint32_t site, uint32_t thr) {
+    // one thread per (row, 8-column group); 8 consecutive threads assemble a row's 64-bit word
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = t >> 3;
+    int c = (int)(t & 7);
+    uint32_t bits = 0;
+    if (n < N) {
+        uint64_t idx = (uint64_t)n * 8u + (uint64_t)c;
+        uint32_t w[4];
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), site, call, k0, k1, w);
+        bits = decisions8(w, thr);
+    }
+    uint64_t word = (uint64_t)bits << (8 * c);
+    // OR-reduce over the 8 threads of the row (aligned 8-lane segments)
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    if (n < N && c == 0) out[n] = word;
+}
+
+__global__ void edge_mask_kernel(uint8_t* __restrict__ out, int64_t E, int H, uint32_t k0, uint32_t k1, uint32_t call, uint32_t site, uint32_t thr) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), site, call, k0, k1, w);
+    uint32_t bits = decisions8(w, thr);
+    out[e] = (uint8_t)(bits & ((1u << H) - 1u));
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense transform: h = Xd @ Wcat, s = per-head a . h
+// block = 256 threads, tile = 128 rows of one side; thread = 8 rows x 4 columns
+// ------------------------------------------------------------------------------------------------
+constexpr int TF_TM = 128;
+constexpr int TF_XS = 68;   // padded smem row stride (floats)
+constexpr size_t TF_SMEM = (size_t)(64 * 64 + TF_TM * TF_XS + 64) * sizeof(float);
+
+// load the H per-head (64,DH) matrices of one side into Ws[k][c], c = head*DH + j
+__device__ __forceinline__ void load_wcat(float* Ws, const float* const* wptr, int H, bool transpose) {
+    const int DH = D / H;
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+        int k = idx >> 6, c = idx & 63;          // coalesced over c for H=1; 8-float runs for H=8
+        float v = __ldg(wptr[c / DH] + k * DH + (c % DH));
+        if (transpose) Ws[c * 64 + k] = v; else Ws[k * 64 + c] = v;
+    }
+}
+
+// stage-input element: ELU on load for stage > 0, then dropout keep-bit and 1/(1-p)
+__device__ __forceinline__ float4 load_input4(const float* __restrict__ X, int64_t row, int q, bool apply_elu,
+                                              const uint64_t* __restrict__ featmask, int64_t node, float scale) {
+    float4 v = ld_stream4(X + row * D + q * 4);
+    if (apply_elu) { v.x = elu(v.x); v.y = elu(v.y); v.z = elu(v.z); v.w = elu(v.w); }
+    if (featmask) {
+        uint32_t m = (uint32_t)(featmask[node] >> (q * 4)) & 0xFu;
+        v.x = (m & 1u) ? v.x * scale : 0.f;
+        v.y = (m & 2u) ? v.y * scale : 0.f;
+        v.z = (m & 4u) ? v.z * scale : 0.f;
+        v.w = (m & 8u) ? v.w * scale : 0.f;
+    }
+    return v;
+}
+
+template <int H>
+__global__ void __launch_bounds__(256) transform_fwd_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, int apply_elu,
+                                                            const uint64_t* __restrict__ featmask, float scale,
+                                                            const float* const* __restrict__ wtab, int U, int I, int tiles_u,
+                                                            float* __restrict__ h, float* __restrict__ s) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;                    // [64][64]
+    float* Xs = smem + 64 * 64;          // [128][68]
+    float* av = Xs + TF_TM * TF_XS;      // [64]
+    constexpr int DH = D / H;
+    const bool item_side = (int)blockIdx.x >= tiles_u;
+    const int tile = item_side ? blockIdx.x - tiles_u : blockIdx.x;
+    const int rows_side = item_side ? I : U;
+    const float* X = item_side ? Xi : Xu;
+    const int64_t node0 = (item_side ? (int64_t)U : 0) + (int64_t)tile * TF_TM;
+    const int row0 = tile * TF_TM;
+    const int nrows = min(TF_TM, rows_side - row0);
+
+    load_wcat(Ws, wtab + (item_side ? H : 0), H, false);
+    if (threadIdx.x < 64) {
+        int k = threadIdx.x / DH, j = threadIdx.x % DH;
+        av[threadIdx.x] = __ldg(wtab[2 * H + k] + (item_side ? DH : 0) + j);
+    }
+    for (int idx = threadIdx.x; idx < TF_TM * 16; idx += 256) {
+        int r = idx >> 4, q = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows) v = load_input4(X, row0 + r, q, apply_elu != 0, featmask, node0 + r, scale);
+        *reinterpret_cast<float4*>(Xs + r * TF_XS + q * 4) = v;
+    }
+    __syncthreads();
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+#pragma unroll 4
+    for (int k4 = 0; k4 < 16; ++k4) {
+        float4 w0 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + 0) * 64 + tx * 4);
+        float4 w1 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + 1) * 64 + tx * 4);
+        float4 w2 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + 2) * 64 + tx * 4);
+        float4 w3 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + 3) * 64 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 x = *reinterpret_cast<const float4*>(Xs + (ty + 16 * i) * TF_XS + k4 * 4);
+            acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
+            acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
+            acc[i][2] = fmaf(x.y, w1.z, acc[i][2]); acc[i][3] = fmaf(x.y, w1.w, acc[i][3]);
+            acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]);
+            acc[i][2] = fmaf(x.z, w2.z, acc[i][2]); acc[i][3] = fmaf(x.z, w2.w, acc[i][3]);
+            acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(x.w, w3.z, acc[i][2]); acc[i][3] = fmaf(x.w, w3.w, acc[i][3]);
+        }
+    }
+    const float4 a4 = *reinterpret_cast<const float4*>(av + tx * 4);
+    const unsigned gm = group_mask();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int r = ty + 16 * i;
+        float part = acc[i][0] * a4.x + acc[i][1] * a4.y + acc[i][2] * a4.z + acc[i][3] * a4.w;
+        part = head_reduce<H>(part, gm);     // every thread of the warp executes the shuffles
+        if (r < nrows) {
+            int64_t node = node0 + r;
+            st_stream4(h + node * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            if (H == 8) { if ((tx & 1) == 0) s[node * 8 + (tx >> 1)] = part; }
+            else        { if (tx == 0) s[node] = part; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused edge softmax + aggregation.  One 16-lane group per task (a row, or a <=128-edge chunk of a
+// long row); lane l owns columns 4l..4l+3 (16-byte vector loads of the gathered rows).
+// ------------------------------------------------------------------------------------------------
+template <int H>
+__device__ __forceinline__ int lane_head(int lane16) { return H == 8 ? (lane16 >> 1) : 0; }
+
+// combine the partials of a long row: called by every group that finishes a chunk; returns true for
+// the group that arrived last (which then holds the totals, summed in slot order -> deterministic)
+template <int H, int NSUM>
+__device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
+                                                 float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
+    const int head = lane_head<H>(lane16);
+    const int first = long_first_slot[lid];
+    const int nslots = long_first_slot[lid + 1] - first;
+    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
+    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
+    // per-head scalars: NSUM values per head, stored at [64 + j*H... ]: slot has 8 floats of room => NSUM*H <= 8
+    if ((H == 8 && (lane16 & 1) == 0) || (H == 1 && lane16 == 0)) {
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
+    }
+    __threadfence();
+    __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
+    int old = 0;
+    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
+    old = __shfl_sync(gm, old, 0, 16);
+    if (old != nslots - 1) return false;
+    __threadfence();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ts[NSUM];
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
+    for (int c = 0; c < nslots; ++c) {
+        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
+        float4 v = ld_cg4(sl + lane16 * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
+    }
+    acc = t;
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
+    if (lane16 == 0) long_counter[lid] = 0;    // re-arm for the next launch
+    return true;
+}
+
+template <int H, bool DROP>
+__global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ adj_ptr,
+                                                            const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
+                                                            const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
+                                                            const float* __restrict__ h, const float* __restrict__ s,
+                                                            const uint8_t* __restrict__ edgemask, float scale,
+                                                            float* __restrict__ Z, float* __restrict__ norm) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (t >= T) return;                                  // whole 16-lane groups exit together
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int head = lane_head<H>(lane16);
+    const int4 tk = __ldg(tasks + t);
+    const int node = tk.x, beg = tk.y, end = tk.z, lid = tk.w;
+    const float sn = __ldg(s + (int64_t)node * H + head);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rs = 0.f;
+    for (int base = beg; base < end; base += 16) {
+        const int idx = base + lane16;
+        int m_l = 0;
+        unsigned mk_l = 0xFFu;
+        if (idx < end) {
+            m_l = ld_stream_i32(adj_idx + idx);
+            if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + idx)];
+        }
+        const int cnt = min(16, end - base);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const int m = __shfl_sync(gm, m_l, j, 16);
+            const float sm = __ldg(s + (int64_t)m * H + head);
+            const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+            const float w = edge_weight(sn + sm);
+            rs += w;
+            float wd = w;
+            if (DROP) {
+                const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
+                wd = ((mk >> head) & 1u) ? w * scale : 0.f;
+            }
+            acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
+            acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
+        }
+    }
+    if (lid >= 0) {
+        float sums[1] = {rs};
+        const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
+        if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        rs = sums[0];
+    }
+    // epilogue: Z = h + agg / norm, NaN -> 0 for isolated nodes (SPUIGACF.py:383,388-390)
+    const float inv = rs != 0.f ? 1.0f / rs : 0.f;
+    const float4 hn = ld_stream4(h + (int64_t)node * D + lane16 * 4);
+    st_stream4(Z + (int64_t)node * D + lane16 * 4,
+               make_float4(fmaf(acc.x, inv, hn.x), fmaf(acc.y, inv, hn.y), fmaf(acc.z, inv, hn.z), fmaf(acc.w, inv, hn.w)));
+    if (H == 8) { if ((lane16 & 1) == 0) norm[(int64_t)node * 8 + head] = rs; }
+    else        { if (lane16 == 0) norm[node] = rs; }
+}
+
+}  // namespace ngacf
+
+using namespace ngacf;
+
+extern "C" int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream) {
+    NGACF_REQUIRE(feat && N >= 0, "feature_mask: bad args");
+    if (N == 0) return NGACF_OK;
+    uint32_t thr = keep_threshold(droprate);
+    feature_mask_kernel<<<ceil_div(N * 8, 256), 256, 0, (cudaStream_t)stream>>>(feat, N, (uint32_t)seed, (uint32_t)(seed >> 32), call,
+                                                                                 stage * 2 + 0, thr);
+    return check_launch("feature_mask");
+}
+
+extern "C" int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream) {
+    NGACF_REQUIRE(edge && E >= 0 && (H == 1 || H == 8), "edge_mask: bad args");
+    if (E == 0) return NGACF_OK;
+    uint32_t thr = keep_threshold(droprate);
+    edge_mask_kernel<<<ceil_div(E, 256), 256, 0, (cudaStream_t)stream>>>(edge, E, H, (uint32_t)seed, (uint32_t)(seed >> 32), call,
+                                                                          stage * 2 + 1, thr);
+    return check_launch("edge_mask");
+}
+
+extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
+                                   const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream) {
+    NGACF_REQUIRE(Xu && Xi && wtab && h && s && U > 0 && I > 0, "transform_fwd: null/empty argument");
+    NGACF_REQUIRE(H == 1 || H == 8, "transform_fwd: H must be 1 or 8 (got %d)", H);
+    const int tiles_u = ceil_div(U, TF_TM), tiles_i = ceil_div(I, TF_TM);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(transform_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+        cudaFuncSetAttribute(transform_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+        attr_done = true;
+    }
+    if (H == 8)
+        transform_fwd_kernel<8><<<tiles_u + tiles_i, 256, TF_SMEM, (cudaStream_t)stream>>>(Xu, Xi, apply_elu, featmask, scale, wtab, U, I, tiles_u, h, s);
+    else
+        transform_fwd_kernel<1><<<tiles_u + tiles_i, 256, TF_SMEM, (cudaStream_t)stream>>>(Xu, Xi, apply_elu, featmask, scale, wtab, U, I, tiles_u, h, s);
+    return check_launch("transform_fwd");
+}
+
+extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
+                                   const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* h, const float* s,
+                                   int32_t H, const uint8_t* edgemask, float scale, float* Z, float* norm, void* stream) {
+    NGACF_REQUIRE(tasks && adj_ptr && adj_idx && h && s && Z && norm && T > 0, "aggregate_fwd: null/empty argument");
+    NGACF_REQUIRE(H == 1 || H == 8, "aggregate_fwd: H must be 1 or 8 (got %d)", H);
+    NGACF_REQUIRE(!edgemask || adj_eid, "aggregate_fwd: edge dropout needs adj_eid");
+    const int blocks = ceil_div((int64_t)T * 16, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int4* tk = reinterpret_cast<const int4*>(tasks);
+#define LAUNCH(HH, DR) aggregate_fwd_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
+    if (H == 8) { if (edgemask) LAUNCH(8, true); else LAUNCH(8, false); }
+    else        { if (edgemask) LAUNCH(1, true); else LAUNCH(1, false); }
+#undef LAUNCH
+    return check_launch("aggregate_fwd");
+}

@@ -1,0 +1,271 @@
+// Pair scoring + BPR loss + gradient scatter, table-driven Adam, PairSampling sampler.
+// Reference: graphattention/SPUIGACF.py:49-52, graphattention/BPRLoss.py:8-9,
+// train_eval_Gowalla.py:117-138, data/loadGowalla.py:63-77, run_Gowalla.py:114.
+#include "common.cuh"
+
+namespace ngacf {
+
+// fixed summation tree of the 64-wide dot product (oracle/port.py:dot64_tree): products rounded to
+// fp32 (no FMA contraction), adjacent pairs first, then lanes 1,2,4,8.
+__device__ __forceinline__ float dot64_tree(float4 a, float4 b, unsigned gm) {
+    float p0 = __fmul_rn(a.x, b.x), p1 = __fmul_rn(a.y, b.y), p2 = __fmul_rn(a.z, b.z), p3 = __fmul_rn(a.w, b.w);
+    float v = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 1, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 2, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 4, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 8, 16));
+    return v;
+}
+
+__device__ __forceinline__ float4 elu4(float4 z) { return make_float4(elu(z.x), elu(z.y), elu(z.z), elu(z.w)); }
+
+__global__ void __launch_bounds__(256) score_pairs_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
+                                                          const int64_t* __restrict__ items, int B, float* __restrict__ scores) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (b >= B) return;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int64_t u = users[b], it = items[b] + U;
+    const float4 fu = elu4(ld_gather4(Z + u * D + lane16 * 4));
+    const float4 fi = elu4(ld_gather4(Z + it * D + lane16 * 4));
+    const float sc = dot64_tree(fu, fi, gm);
+    if (lane16 == 0) scores[b] = sc;
+}
+
+__global__ void final_features_kernel(const float* __restrict__ Z, int64_t n4, float* __restrict__ F) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    st_stream4(F + i * 4, elu4(ld_stream4(Z + i * 4)));
+}
+
+// entry e in [0,2B): e<B -> (row = users[e], other = U+items[e]); else (row = U+items[e-B], other = users[e-B]).
+// The group of the FIRST entry of each distinct row sums all entries of that row in entry order and
+// stores G[row] with a plain store: deterministic, no atomics, no sort.
+__global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
+                                                              const int64_t* __restrict__ items, const float* __restrict__ dscore, int B,
+                                                              float* __restrict__ G) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (e >= 2 * B) return;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int64_t row = e < B ? users[e] : items[e - B] + U;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool user_row = e < B;
+    // only entries of the same kind can match (user rows < U <= item rows)
+    const int64_t* keys = user_row ? users : items;
+    const int64_t key = user_row ? row : row - U;
+    for (int base = 0; base < B; base += 16) {
+        const int j = base + lane16;
+        const bool match = j < B && keys[j] == key;
+        unsigned bal = __ballot_sync(gm, match) >> (threadIdx.x & 16);   // this group's 16 bits
+        bal &= 0xFFFFu;
+        while (bal) {
+            const int jj = base + __ffs(bal) - 1;
+            bal &= bal - 1;
+            const int eb = user_row ? e : e - B;
+            if (jj < eb) return;                       // an earlier entry owns this row (group-uniform)
+            const int64_t other = user_row ? items[jj] + U : users[jj];
+            const float c = dscore[jj];
+            const float4 fo = elu4(ld_gather4(Z + other * D + lane16 * 4));
+            acc.x = fmaf(c, fo.x, acc.x); acc.y = fmaf(c, fo.y, acc.y); acc.z = fmaf(c, fo.z, acc.z); acc.w = fmaf(c, fo.w, acc.w);
+        }
+    }
+    const float4 z = ld_gather4(Z + row * D + lane16 * 4);
+    *reinterpret_cast<float4*>(G + row * D + lane16 * 4) =
+        make_float4(acc.x * elu_grad(z.x), acc.y * elu_grad(z.y), acc.z * elu_grad(z.z), acc.w * elu_grad(z.w));
+}
+
+// single-block loss: deterministic tree reduction
+__global__ void __launch_bounds__(1024) bpr_loss_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int B, float gscale,
+                                                        float* __restrict__ loss, float* __restrict__ dpos, float* __restrict__ dneg) {
+    __shared__ float red[32];
+    float local = 0.f;
+    const float invB = 1.0f / (float)B;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float x = pos[b] - neg[b];
+        // -log(sigmoid(x)) = softplus(-x), stable form (BPRLoss.py:9 is the naive form)
+        local += fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+        const float sg = 1.0f / (1.0f + expf(x));          // sigmoid(-x)
+        const float d = -sg * invB * gscale;
+        if (dpos) dpos[b] = d;
+        if (dneg) dneg[b] = -d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0 && loss) *loss = v * invB;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam
+// ------------------------------------------------------------------------------------------------
+struct AdamEntry { float* p; const float* g; float* m; float* v; int64_t numel; };
+constexpr int ADAM_MAX_TENSORS = 64;
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamEntry* __restrict__ tab, int n_tensors, float lr_over_bc1, float inv_sqrt_bc2,
+                                                   const double* __restrict__ state, float beta1, float beta2, float eps, float wd) {
+    if (state) { lr_over_bc1 = (float)state[1]; inv_sqrt_bc2 = (float)state[2]; }
+    __shared__ AdamEntry ent[ADAM_MAX_TENSORS];
+    __shared__ int64_t pref[ADAM_MAX_TENSORS + 1];   // prefix in float4 chunks
+    if (threadIdx.x < n_tensors) ent[threadIdx.x] = tab[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int t = 0; t < n_tensors; ++t) { pref[t] = run; run += (ent[t].numel + 3) / 4; }
+        pref[n_tensors] = run;
+    }
+    __syncthreads();
+    const int64_t total = pref[n_tensors];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_tensors - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (pref[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        const AdamEntry& en = ent[lo];
+        const int64_t off = (c - pref[lo]) * 4;
+        const int cnt = (int)min((int64_t)4, en.numel - off);
+        float pv[4], gv[4], mv[4], vv[4];
+        if (cnt == 4) {
+            float4 a = *reinterpret_cast<const float4*>(en.p + off), b = *reinterpret_cast<const float4*>(en.g + off);
+            float4 mm = *reinterpret_cast<const float4*>(en.m + off), v2 = *reinterpret_cast<const float4*>(en.v + off);
+            pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+            mv[0] = mm.x; mv[1] = mm.y; mv[2] = mm.z; mv[3] = mm.w; vv[0] = v2.x; vv[1] = v2.y; vv[2] = v2.z; vv[3] = v2.w;
+        } else {
+            for (int k = 0; k < cnt; ++k) { pv[k] = en.p[off + k]; gv[k] = en.g[off + k]; mv[k] = en.m[off + k]; vv[k] = en.v[off + k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                const float g = fmaf(wd, pv[k], gv[k]);                 // L2 weight decay added to the gradient
+                mv[k] = fmaf(beta1, mv[k], (1.f - beta1) * g);
+                vv[k] = fmaf(beta2, vv[k], (1.f - beta2) * g * g);
+                const float denom = sqrtf(vv[k]) * inv_sqrt_bc2 + eps;
+                pv[k] = pv[k] - lr_over_bc1 * (mv[k] / denom);
+            }
+        }
+        if (cnt == 4) {
+            *reinterpret_cast<float4*>(en.p + off) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+            *reinterpret_cast<float4*>(en.m + off) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+            *reinterpret_cast<float4*>(en.v + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        } else {
+            for (int k = 0; k < cnt; ++k) { en.p[off + k] = pv[k]; en.m[off + k] = mv[k]; en.v[off + k] = vv[k]; }
+        }
+    }
+}
+
+// device-resident step counter variant (CUDA-graph replayable): state = double[4] {step, lr/bc1, 1/sqrt(bc2), -}
+__global__ void adam_tick_kernel(double* state, double lr, double beta1, double beta2) {
+    const double t = state[0] + 1.0;
+    state[0] = t;
+    state[1] = lr / (1.0 - pow(beta1, t));
+    state[2] = 1.0 / sqrt(1.0 - pow(beta2, t));
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairSampling sampler (oracle/port.py:sample_pairs)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t SAMPLER_TAG = 0x5A17u;
+
+__global__ void sample_pairs_kernel(const int* __restrict__ rows_user, const int* __restrict__ train_ptr, const int* __restrict__ train_items,
+                                    const int* __restrict__ train_rank, const int* __restrict__ pool, int P, int64_t row_begin, int64_t n,
+                                    uint32_t k0, uint32_t k1, uint32_t epoch, int64_t* __restrict__ users, int64_t* __restrict__ pos,
+                                    int64_t* __restrict__ neg) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint64_t r = (uint64_t)(row_begin + b);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), epoch, SAMPLER_TAG, k0, k1, w);
+    const int u = rows_user[row_begin + b];
+    const int beg = train_ptr[u], deg = train_ptr[u + 1] - beg;
+    users[b] = u;
+    const uint32_t pidx = __umulhi(w[0], (uint32_t)deg);
+    pos[b] = train_items[beg + (int)pidx];
+    const int nneg = P - deg;
+    if (nneg <= 0) { neg[b] = -1; return; }
+    const int k = (int)__umulhi(w[1], (uint32_t)nneg);
+    int lo = 0, hi = deg;                      // smallest j with rank[j]-j > k
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (train_rank[beg + mid] - mid <= k) lo = mid + 1; else hi = mid;
+    }
+    neg[b] = pool[k + lo];
+}
+
+}  // namespace ngacf
+
+using namespace ngacf;
+
+extern "C" int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream) {
+    NGACF_REQUIRE(Z && users && items && scores && B >= 0, "score_pairs: null argument");
+    if (B == 0) return NGACF_OK;
+    score_pairs_kernel<<<ceil_div((int64_t)B * 16, 256), 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, B, scores);
+    return check_launch("score_pairs");
+}
+
+extern "C" int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream) {
+    NGACF_REQUIRE(Z && F && N >= 0, "final_features: null argument");
+    if (N == 0) return NGACF_OK;
+    final_features_kernel<<<ceil_div(N * 16, 256), 256, 0, (cudaStream_t)stream>>>(Z, N * 16, F);
+    return check_launch("final_features");
+}
+
+extern "C" int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const int64_t* items, const float* dscore, int32_t B,
+                                     float* G, void* stream) {
+    NGACF_REQUIRE(Z && users && items && dscore && G && B >= 0, "score_pairs_bwd: null argument");
+    if (B == 0) return NGACF_OK;
+    score_pairs_bwd_kernel<<<ceil_div((int64_t)B * 2 * 16, 256), 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, dscore, B, G);
+    return check_launch("score_pairs_bwd");
+}
+
+extern "C" int ngacf_bpr_loss(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg, void* stream) {
+    NGACF_REQUIRE(pos && neg && B > 0, "bpr_loss: null/empty argument");
+    bpr_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos, neg, B, gscale, loss, dpos, dneg);
+    return check_launch("bpr_loss");
+}
+
+extern "C" int ngacf_adam_step(const uint64_t* tab, int32_t n_tensors, int64_t total_numel, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int64_t step_host, void* stream) {
+    NGACF_REQUIRE(tab && n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS && step_host >= 1, "adam_step: bad table/step");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step_host);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step_host);
+    const float lr_over_bc1 = (float)((double)lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    int64_t chunks = total_numel / 4 + n_tensors;
+    int blocks = ceil_div(chunks, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamEntry*>(tab), n_tensors, lr_over_bc1, inv_sqrt_bc2,
+                                                          nullptr, beta1, beta2, eps, weight_decay);
+    return check_launch("adam_step");
+}
+
+extern "C" int ngacf_adam_step_dev(const uint64_t* tab, int32_t n_tensors, int64_t total_numel, float lr, float beta1, float beta2, float eps,
+                                   float weight_decay, double* state, void* stream) {
+    NGACF_REQUIRE(tab && state && n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "adam_step_dev: bad table/state");
+    int64_t chunks = total_numel / 4 + n_tensors;
+    int blocks = ceil_div(chunks, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, (double)lr, (double)beta1, (double)beta2);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamEntry*>(tab), n_tensors, 0.f, 0.f, state, beta1, beta2,
+                                                          eps, weight_decay);
+    return check_launch("adam_step_dev");
+}
+
+extern "C" int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr, const int32_t* train_items,
+                                  const int32_t* train_rank, const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end,
+                                  uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream) {
+    NGACF_REQUIRE(train_rows_user && train_ptr && train_items && train_rank && pool && users && pos && neg, "sample_pairs: null argument");
+    NGACF_REQUIRE(row_end >= row_begin && P > 0, "sample_pairs: bad range");
+    const int64_t n = row_end - row_begin;
+    if (n == 0) return NGACF_OK;
+    sample_pairs_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(train_rows_user, train_ptr, train_items, train_rank, pool, P,
+                                                                             row_begin, n, (uint32_t)seed, (uint32_t)(seed >> 32), epoch,
+                                                                             users, pos, neg);
+    return check_launch("sample_pairs");
+}

@@ -1,0 +1,76 @@
+"""AllNeg evaluation on the GPU (train_eval_Gowalla.py:274-354 + :356-429 of the reference):
+one propagation, fused user x item scoring + masking + top-20 per user, hit lists and metric sums on
+the device.  Only top-K lists / 16 sums ever leave the GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .data import Interactions
+
+KS = [1, 5, 10, 20]
+K = 20
+
+
+class AllNegEvaluator:
+    def __init__(self, inter: Interactions, mode: str = "auto"):
+        """mode: 'exact' (fp32 CUDA cores, bit-reproducible), 'tc' (tcgen05 + exact re-score), 'auto' = tc when available."""
+        self.inter = inter
+        self.mode = mode
+        dev = inter.device
+        n = inter.eval_users.numel()
+        self.top_ids = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
+        self.top_scores = torch.empty((max(n, 1), K), dtype=torch.float32, device=dev)
+        self.hits = torch.empty((max(n, 1), K), dtype=torch.uint8, device=dev)
+        self.sums = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.metric_ws = torch.empty(max(n, 1) * 16, dtype=torch.float64, device=dev)
+        self.F = None
+        self._tc_ws = None
+        self.fallback = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+
+    def _use_tc(self):
+        from . import _lib
+        if self.mode == "exact":
+            return False
+        have = hasattr(_lib.load(), "ngacf_score_topk_tc")
+        if self.mode == "tc" and not have:
+            raise _lib.NgacfError("ngacf_score_topk_tc is not built")
+        return have
+
+    def rank(self, Z: torch.Tensor):
+        """Z: pre-ELU last-stage output (N,64).  Fills top_ids/top_scores for inter.eval_users."""
+        it = self.inter
+        if self.F is None or self.F.shape != Z.shape:
+            self.F = torch.empty_like(Z)
+        ops.final_features(Z, self.F)
+        n = it.eval_users.numel()
+        if n == 0:
+            return
+        if self._use_tc():
+            if self._tc_ws is None:
+                self._tc_ws = torch.empty(ops.score_topk_tc_workspace_bytes(it.I, n), dtype=torch.uint8, device=Z.device)
+            ops.score_topk_tc(self.F, it.U, it.I, it.eval_users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws)
+            bad = torch.nonzero(self.fallback[:n]).flatten()
+            if bad.numel():       # rows whose error guard failed: recompute exactly
+                users = it.eval_users[bad].contiguous()
+                ids = torch.empty((bad.numel(), K), dtype=torch.int32, device=Z.device)
+                sc = torch.empty((bad.numel(), K), dtype=torch.float32, device=Z.device)
+                ops.score_topk_exact(self.F, it.U, it.I, users, it, ids, sc)
+                self.top_ids[bad] = ids
+                self.top_scores[bad] = sc
+            self.n_fallback = int(bad.numel())
+        else:
+            ops.score_topk_exact(self.F, it.U, it.I, it.eval_users, it, self.top_ids, self.top_scores)
+            self.n_fallback = 0
+
+    def metrics(self):
+        """dict in the reference's format (train_eval_Gowalla.py:277-278,354)."""
+        it = self.inter
+        ops.eval_metrics(self.top_ids, it.eval_users, it, self.hits, self.sums, self.metric_ws)
+        s = self.sums.cpu().numpy() / max(it.n_train_users, 1)      # divisor = users with train data (:283)
+        return {"precision": s[0:4].copy(), "recall": s[4:8].copy(), "ndcg": s[8:12].copy(), "hit_ratio": s[12:16].copy(), "auc": 0.0}
+
+    def __call__(self, Z):
+        self.rank(Z)
+        return self.metrics()

@@ -1,0 +1,119 @@
+"""Thin tensor-level wrappers over the C-ABI (include/ngacf_b200.h).  Each function only validates
+devices/dtypes, passes raw pointers + the current CUDA stream, and never allocates or synchronises
+(so everything here can be captured in a CUDA graph).  No CPU path exists."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .graph import BipartiteGraph
+
+STAGES = ((8, 8), (1, 64))   # SPUIGACF: eight 64->8 heads, then out_att 64->64 (SPUIGACF.py:17-22,191-205)
+D = 64
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.NgacfError("%s must be a contiguous float32 tensor" % name)
+    _lib.require_cuda(t)
+
+
+def pointer_table(tensors):
+    """Device array of raw pointers (wtab / gtab of the header)."""
+    dev = tensors[0].device
+    for t in tensors:
+        _f32(t, "table entry")
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(dev, non_blocking=False)
+
+
+def feature_mask(out, seed, call, stage, droprate):
+    _lib.call("ngacf_feature_mask", _p(out), out.numel(), int(seed), int(call), int(stage), float(droprate), _s())
+
+
+def edge_mask(out, H, seed, call, stage, droprate):
+    _lib.call("ngacf_edge_mask", _p(out), out.numel(), int(H), int(seed), int(call), int(stage), float(droprate), _s())
+
+
+def transform_fwd(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s):
+    _lib.call("ngacf_transform_fwd", _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab), H, U, I, _p(h), _p(s), _s())
+
+
+def aggregate_fwd(g: BipartiteGraph, scratch, counter, h, s, H, edgemask, scale, Z, norm):
+    _lib.call("ngacf_aggregate_fwd", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid), _p(g.long_first_slot),
+              _p(counter), _p(scratch), _p(h), _p(s), H, _p(edgemask), float(scale), _p(Z), _p(norm), _s())
+
+
+def score_pairs(Z, U, users, items, out):
+    _lib.call("ngacf_score_pairs", _p(Z), U, _p(users), _p(items), users.numel(), _p(out), _s())
+
+
+def score_pairs_bwd(Z, U, users, items, dscore, G):
+    _lib.call("ngacf_score_pairs_bwd", _p(Z), U, _p(users), _p(items), _p(dscore), users.numel(), _p(G), _s())
+
+
+def final_features(Z, F):
+    _lib.call("ngacf_final_features", _p(Z), Z.shape[0], _p(F), _s())
+
+
+def bpr_loss(pos, neg, gscale, loss, dpos, dneg):
+    _lib.call("ngacf_bpr_loss", _p(pos), _p(neg), pos.numel(), float(gscale), _p(loss), _p(dpos), _p(dneg), _s())
+
+
+def stage_bwd_prep(G, Z, h, norm, H, Ghat, dN):
+    _lib.call("ngacf_stage_bwd_prep", _p(G), _p(Z), _p(h), _p(norm), H, G.shape[0], _p(Ghat), _p(dN), _s())
+
+
+def stage_bwd_edges(mode, g: BipartiteGraph, scratch, counter, G, Ghat, dN, h, s, H, edgemask, scale, wtab, ds_store, dh, dS):
+    t0, t1 = (0, g.T_users) if mode == 0 else (g.T_users, g.T)
+    _lib.call("ngacf_stage_bwd_edges", mode, _p(g.tasks), t0, t1, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid),
+              _p(g.long_first_slot), _p(counter), _p(scratch), _p(G), _p(Ghat), _p(dN), _p(h), _p(s), H, _p(edgemask),
+              float(scale), _p(wtab), g.U, _p(ds_store), _p(dh), _p(dS), _s())
+
+
+def transform_bwd_workspace_bytes(U, I):
+    return int(_lib.load().ngacf_transform_bwd_workspace_bytes(U, I))
+
+
+def transform_bwd(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, gtab, H, U, I, dXu, dXi, accumulate_dx, accumulate_dw, ws):
+    _lib.call("ngacf_transform_bwd", _p(dh), _p(dS), _p(h), _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab),
+              _p(gtab), H, U, I, _p(dXu), _p(dXi), int(accumulate_dx), int(accumulate_dw), _p(ws), ws.numel() * ws.element_size(), _s())
+
+
+def adam_step(tab, n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, step):
+    _lib.call("ngacf_adam_step", _p(tab), n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, int(step), _s())
+
+
+def adam_step_dev(tab, n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, state):
+    _lib.call("ngacf_adam_step_dev", _p(tab), n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, _p(state), _s())
+
+
+def sample_pairs(inter, row_begin, row_end, seed, epoch, users, pos, neg):
+    _lib.call("ngacf_sample_pairs", _p(inter.train_rows_user), _p(inter.train_ptr), _p(inter.train_items), _p(inter.train_rank),
+              _p(inter.pool), inter.pool.numel(), int(row_begin), int(row_end), int(seed), int(epoch), _p(users), _p(pos), _p(neg), _s())
+
+
+def score_topk_exact(F, U, I, users, inter, top_ids, top_scores):
+    _lib.call("ngacf_score_topk_exact", _p(F), U, I, _p(users), users.numel(), _p(inter.train_ptr), _p(inter.train_items),
+              _p(inter.in_pool), _p(top_ids), _p(top_scores), _s())
+
+
+def score_topk_tc_workspace_bytes(I, n_users):
+    return int(_lib.load().ngacf_score_topk_tc_workspace_bytes(I, n_users))
+
+
+def score_topk_tc(F, U, I, users, inter, top_ids, top_scores, fallback, ws):
+    _lib.call("ngacf_score_topk_tc", _p(F), U, I, _p(users), users.numel(), _p(inter.train_ptr), _p(inter.train_items),
+              _p(inter.in_pool), _p(top_ids), _p(top_scores), _p(fallback), _p(ws), ws.numel() * ws.element_size(), _s())
+
+
+def eval_metrics(top_ids, users, inter, hits, sums, ws):
+    _lib.call("ngacf_eval_metrics", _p(top_ids), _p(users), users.numel(), _p(inter.test_ptr), _p(inter.test_items), _p(hits),
+              _p(sums), _p(ws), ws.numel() * ws.element_size(), _s())

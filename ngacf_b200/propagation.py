@@ -1,0 +1,197 @@
+"""Full-graph SpUIGAT propagation on the GPU: forward (SPUIGACF.py:30-39,207-215,340-400) and the
+closed-form backward over persistent HBM buffers, plus the autograd bridge used by the
+drop-in ``SPUIGACF.forward``.
+
+Layout in HBM per propagation (N = U+I nodes, users first; every row is 64 fp32 = 256 B):
+  stage k:  h_k (N,64)  transformed features      s_k (N,H)  rank-1 logit scalars (p|q)
+            Z_k (N,64)  pre-ELU stage output       norm_k (N,H) attention row/col sums (R|C)
+            featmask_k uint64[N], edgemask_k uint8[E]   dropout keep bits (only when dropout is on)
+  backward: G (N,64) x2 ping-pong, Ghat (N,64), dh (N,64), dN/dS (N,8), ds_store (E,8)
+The stage input is never materialised: stage 0 reads the embedding tables in place, stage k>0 reads
+Z_{k-1} and applies ELU + dropout on load.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .graph import BipartiteGraph
+from .ops import D, STAGES
+
+
+class Propagation:
+    def __init__(self, graph: BipartiteGraph, stages=STAGES):
+        self.g = graph
+        self.stages = tuple(stages)
+        dev, N, E = graph.device, graph.N, graph.E
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.h = [torch.empty((N, D), **f32) for _ in self.stages]
+        self.Z = [torch.empty((N, D), **f32) for _ in self.stages]
+        self.s = [torch.empty((N, H), **f32) for H, _ in self.stages]
+        self.norm = [torch.empty((N, H), **f32) for H, _ in self.stages]
+        self.featmask: List[Optional[torch.Tensor]] = [None] * len(self.stages)
+        self.edgemask: List[Optional[torch.Tensor]] = [None] * len(self.stages)
+        self._own_masks = None
+        self.scale = 1.0
+        self.scratch, self.counter = (torch.empty(max(graph.S, 1) * 72, **f32),
+                                      torch.zeros(max(graph.L, 1), dtype=torch.int32, device=dev))
+        self._bwd = None
+
+    # ------------------------------------------------------------------------------------------
+    def _mask_buffers(self):
+        if self._own_masks is None:
+            dev = self.g.device
+            self._own_masks = ([torch.empty(self.g.N, dtype=torch.int64, device=dev) for _ in self.stages],
+                               [torch.empty(max(self.g.E, 1), dtype=torch.uint8, device=dev) for _ in self.stages])
+        return self._own_masks
+
+    def set_dropout(self, droprate: float, seed: int = 0, call: int = 0, injected=None):
+        """droprate 0 -> no masks.  injected = dict(feat=[uint64/int64 [N]]*S, edge=[uint8 [E]]*S) device tensors
+        (parity tests inject masks captured from the reference); else Philox(seed, call)."""
+        S = len(self.stages)
+        if droprate <= 0.0:
+            self.featmask, self.edgemask, self.scale = [None] * S, [None] * S, 1.0
+            return
+        self.scale = 1.0 / (1.0 - droprate)
+        if injected is not None:
+            self.featmask = [m.contiguous() for m in injected["feat"]]
+            self.edgemask = [m.contiguous() for m in injected["edge"]]
+            return
+        fm, em = self._mask_buffers()
+        for k, (H, _) in enumerate(self.stages):
+            ops.feature_mask(fm[k], seed, call, k, droprate)
+            ops.edge_mask(em[k][:self.g.E], H, seed, call, k, droprate)
+        self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor]) -> torch.Tensor:
+        g = self.g
+        Xu, Xi, act = uEmbd, iEmbd, 0
+        for k, (H, _) in enumerate(self.stages):
+            ops.transform_fwd(Xu, Xi, act, self.featmask[k], self.scale, wtabs[k], H, g.U, g.I, self.h[k], self.s[k])
+            ops.aggregate_fwd(g, self.scratch, self.counter, self.h[k], self.s[k], H, self.edgemask[k], self.scale,
+                              self.Z[k], self.norm[k])
+            Xu, Xi, act = self.Z[k], self.Z[k][g.U:], 1
+        return self.Z[-1]
+
+    # ------------------------------------------------------------------------------------------
+    def _bwd_buffers(self):
+        if self._bwd is None:
+            dev, N, E = self.g.device, self.g.N, self.g.E
+            f32 = dict(dtype=torch.float32, device=dev)
+            self._bwd = dict(G=[torch.empty((N, D), **f32), torch.empty((N, D), **f32)], Ghat=torch.empty((N, D), **f32),
+                             dh=torch.empty((N, D), **f32), dN=torch.empty((N, 8), **f32), dS=torch.empty((N, 8), **f32),
+                             ds=torch.empty(max(E, 1) * 8, **f32),
+                             ws=torch.empty(ops.transform_bwd_workspace_bytes(self.g.U, self.g.I) // 4, **f32))
+        return self._bwd
+
+    def grad_in(self) -> torch.Tensor:
+        """(N,64) buffer the caller fills with dL/dZ_last (zero-filled by the caller as needed)."""
+        return self._bwd_buffers()["G"][0]
+
+    def backward(self, G_last: torch.Tensor, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate: bool):
+        """G_last = dL/dZ_last (N,64).  Writes (accumulate=False) or adds (True) every parameter gradient:
+        embedding grads into dU/dI, attention grads through the pointer tables gtabs[k]."""
+        g = self.g
+        b = self._bwd_buffers()
+        G = G_last
+        for k in range(len(self.stages) - 1, -1, -1):
+            H, _ = self.stages[k]
+            ops.stage_bwd_prep(G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"])
+            for mode in (0, 1):
+                ops.stage_bwd_edges(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
+                                    self.edgemask[k], self.scale, wtabs[k], b["ds"], b["dh"], b["dS"])
+            if k > 0:
+                Gprev = b["G"][1] if G is not b["G"][1] else b["G"][0]
+                ops.transform_bwd(b["dh"], b["dS"], self.h[k], self.Z[k - 1], self.Z[k - 1][g.U:], 1, self.featmask[k], self.scale,
+                                  wtabs[k], gtabs[k], H, g.U, g.I, Gprev, Gprev[g.U:], 0, int(accumulate), b["ws"])
+                G = Gprev
+            else:
+                ops.transform_bwd(b["dh"], b["dS"], self.h[k], uEmbd, iEmbd, 0, self.featmask[k], self.scale, wtabs[k], gtabs[k],
+                                  H, g.U, g.I, dU, dI, int(accumulate), int(accumulate), b["ws"])
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd bridge (generic path: model(u, i, adj) -> scores, loss.backward())
+# ------------------------------------------------------------------------------------------------
+
+
+def stage_param_lists(stage_params, stages=STAGES):
+    """flat [Wu heads | Wi heads | a heads] per stage -> list of lists."""
+    out, i = [], 0
+    for H, _ in stages:
+        out.append(list(stage_params[i:i + 3 * H]))
+        i += 3 * H
+    return out
+
+
+class PropagateFn(torch.autograd.Function):
+    """Z_last = propagate(uEmbd, iEmbd, attention params).  Fresh buffers per call (the two forwards of a
+    PairSampling step are alive together until loss.backward)."""
+
+    @staticmethod
+    def forward(ctx, graph, droprate, seed, call, injected, uEmbd, iEmbd, *stage_params):
+        prop = Propagation(graph)
+        prop.set_dropout(droprate, seed, call, injected)
+        per_stage = stage_param_lists([p.detach() for p in stage_params])
+        wtabs = [ops.pointer_table(ps) for ps in per_stage]
+        Z = prop.forward(uEmbd.detach(), iEmbd.detach(), wtabs)
+        ctx.prop, ctx.wtabs = prop, wtabs
+        ctx.shapes = [p.shape for p in stage_params]
+        ctx.uEmbd, ctx.iEmbd = uEmbd.detach(), iEmbd.detach()
+        return Z
+
+    @staticmethod
+    def backward(ctx, G):
+        prop = ctx.prop
+        G = G.contiguous()
+        dU = torch.empty_like(ctx.uEmbd)
+        dI = torch.empty_like(ctx.iEmbd)
+        grads = [torch.empty(s, dtype=torch.float32, device=G.device) for s in ctx.shapes]
+        gtabs = [ops.pointer_table(gs) for gs in stage_param_lists(grads)]
+        prop.backward(G, ctx.uEmbd, ctx.iEmbd, ctx.wtabs, gtabs, dU, dI, accumulate=False)
+        ctx.prop = None
+        return (None, None, None, None, None, dU, dI, *grads)
+
+
+class ScoreFn(torch.autograd.Function):
+    """score_b = ELU(Z[u_b]) . ELU(Z[U+i_b])  (SPUIGACF.py:49-52)."""
+
+    @staticmethod
+    def forward(ctx, Z, U, users, items):
+        users = users.to(torch.int64).contiguous()
+        items = items.to(torch.int64).contiguous()
+        out = torch.empty(users.numel(), dtype=torch.float32, device=Z.device)
+        ops.score_pairs(Z, U, users, items, out)
+        ctx.save_for_backward(Z, users, items)
+        ctx.U = U
+        return out
+
+    @staticmethod
+    def backward(ctx, dscore):
+        Z, users, items = ctx.saved_tensors
+        G = torch.zeros_like(Z)
+        ops.score_pairs_bwd(Z, ctx.U, users, items, dscore.contiguous().float(), G)
+        return G, None, None, None
+
+
+class BPRLossFn(torch.autograd.Function):
+    """-log(sigmoid(pos-neg)).mean()  (BPRLoss.py:8-9), stable form."""
+
+    @staticmethod
+    def forward(ctx, pos, neg):
+        pos = pos.contiguous()
+        neg = neg.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=pos.device)
+        dpos = torch.empty_like(pos)
+        dneg = torch.empty_like(neg)
+        ops.bpr_loss(pos, neg, 1.0, loss, dpos, dneg)
+        ctx.save_for_backward(dpos, dneg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        dpos, dneg = ctx.saved_tensors
+        return dpos * gl, dneg * gl

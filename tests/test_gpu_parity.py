@@ -1,0 +1,361 @@
+"""GPU parity tests: every CUDA entry point, called through the C-ABI (ctypes), against the oracle
+(oracle/port.py) and the committed reference fixtures (tests/golden).  Bit-exact for integer work
+(graph, masks, sampler), 1e-4 relative for fp32 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def sd_from(gz, prefix):
+    return {k[len(prefix):]: torch.from_numpy(gz[k]) for k in gz.files if k.startswith(prefix)}
+
+
+def cuda_graph(u, i, U, I):
+    from ngacf_b200.graph import BipartiteGraph
+    idx = torch.from_numpy(np.stack([u, i]).astype(np.int64)).to(DEV)
+    return BipartiteGraph(idx, U, I)
+
+
+# ------------------------------------------------------------------------------------------------
+# graph builder
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("U,I,E,seed", [(50, 70, 900, 0), (400, 700, 9000, 1), (3000, 5000, 200000, 2)])
+def test_graph_build_bit_exact(U, I, E, seed):
+    rng = np.random.default_rng(seed)
+    u, i = port.synth_bipartite(U, I, E, seed)
+    # duplicates + shuffled input
+    dup = rng.integers(0, E, E // 10)
+    u2, i2 = np.concatenate([u, u[dup]]), np.concatenate([i, i[dup]])
+    p = rng.permutation(u2.shape[0])
+    g = cuda_graph(u2[p], i2[p], U, I)
+    ref = port.build_graph(np.stack([u, i]), U, I)
+    assert g.E == ref.E
+    assert np.array_equal(g.rowptr.cpu().numpy(), ref.rowptr)
+    assert np.array_equal(g.colidx.cpu().numpy(), ref.colidx)
+    assert np.array_equal(g.colptr.cpu().numpy(), ref.colptr)
+    assert np.array_equal(g.rowidx.cpu().numpy(), ref.rowidx)
+    assert np.array_equal(g.perm.cpu().numpy(), ref.perm)
+    # unified adjacency
+    adj_ptr = g.adj_ptr.cpu().numpy()
+    assert np.array_equal(adj_ptr[:U + 1], ref.rowptr) and np.array_equal(adj_ptr[U:], ref.colptr + ref.E)
+    adj = g.adj_idx.cpu().numpy()
+    assert np.array_equal(adj[:ref.E], ref.colidx + U) and np.array_equal(adj[ref.E:], ref.rowidx)
+    eid = g.adj_eid.cpu().numpy()
+    assert np.array_equal(eid[:ref.E], np.arange(ref.E)) and np.array_equal(eid[ref.E:], ref.perm)
+    # tasks: cover every adjacency range exactly once, <= CHUNK edges unless single-task, users first, longest first
+    t = g.tasks.cpu().numpy()
+    deg = np.diff(adj_ptr)
+    ntasks = np.where(deg <= 128, 1, -(-deg // 128))
+    assert t.shape[0] == ntasks.sum() == g.T
+    covered = np.zeros(2 * ref.E + 1, np.int32)
+    for node, b, e, lid in t:
+        covered[b:e] += 1
+        assert adj_ptr[node] <= b <= e <= adj_ptr[node + 1]
+        assert (lid >= 0) == (deg[node] > 128)
+    assert (covered[:2 * ref.E] == 1).all()
+    side = (t[:, 0] >= U).astype(int)
+    assert (np.diff(side) >= 0).all() and side[:g.T_users].sum() == 0 and side[g.T_users:].all()
+    ln = t[:, 2] - t[:, 1]
+    assert (np.diff(ln[:g.T_users]) <= 0).all() and (np.diff(ln[g.T_users:]) <= 0).all()
+    assert g.L == int((deg > 128).sum()) and g.S == int(ntasks[deg > 128].sum())
+
+
+def test_graph_build_rejects_bad_input():
+    from ngacf_b200.graph import BipartiteGraph
+    idx = torch.tensor([[0, 2], [1, 1]], device=DEV)
+    with pytest.raises(ValueError):
+        BipartiteGraph(idx, 3, 2)            # user 1 has no edge (SPUIGACF.py:368)
+    with pytest.raises(ValueError):
+        BipartiteGraph(torch.tensor([[0, 5], [1, 1]], device=DEV), 3, 2)   # out of range
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout masks / sampler: bit exact vs the CPU restatement
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [0.1, 0.2, 0.5])
+def test_dropout_masks_bit_exact(p):
+    from ngacf_b200 import ops
+    N, E = 3001, 70001
+    for stage, H in ((0, 8), (1, 1)):
+        fm = torch.empty(N, dtype=torch.int64, device=DEV)
+        em = torch.empty(E, dtype=torch.uint8, device=DEV)
+        ops.feature_mask(fm, 0x1234567890ABCDEF, 7, stage, p)
+        ops.edge_mask(em, H, 0x1234567890ABCDEF, 7, stage, p)
+        assert np.array_equal(fm.cpu().numpy().view(np.uint64), port.feature_mask_bits(N, 0x1234567890ABCDEF, 7, stage, p))
+        assert np.array_equal(em.cpu().numpy(), port.edge_mask_bits(E, H, 0x1234567890ABCDEF, 7, stage, p))
+
+
+def make_interactions(U, I, E, seed):
+    from ngacf_b200.data import Interactions
+    u, i = port.synth_bipartite(U, I, E, seed)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, seed + 1)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    return it, Interactions.from_arrays(U, I, tu, ti, su, si, device=DEV), (u, i)
+
+
+def test_sampler_bit_exact():
+    from ngacf_b200 import ops
+    it, dit, _ = make_interactions(300, 500, 6000, 3)
+    n = it.train_rows_user.shape[0]
+    for (lo, hi, seed, epoch) in ((0, n, 11, 0), (100, 1500, 2 ** 40 + 5, 3)):
+        users = torch.empty(hi - lo, dtype=torch.int64, device=DEV)
+        pos = torch.empty_like(users)
+        neg = torch.empty_like(users)
+        ops.sample_pairs(dit, lo, hi, seed, epoch, users, pos, neg)
+        ru, rp, rn = port.sample_pairs(it, lo, hi, seed, epoch)
+        assert np.array_equal(users.cpu().numpy(), ru)
+        assert np.array_equal(pos.cpu().numpy(), rp)
+        assert np.array_equal(neg.cpu().numpy(), rn)
+
+
+# ------------------------------------------------------------------------------------------------
+# model forward / backward vs the reference fixtures
+# ------------------------------------------------------------------------------------------------
+def make_model(gz, prefix, droprate=0.0):
+    from ngacf_b200.model import SPUIGACF
+    U, I = int(gz["U"]), int(gz["I"])
+    m = SPUIGACF(U, I, 64, [64, 64], droprate)
+    m.load_state_dict(sd_from(gz, prefix))
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["fwd_bwd_small", "fwd_bwd_medium"])
+def test_forward_backward_vs_reference(golden, name):
+    gz = golden(name)
+    model = make_model(gz, "sd/")
+    model.train()
+    adj = torch.from_numpy(np.stack([gz["edge_u"], gz["edge_i"]])).to(DEV)
+    users = torch.from_numpy(gz["users"]).to(DEV)
+    items = torch.from_numpy(gz["items"]).to(DEV)
+    sc = model(users, items, adj)
+    assert rel_err(sc.detach().cpu().numpy(), gz["scores_f64"]) < 1e-4
+    (sc * torch.from_numpy(gz["w"]).float().to(DEV)).sum().backward()
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), gz["grad_f64/" + k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", ["fwd_bwd_small", "fwd_bwd_medium"])
+def test_forward_backward_with_injected_dropout(golden, name):
+    """masks generated ON THE GPU by the Philox kernels == the masks that were injected into the reference."""
+    gz = golden(name)
+    model = make_model(gz, "sd/", float(gz["drop_p"]))
+    model.train()
+    model.drop_seed = int(gz["drop_seed"])
+    model._call = int(gz["drop_call"])
+    adj = torch.from_numpy(np.stack([gz["edge_u"], gz["edge_i"]])).to(DEV)
+    users = torch.from_numpy(gz["users"]).to(DEV)
+    items = torch.from_numpy(gz["items"]).to(DEV)
+    sc = model(users, items, adj)
+    assert rel_err(sc.detach().cpu().numpy(), gz["scores_drop_f64"]) < 1e-4
+    (sc * torch.from_numpy(gz["w"]).float().to(DEV)).sum().backward()
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), gz["grad_drop_f64/" + k]) < 1e-4, k
+
+
+def test_long_rows_and_isolated_items_vs_port():
+    """Rows longer than CHUNK (split across tasks, combined by the last arriver) and items with no edge
+    (NaN -> 0 path, SPUIGACF.py:389), fp32 GPU vs fp64 port."""
+    U, I, E = 600, 900, 60000
+    u, i = port.synth_bipartite(U, I - 7, E, 5)       # items I-7.. have no edges
+    ref = port.build_graph(np.stack([u, i]), U, I)
+    assert (np.diff(ref.rowptr) > 128).any() and (np.diff(ref.colptr) > 128).any() and (np.diff(ref.colptr) == 0).any()
+    p64 = port.init_params(U, I, 3, torch.float64)
+    p64["uEmbd"] *= 20
+    p64["iEmbd"] *= 20
+    from ngacf_b200.model import SPUIGACF
+    model = SPUIGACF(U, I, 64, [64, 64], 0.25)
+    model.load_state_dict({k: v.float() for k, v in port.state_dict_from_params(p64).items()})
+    model = model.to(DEV).train()
+    model.drop_seed, model._call = 99, 3
+    masks = port.dropout_masks(ref, 99, 3, 0.25)
+    F, caches = port.propagate(p64, ref, masks, 0.25)
+    rng = np.random.default_rng(0)
+    users, items, w = rng.integers(0, U, 512), rng.integers(0, I, 512), rng.standard_normal(512)
+    sc_ref = port.scores(F, U, users, items)
+    ut, itt, wt = torch.from_numpy(users), torch.from_numpy(items) + U, torch.from_numpy(w)
+    dF = torch.zeros_like(F)
+    dF.index_add_(0, ut, wt[:, None] * F[itt])
+    dF.index_add_(0, itt, wt[:, None] * F[ut])
+    gref = port.state_dict_from_params(port.propagate_backward(dF, p64, ref, caches))
+    adj = torch.from_numpy(np.stack([u, i])).to(DEV)
+    sc = model(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), adj)
+    assert rel_err(sc.detach().cpu().numpy(), sc_ref.numpy()) < 1e-4
+    (sc * wt.float().to(DEV)).sum().backward()
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), gref[k].numpy()) < 1e-4, k
+    # determinism: a second identical call gives bit-identical scores (fixed combine order of long rows)
+    model._call = 3
+    sc2 = model(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), adj)
+    assert torch.equal(sc, sc2)
+
+
+def test_score_tree_bit_exact():
+    """scores follow the specified summation tree exactly (given the GPU's own ELU values)."""
+    from ngacf_b200 import ops
+    rng = np.random.default_rng(4)
+    U, I = 37, 53
+    Z = torch.from_numpy(rng.standard_normal((U + I, 64)).astype(np.float32)).to(DEV)
+    F = torch.empty_like(Z)
+    ops.final_features(Z, F)
+    users = torch.from_numpy(rng.integers(0, U, 300)).to(DEV)
+    items = torch.from_numpy(rng.integers(0, I, 300)).to(DEV)
+    out = torch.empty(300, device=DEV)
+    ops.score_pairs(Z, U, users, items, out)
+    Fn = F.cpu().numpy()
+    ref = port.dot64_tree(Fn[users.cpu().numpy()], Fn[items.cpu().numpy() + U])
+    assert np.array_equal(out.cpu().numpy(), ref)
+    Fref = torch.nn.functional.elu(Z.cpu().double()).numpy()
+    assert rel_err(Fn, Fref) < 1e-6
+
+
+def test_bpr_loss_and_saturation():
+    from ngacf_b200.loss import BPRLoss
+    pos = torch.tensor([0.3, -2.0, 40.0, -40.0, 120.0, -120.0, 0.0], device=DEV, requires_grad=True)
+    neg = torch.tensor([0.1, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0], device=DEV, requires_grad=True)
+    loss = BPRLoss()(pos, neg)
+    loss.backward()
+    p64 = pos.detach().cpu().double().requires_grad_()
+    n64 = neg.detach().cpu().double().requires_grad_()
+    ref = torch.nn.functional.softplus(-(p64 - n64)).mean()
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert np.allclose(pos.grad.cpu().numpy(), p64.grad.numpy(), rtol=1e-5, atol=1e-12)
+    assert np.allclose(neg.grad.cpu().numpy(), n64.grad.numpy(), rtol=1e-5, atol=1e-12)
+    assert np.isfinite(loss.item())
+
+
+def test_adam_matches_torch():
+    from ngacf_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(1000, 64), (777, 64), (64, 8), (1, 16), (64, 64), (1, 128)]
+    ps = [torch.randn(s, device=DEV).requires_grad_() for s in shapes]
+    qs = [p.detach().clone().requires_grad_() for p in ps]
+    a = FusedAdam(ps, lr=0.01, weight_decay=1e-3)
+    b = torch.optim.Adam(qs, lr=0.01, weight_decay=1e-3)
+    for step in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = g.clone()
+            q.grad = g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        assert rel_err(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-5
+    sd = a.state_dict()
+    b.load_state_dict(sd)          # state layout is torch.optim.Adam's (checkpoint compatibility)
+
+
+def test_train_epochs_vs_reference(golden):
+    """Two PairSampling epochs (dropout 0.2, Adam, GPU sampler + GPU Philox masks) vs the reference run that
+    had the same samples and masks injected (tests/golden/train_eval_small.npz)."""
+    import train_eval_Gowalla as T
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.loss import BPRLoss
+    from ngacf_b200.optim import FusedAdam
+    gz = golden("train_eval_small")
+    model = make_model(gz, "sd0/", float(gz["droprate"]))
+    U, I = int(gz["U"]), int(gz["I"])
+    dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)
+    adj = torch.from_numpy(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]), np.concatenate([gz["train_i"], gz["test_i"]])]))
+    optim = FusedAdam(model.parameters(), lr=float(gz["lr"]), weight_decay=float(gz["wd"]))
+    model.drop_seed = int(gz["drop_seed"])
+    losses = []
+    for ep in range(int(gz["epochs"])):
+        losses.append(T.train_bpr(model, int(gz["batch"]), dit, dit, adj, optim, BPRLoss(), False,
+                                  epoch=ep, sample_seed=int(gz["sample_seed"])))
+    assert rel_err(np.array(losses), gz["epoch_losses"]) < 1e-4
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    for k in sd:
+        assert rel_err(sd[k], gz["sd1/" + k]) < 5e-3, k
+    # eval on the GPU-trained weights: metrics within tolerance of the reference's eval of ITS weights
+    res = T.eval_neg_all(model, 2048, dit, dit, adj, I, False)
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        assert np.allclose(res[k], gz["eval/" + k], rtol=2e-2, atol=2e-3), (k, res[k], gz["eval/" + k])
+
+
+# ------------------------------------------------------------------------------------------------
+# AllNeg evaluation
+# ------------------------------------------------------------------------------------------------
+def _eval_case(U, I, E, seed, dup_items=0):
+    from ngacf_b200 import ops
+    it, dit, _ = make_interactions(U, I, E, seed)
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((U + I, 64)).astype(np.float32) * 0.5
+    if dup_items:       # identical item rows -> exactly equal scores -> the tie rule (lowest id) decides
+        src = rng.integers(0, I, dup_items)
+        dst = rng.integers(0, I, dup_items)
+        Z[U + dst] = Z[U + src]
+    Zt = torch.from_numpy(Z).to(DEV)
+    F = torch.empty_like(Zt)
+    ops.final_features(Zt, F)
+    return it, dit, Zt, F.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["exact", "tc"])
+@pytest.mark.parametrize("U,I,E,seed,dup", [(90, 150, 1500, 1, 40), (300, 1000, 9000, 2, 200), (1000, 3000, 40000, 3, 0)])
+def test_eval_topk_ids_bit_exact(mode, U, I, E, seed, dup):
+    from ngacf_b200 import _lib
+    from ngacf_b200.evaluate import AllNegEvaluator
+    if mode == "tc" and not hasattr(_lib.load(), "ngacf_score_topk_tc"):
+        pytest.skip("tensor-core path not built")
+    it, dit, Zt, Fn = _eval_case(U, I, E, seed, dup)
+    ev = AllNegEvaluator(dit, mode)
+    ev.rank(Zt)
+    users = dit.eval_users.cpu().numpy()
+    top = ev.top_ids.cpu().numpy()
+    tsc = ev.top_scores.cpu().numpy()
+    Fi = Fn[U:]
+    for j, u in enumerate(users):
+        sc = port.dot64_tree(np.broadcast_to(Fn[u], Fi.shape), Fi)
+        ref = port.topk_allneg(sc, it, int(u))
+        assert np.array_equal(top[j][:ref.shape[0]], ref), (mode, u)
+        assert np.array_equal(tsc[j][:ref.shape[0]], sc[ref]), (mode, u)
+        assert (top[j][ref.shape[0]:] == -1).all()
+
+
+def test_eval_metrics_vs_reference_fixture(golden):
+    """hit lists + metric sums from the reference's own top-20 lists (tests/golden/train_eval_small.npz)."""
+    from ngacf_b200 import ops
+    from ngacf_b200.data import Interactions
+    gz = golden("train_eval_small")
+    U, I = int(gz["U"]), int(gz["I"])
+    dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)
+    assert np.array_equal(dit.eval_users.cpu().numpy(), gz["eval/users"])
+    n = dit.eval_users.numel()
+    top = torch.from_numpy(gz["eval/top20"].astype(np.int32)).to(DEV)
+    hits = torch.empty((n, 20), dtype=torch.uint8, device=DEV)
+    sums = torch.zeros(16, dtype=torch.float64, device=DEV)
+    ws = torch.empty(n * 16, dtype=torch.float64, device=DEV)
+    ops.eval_metrics(top, dit.eval_users, dit, hits, sums, ws)
+    s = sums.cpu().numpy() / dit.n_train_users
+    for q, k in enumerate(("precision", "recall", "ndcg", "hit_ratio")):
+        assert np.allclose(s[4 * q:4 * q + 4], gz["eval/" + k], rtol=1e-12, atol=1e-15), k
+
+
+def test_eval_topk_on_reference_scores_fixture(golden):
+    """Same fp32 embeddings as the reference model -> same top-20 ids as its ranklist_by_heapq, except where
+    two reference scores differ by less than fp32 summation-order noise."""
+    import train_eval_Gowalla as T
+    from ngacf_b200.data import Interactions
+    gz = golden("train_eval_small")
+    model = make_model(gz, "sd1/")
+    U, I = int(gz["U"]), int(gz["I"])
+    dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)
+    adj = torch.from_numpy(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]), np.concatenate([gz["train_i"], gz["test_i"]])]))
+    res = T.eval_neg_all(model, 2048, dit, dit, adj, I, False, mode="exact")
+    top = model._evaluator.top_ids.cpu().numpy()
+    assert (top == gz["eval/top20"]).mean() > 0.995
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        assert np.allclose(res[k], gz["eval/" + k], rtol=1e-3, atol=1e-4), k

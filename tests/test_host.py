@@ -1,0 +1,122 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/ngacf_b200.h
+declares (no compute call is made without a GPU), the drop-in module mirrors the reference's
+constructor / parameter names / init, and the product refuses to run without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from oracle import ref_harness as rh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "ngacf_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ngacf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    from ngacf_b200 import _lib
+    ge.build()
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert lib.ngacf_version() >= 100
+    # argument validation happens before any CUDA call
+    assert lib.ngacf_transform_fwd(None, None, 0, None, 1.0, None, 8, 10, 10, None, None, None) == -1
+    assert b"transform_fwd" in lib.ngacf_last_error()
+
+
+def test_only_sm100a_code_in_the_library():
+    import subprocess
+    from ngacf_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).stdout.decode()
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_model_mirrors_reference_names_and_shapes():
+    from graphattention.BPRLoss import BPRLoss  # noqa: F401  (re-export import path of the reference)
+    from graphattention.SPUIGACF import SPUIGACF
+    m = SPUIGACF(30, 40, 64, [64, 64], 0.1)
+    sd = m.state_dict()
+    want = {"uEmbd.weight": (30, 64), "iEmbd.weight": (40, 64), "gat.out_att.W_u": (64, 64), "gat.out_att.W_i": (64, 64), "gat.out_att.a": (1, 128)}
+    for k in range(8):
+        want.update({f"gat.attention_{k}.W_u": (64, 8), f"gat.attention_{k}.W_i": (64, 8), f"gat.attention_{k}.a": (1, 16)})
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    assert len(list(m.parameters())) == 29
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference checkout absent (GPU box)")
+def test_same_seed_same_init_and_checkpoint_interchange():
+    """torch.manual_seed(s) -> the drop-in module draws exactly the reference's initial parameters, and the
+    state_dicts load into each other (SURVEY.md 5.4 checkpoint contract)."""
+    from ngacf_b200.model import SPUIGACF
+    ns = rh.load()
+    torch.manual_seed(2019)
+    ref = ns["SPUIGACF"].SPUIGACF(50, 70, 64, [64, 64], 0.1, useCuda=False)
+    torch.manual_seed(2019)
+    mine = SPUIGACF(50, 70, 64, [64, 64], 0.1)
+    sr, sm = ref.state_dict(), mine.state_dict()
+    assert list(sr.keys()) == list(sm.keys())
+    for k in sr:
+        assert torch.equal(sr[k], sm[k]), k
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    mine.load_state_dict(sr)
+    ref.load_state_dict(sm)
+
+
+def test_no_cpu_fallback():
+    from ngacf_b200 import NgacfError
+    from ngacf_b200.model import SPUIGACF
+    m = SPUIGACF(5, 6, 64, [64, 64], 0.0)
+    with pytest.raises(NgacfError):
+        m(torch.tensor([0]), torch.tensor([1]), torch.tensor([[0, 1, 2, 3, 4], [0, 1, 2, 3, 4]]))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under ngacf_b200/ or the drop-in entry modules may import it."""
+    bad = []
+    files = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "ngacf_b200")) for f in fs if f.endswith(".py")]
+    files += [os.path.join(ROOT, f) for f in ("train_eval_Gowalla.py", "run_Gowalla.py") if os.path.exists(os.path.join(ROOT, f))]
+    files += [os.path.join(ROOT, "graphattention", f) for f in os.listdir(os.path.join(ROOT, "graphattention")) if f.endswith(".py")]
+    for f in files:
+        src = open(f).read()
+        if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+            bad.append(f)
+    assert not bad, bad
+
+
+def test_interactions_from_reference_frames_matches_arrays():
+    """The pandas-sets structures of the reference (loadGowalla.py:63-67,86-88) convert to the same CSR."""
+    import pandas as pd
+    from ngacf_b200.data import Interactions
+    U, I = 40, 60
+    u, i = port.synth_bipartite(U, I, 500, 9)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, 10)
+    a = Interactions.from_arrays(U, I, tu, ti, su, si, device="cpu")
+    rt_items = set(np.concatenate([ti, si]).tolist())
+    train_df = pd.DataFrame(dict(userId=tu, itemId=ti, rating=1))
+    tpn = train_df.groupby("userId")["itemId"].apply(set).reset_index().rename(columns={"itemId": "positive_items"})
+    tpn["negative_items"] = tpn["positive_items"].apply(lambda x: rt_items - x)
+    test_pos = pd.DataFrame(dict(userId=su, itemId=si)).groupby("userId")["itemId"].apply(set).reset_index().rename(columns={"itemId": "positive_items"})
+    b = Interactions.from_reference_frames(U, I, train_df, tpn, test_pos, device="cpu")
+    c = Interactions.from_reference_frames(U, I, None, tpn, test_pos, device="cpu")
+    for name in ("train_ptr", "train_items", "train_rank", "pool", "in_pool", "test_ptr", "test_items", "eval_users"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+        assert torch.equal(getattr(a, name), getattr(c, name)), name
+    assert torch.equal(a.train_rows_user, b.train_rows_user)
+    assert a.n_train_users == b.n_train_users == c.n_train_users
+    ref = port.build_interactions(U, I, tu, ti, su, si)
+    assert np.array_equal(a.train_ptr.numpy(), ref.train_ptr) and np.array_equal(a.train_rank.numpy(), ref.train_rank)
+    users, div = port.eval_users(ref)
+    assert np.array_equal(a.eval_users.numpy(), users) and a.n_train_users == div

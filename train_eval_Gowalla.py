@@ -1,0 +1,105 @@
+"""PairSampling training epoch and AllNeg evaluation with the reference's call signatures
+(train_eval_Gowalla.py:90 `train_bpr`, :274 `eval_neg_all` of cleverer123/NGACF), on the B200 path.
+
+Both accept either the reference's pandas structures (train_df rows + train_pos_neg with python sets,
+data/loadGowalla.py:63-92) or an ``ngacf_b200.data.Interactions`` object in their place; the sets are
+converted once into CSR arrays in HBM and never consulted again.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from ngacf_b200 import ops
+from ngacf_b200.data import Interactions
+from ngacf_b200.evaluate import AllNegEvaluator
+
+_INTER_CACHE = {}
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def _interactions(model, train_df, pos_neg, test_df=None):
+    """Interactions for the reference's pandas structures -- converted once per object identity."""
+    for cand in (train_df, pos_neg, test_df):
+        if isinstance(cand, Interactions):
+            return cand
+    key = (id(train_df), id(pos_neg), id(test_df))
+    if key not in _INTER_CACHE:
+        m = _unwrap(model)
+        _INTER_CACHE[key] = Interactions.from_reference_frames(m.userNum, m.itemNum, train_df, pos_neg, test_df,
+                                                               device=m.uEmbd.weight.device)
+    return _INTER_CACHE[key]
+
+
+def _device_adj(model, adj):
+    m = _unwrap(model)
+    cached = getattr(m, "_adj_cache", None)
+    if cached is not None and cached[0] is adj:
+        return cached[1]
+    dev = m.uEmbd.weight.device
+    t = torch.as_tensor(adj, dtype=torch.int64).to(dev)        # torch.LongTensor(adj).cuda(), train_eval_Gowalla.py:106
+    m._adj_cache = (adj, t)
+    return t
+
+
+def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is_parallel, epoch=0, sample_seed=None):
+    """One epoch over train_df in file order (train_eval_Gowalla.py:108-115): per batch, one (u,pos,neg)
+    triple per train row from the GPU sampler, two full propagations with independent dropout, BPR,
+    backward, optimizer step.  Returns sum(batch-mean loss) / len(train_df) like the reference (:139,144).
+    `epoch`/`sample_seed` select the sampler's Philox stream (the reference's sampler is unseeded)."""
+    if is_parallel:
+        raise NotImplementedError("--parallel True (single-process DataParallel, parallel.py) is replaced by one process per GPU: "
+                                  "see ngacf_b200/dist.py and bench.py --gpus N")
+    m = _unwrap(model)
+    model.train()
+    inter = _interactions(model, train_df, train_pos_neg)
+    dev = m.uEmbd.weight.device
+    adj_t = _device_adj(model, adj)
+    graph = m.graph_for(adj_t)
+    if sample_seed is None:
+        sample_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    n = len(inter)
+    n_batches = n // batch_size + 1
+    users = torch.empty(batch_size, dtype=torch.int64, device=dev)
+    pos = torch.empty_like(users)
+    neg = torch.empty_like(users)
+    total = torch.zeros((), dtype=torch.float64, device=dev)
+    for batch_id in range(n_batches):
+        lo, hi = batch_id * batch_size, min(n, (batch_id + 1) * batch_size)
+        if hi <= lo:
+            continue        # len(train_df) % batch_size == 0: the reference's empty batch yields a NaN mean; skipped
+        b = hi - lo
+        ops.sample_pairs(inter, lo, hi, sample_seed, epoch, users, pos, neg)
+        optim.zero_grad()
+        pos_scores = model(users[:b], pos[:b], graph)
+        neg_scores = model(users[:b], neg[:b], graph)
+        loss = lossfn(pos_scores, neg_scores)
+        loss.backward()
+        optim.step()
+        total += loss.detach().double()
+        if batch_id % 60 == 0:
+            print("-----------The timeStamp of training batch {:03d}/{}".format(batch_id, n_batches) + " is: "
+                  + time.strftime("%H: %M: %S", time.gmtime(time.time())))
+    return float(total.item()) / n
+
+
+def eval_neg_all(model, batch_size, test_df, test_pos_neg, adj, itemNum, is_parallel, mode="auto"):
+    """Full-ranking evaluation: every test user against every candidate item (item_pool minus the user's
+    train items), top-20, precision/recall/ndcg/hit_ratio @ [1,5,10,20] averaged with the reference's
+    divisor (train_eval_Gowalla.py:283).  Returns the reference's result dict (:277-278,354)."""
+    m = _unwrap(model)
+    model.eval()
+    inter = _interactions(model, None, test_pos_neg, test_df)
+    adj_t = _device_adj(model, adj)
+    with torch.no_grad():
+        Z = m.propagate(adj_t)
+        ev = getattr(m, "_evaluator", None)
+        if ev is None or ev.inter is not inter or ev.mode != mode:
+            ev = AllNegEvaluator(inter, mode)
+            m._evaluator = ev
+        return ev(Z)
