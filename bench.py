@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- SPUIGACF PairSampling training step + AllNeg evaluation on synthetic Gowalla-shape data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port), host cores
+
+One JSON line on stdout (rank 0).  metric/unit/config follow BASELINE.json:
+  value      = propagated edges/s of the training step (steps * 2 * E / time), inputs resident in HBM,
+               CUDA events, max over ranks; a "step" = sampler -> 2 propagations (independent dropout)
+               -> BPR -> backward through both -> Adam (train_eval_Gowalla.py:109-139 of the reference)
+  e2e        = the same through the public train_bpr-style API with the batch's train rows copied from
+               pinned host memory every step and the loss read back every step
+  eval       = AllNeg full-ranking users/s (device) and its own e2e (top-K lists copied to the host)
+  roofline   = dominant kernel's algorithmic bytes / its live CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline = oracle port (closed-form CPU restatement) on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPES = {   # U, I, E
+    "gowalla": (29858, 40981, 1027370),
+    "yelp2018": (31668, 38048, 1561406),
+    "amazon-book": (52643, 91599, 2984108),
+    "ml100k-shape": (943, 1682, 100000),
+    "tiny": (2000, 3000, 60000),
+}
+HYPER = dict(lr=0.01, weight_decay=1e-6, droprate=0.2, batch=2048)   # README.md:27 of the reference
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_data(workload):
+    from oracle import port   # synthetic graph generator only (not on the timed path)
+    U, I, E = SHAPES[workload]
+    u, i = port.synth_bipartite(U, I, E, 0)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, 1)
+    return U, I, u, i, tu, ti, su, si
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            # "under load" = upper half of the power samples
+            order = np.argsort(pw)[len(pw) // 2:]
+            out.update(sm_mhz=float(np.median(np.array(sm)[order])), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(max(pw)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_train_steps(workload, n_steps, warmup, budget_s):
+    import torch
+    from oracle import port
+    U, I, u, i, tu, ti, su, si = make_data(workload)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = port.build_graph(np.stack([u, i]), U, I)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    p = port.init_params(U, I, 2019)
+    st = port.adam_init(p)
+    B = HYPER["batch"]
+    times = []
+    t_start = time.time()
+    k = 0
+    while k < warmup + n_steps:
+        t0 = time.time()
+        lo = (k * B) % max(1, len(it.train_rows_user) - B)
+        users, pos, neg = port.sample_pairs(it, lo, lo + B, 0, 0)
+        mp = port.dropout_masks(g, 0, 2 * k, HYPER["droprate"])
+        mn = port.dropout_masks(g, 0, 2 * k + 1, HYPER["droprate"])
+        loss, grads, _, _ = port.train_step_grads(p, g, users, pos, neg, mp, mn, HYPER["droprate"])
+        port.adam_step(p, grads, st, HYPER["lr"], HYPER["weight_decay"])
+        dt = time.time() - t0
+        if k >= warmup:
+            times.append(dt)
+        k += 1
+        if time.time() - t_start > budget_s and len(times) >= 1:
+            break
+    return g.E, times, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm for this path on the CPU.  /root/reference is Python and cannot
+    travel to the GPU box, so this is the oracle port (kind "port": closed-form restatement, ~16x faster than the
+    reference as written)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    E, times, threads = cpu_train_steps(args.workload, args.steps, min(args.warmup, 1), budget_s=150.0)
+    ms = 1000.0 * float(np.mean(times))
+    val = 2 * E / (ms / 1000.0)
+    sample = "%d of %d requested steps timed (each a full %s-shape step: 2 propagations fwd+bwd + Adam); %d warm-up" % (
+        len(times), args.steps, args.workload, min(args.warmup, 1))
+    line = dict(metric="spuigacf_train_propagated_edges_per_s", value=val, unit="edges/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=args.workload + "-shape SPUIGACF PairSampling step", batch=HYPER["batch"], droprate=HYPER["droprate"]),
+                cpu_baseline=dict(value=val, unit="edges/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=val, unit="edges/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gowalla", choices=sorted(SHAPES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--eval-mode", default="auto")
+    ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ngacf_b200 import _lib, roofline
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.evaluate import AllNegEvaluator
+    from ngacf_b200.graph import BipartiteGraph
+    from ngacf_b200.model import SPUIGACF
+    from ngacf_b200.optim import FusedAdam
+    from ngacf_b200.train import FusedTrainer
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    t0 = time.time()
+    U, I, u, i, tu, ti, su, si = make_data(args.workload)
+    log("[bench] synthetic %s-shape graph: U=%d I=%d E=%d (%.1fs)" % (args.workload, U, I, len(u), time.time() - t0))
+    torch.manual_seed(2019)
+    model = SPUIGACF(U, I, 64, [64, 64], HYPER["droprate"]).to(dev)
+    adj = torch.from_numpy(np.stack([u, i])).to(dev)
+    tb = time.time()
+    graph = BipartiteGraph(adj, U, I)
+    torch.cuda.synchronize()
+    graph_build_ms = 1000 * (time.time() - tb)
+    E = graph.E
+    B = HYPER["batch"]
+    optim = FusedAdam(model.parameters(), lr=HYPER["lr"], weight_decay=HYPER["weight_decay"])
+
+    if world > 1:
+        from ngacf_b200.dist import ShardedTrainer
+        inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
+        trainer = ShardedTrainer(model, inter, graph, B, optim, sample_seed=0)
+    else:
+        inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
+        trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0)
+    launches_per_step = trainer.launches_per_step(HYPER["droprate"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.profile_only:
+        trainer.run_steps(W + 3)
+        torch.cuda.synchronize()
+        return
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    # ---------------- device-resident timed region ----------------
+    trainer.run_steps(W)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    trainer.run_steps(K)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    units_per_step = trainer.units_per_step()          # propagated edges per step, all ranks
+    value = units_per_step / (ms_step / 1000.0)
+
+    # ---------------- e2e: host rows in, loss out, every step ----------------
+    rows_host = torch.from_numpy(np.ascontiguousarray(tu.astype(np.int32))).pin_memory()
+    trainer.run_steps(2, host_rows=rows_host, read_loss=True)
+    barrier()
+    e0.record()
+    trainer.run_steps(K, host_rows=rows_host, read_loss=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = units_per_step / (ms_e2e / K / 1000.0)
+    clk = clocks.stop() if clocks else {}
+
+    # ---------------- per-kernel live timing (eager, one stream) -> roofline of the dominant kernel ----------------
+    prof = trainer.profile_kernels(3)
+    hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10}
+    agg = {}
+    for name, args_, ms in prof:
+        key = name
+        H = args_[hdr[name]] if name in hdr else 0
+        if name == "ngacf_stage_bwd_edges":
+            key = name + ("_users" if args_[0] == 0 else "_items")
+        key = key + ("/H%d" % H if H else "")
+        a = agg.setdefault(key, [0.0, 0])
+        a[0] += ms
+        a[1] += 1
+    nsteps_prof = 3
+    table = sorted(((k, v[0] / nsteps_prof, v[1] / nsteps_prof) for k, v in agg.items()), key=lambda x: -x[1])
+    total_prof = sum(x[1] for x in table)
+    top_key, top_ms_step, top_n = table[0]
+    top_name, top_H = top_key.split("/H")[0], int(top_key.split("/H")[1]) if "/H" in top_key else 0
+    n_params = sum(p.numel() for p in model.parameters())
+    pk = peaks()
+    top_bytes = roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params)
+    top_avg_ms = top_ms_step / top_n
+    achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
+    step_bytes = roofline.step_bytes_compulsory(U, I, E, 2, B)
+    roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+                peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
+                share_of_step=top_ms_step / total_prof,
+                step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
+                                frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
+                kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
+
+    # ---------------- AllNeg evaluation ----------------
+    ev_out = None
+    if not args.no_eval:
+        model.eval()
+        ev = AllNegEvaluator(inter, args.eval_mode)
+        n_eval = int(inter.eval_users.numel())
+
+        def eval_once(to_host):
+            with torch.no_grad():
+                model._eval_key = None            # force the propagation: it is part of the evaluation
+                Z = model.propagate(graph)
+                ev.rank(Z)
+                res = ev.metrics()                # reads 16 sums back (the reference's result dict)
+                if to_host:
+                    return res, ev.top_ids.cpu()
+                return res, None
+        eval_once(False)
+        barrier()
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            res, _ = eval_once(False)
+        e1.record()
+        barrier()
+        ms_eval = e0.elapsed_time(e1) / reps
+        e0.record()
+        for _ in range(reps):
+            res, _ = eval_once(True)
+        e1.record()
+        barrier()
+        ms_eval_e2e = e0.elapsed_time(e1) / reps
+        fl = roofline.eval_flops(n_eval, I)
+        ev_out = dict(metric="allneg_eval_users_per_s", value=n_eval / (ms_eval / 1000.0), unit="users/s", ms=ms_eval, users=n_eval,
+                      e2e=dict(value=n_eval / (ms_eval_e2e / 1000.0), unit="users/s", d2h_bytes=n_eval * 20 * 4 + 128),
+                      mode=("tc" if ev._use_tc() else "exact"), fallback_rows=getattr(ev, "n_fallback", 0),
+                      tensor_frac_of_peak=fl / (ms_eval / 1000.0) / 1e12 / pk["bf16"],
+                      recall_at_20=float(res["recall"][3]), ndcg_at_20=float(res["ndcg"][3]))
+        model.train()
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Ecpu, times, threads = cpu_train_steps(args.workload, 2, 1, budget_s=25.0)
+        cpu_ms = 1000.0 * float(np.mean(times))
+        cpu = dict(value=2 * Ecpu / (cpu_ms / 1000.0), unit="edges/s", cores=threads, kind="port",
+                   sample="%d full %s-shape training steps of the oracle port (closed form, torch CPU), 1 warm-up; %.2f s/step"
+                          % (len(times), args.workload, cpu_ms / 1000.0))
+
+    if rank == 0:
+        line = dict(metric="spuigacf_train_propagated_edges_per_s", value=value, unit="edges/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak" if world > 1 else "weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload="%s-shape SPUIGACF (U=%d I=%d E=%d d=64, 2 attention stages) PairSampling step: sampler + 2 propagations "
+                                         "(dropout %.1f) + BPR + backward + Adam" % (args.workload, U, I, E, HYPER["droprate"]),
+                                batch=B, l2="per-step working set ~%d MB > 126 MB L2, no flush" % (trainer.working_set_bytes() // 2 ** 20),
+                                parallelism=trainer.parallelism(), graph_build_ms=graph_build_ms,
+                                train_rows_per_s=B / (ms_step / 1000.0) * (world if getattr(trainer, "weak", False) else 1)),
+                    roofline=roof, cpu_baseline=cpu, clocks=clk,
+                    e2e=dict(value=e2e_value, unit="edges/s", h2d_bytes_per_step=B * 4, d2h_bytes_per_step=4, ms_per_step=ms_e2e / K),
+                    gpu_launches=launches_per_step * K, eval=ev_out)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,8 +66,12 @@ int ngacf_graph_build(const int64_t* coo_u, const int64_t* coo_i, int64_t E_in, 
  * generator at SPUIGACF.py:208,213 (features) and :375 (edges), which no custom kernel can replay).
  * feat: uint64[N], bit d = keep (n,d).  edge: uint8[E], bit k = keep (edge e, head k).
  * ------------------------------------------------------------------------------------------- */
-int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream);
-int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream);
+int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage, float droprate, void* stream);
+int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage, float droprate, void* stream);
+/* call_dev (may be NULL): device-resident int64 added to `call` at run time; likewise ngacf_sample_pairs'
+ * row_dev = int64[2] {added to row_begin, added to epoch}.  A CUDA graph captured once then replays with
+ * advancing dropout streams, train rows and epochs. */
+int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a3,a5,a6) dense transform: h = dropout(act(X)) @ [W_0..W_{H-1}],  s[n,k] = a_k . h[n, head k].
@@ -148,7 +152,7 @@ int ngacf_adam_step_dev(const uint64_t* tab, int32_t n_tensors, int64_t total_nu
  * ------------------------------------------------------------------------------------------- */
 int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr, const int32_t* train_items,
                        const int32_t* train_rank, const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end,
-                       uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream);
+                       const int64_t* row_dev, uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a16,a17) AllNeg evaluation.  Replaces the 64x2048 score tiles + D2H + heapq.nlargest of

@@ -17,8 +17,9 @@ SIGNATURES = {
     "ngacf_version": (c_int32, []),
     "ngacf_graph_build_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "ngacf_graph_build": (c_int32, [P, P, c_int64, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
-    "ngacf_feature_mask": (c_int32, [P, c_int64, c_uint64, c_uint32, c_uint32, c_float, P]),
-    "ngacf_edge_mask": (c_int32, [P, c_int64, c_int32, c_uint64, c_uint32, c_uint32, c_float, P]),
+    "ngacf_feature_mask": (c_int32, [P, c_int64, c_uint64, c_uint32, P, c_uint32, c_float, P]),
+    "ngacf_edge_mask": (c_int32, [P, c_int64, c_int32, c_uint64, c_uint32, P, c_uint32, c_float, P]),
+    "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_transform_fwd": (c_int32, [P, P, c_int32, P, c_float, P, c_int32, c_int32, c_int32, P, P, P]),
     "ngacf_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, P]),
     "ngacf_score_pairs": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
@@ -33,13 +34,14 @@ SIGNATURES = {
                                       P, c_size_t, P]),
     "ngacf_adam_step": (c_int32, [P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, P]),
     "ngacf_adam_step_dev": (c_int32, [P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
-    "ngacf_sample_pairs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, c_uint64, c_uint32, P, P, P, P]),
+    "ngacf_sample_pairs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, P, P, P, P]),
     "ngacf_score_topk_exact": (c_int32, [P, c_int32, c_int32, P, c_int32, P, P, P, P, P, P]),
     "ngacf_eval_metrics_workspace_bytes": (c_size_t, [c_int32]),
     "ngacf_eval_metrics": (c_int32, [P, P, c_int32, P, P, P, P, P, c_size_t, P]),
 }
 
 _lib = None
+PROFILE = None      # bench.py sets this to a list: every call is then bracketed with CUDA events on its stream
 
 
 class NgacfError(RuntimeError):
@@ -79,7 +81,15 @@ def call(name: str, *args):
     fn = getattr(lib, name, None)
     if fn is None:
         raise NgacfError("entry point %s is not in %s" % (name, LIB_PATH))
-    rc = fn(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((name, args, e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise NgacfError("%s failed (%d): %s" % (name, rc, lib.ngacf_last_error().decode()))
     return rc

@@ -20,7 +20,9 @@ __device__ __forceinline__ uint32_t decisions8(const uint32_t w[4], uint32_t thr
     return bits;
 }
 
-__global__ void feature_mask_kernel(uint64_t* __restrict__ out, int64_t N, uint32_t k0, uint32_t k1, uint32_t call, uint32_t site, uint32_t thr) {
+__global__ void feature_mask_kernel(uint64_t* __restrict__ out, int64_t N, uint32_t k0, uint32_t k1, uint32_t call,
+                                    const int64_t* __restrict__ call_dev, uint32_t site, uint32_t thr) {
+    if (call_dev) call += (uint32_t)*call_dev;
     // one thread per (row, 8-column group); 8 consecutive threads assemble a row's 64-bit word
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t n = t >> 3;
@@ -40,7 +42,9 @@ __global__ void feature_mask_kernel(uint64_t* __restrict__ out, int64_t N, uint3
     if (n < N && c == 0) out[n] = word;
 }
 
-__global__ void edge_mask_kernel(uint8_t* __restrict__ out, int64_t E, int H, uint32_t k0, uint32_t k1, uint32_t call, uint32_t site, uint32_t thr) {
+__global__ void edge_mask_kernel(uint8_t* __restrict__ out, int64_t E, int H, uint32_t k0, uint32_t k1, uint32_t call,
+                                 const int64_t* __restrict__ call_dev, uint32_t site, uint32_t thr) {
+    if (call_dev) call += (uint32_t)*call_dev;
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     uint32_t w[4];
@@ -260,21 +264,23 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
 
 using namespace ngacf;
 
-extern "C" int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream) {
+extern "C" int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage,
+                                  float droprate, void* stream) {
     NGACF_REQUIRE(feat && N >= 0, "feature_mask: bad args");
     if (N == 0) return NGACF_OK;
     uint32_t thr = keep_threshold(droprate);
     feature_mask_kernel<<<ceil_div(N * 8, 256), 256, 0, (cudaStream_t)stream>>>(feat, N, (uint32_t)seed, (uint32_t)(seed >> 32), call,
-                                                                                 stage * 2 + 0, thr);
+                                                                                 call_dev, stage * 2 + 0, thr);
     return check_launch("feature_mask");
 }
 
-extern "C" int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, uint32_t stage, float droprate, void* stream) {
+extern "C" int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage,
+                               float droprate, void* stream) {
     NGACF_REQUIRE(edge && E >= 0 && (H == 1 || H == 8), "edge_mask: bad args");
     if (E == 0) return NGACF_OK;
     uint32_t thr = keep_threshold(droprate);
     edge_mask_kernel<<<ceil_div(E, 256), 256, 0, (cudaStream_t)stream>>>(edge, E, H, (uint32_t)seed, (uint32_t)(seed >> 32), call,
-                                                                          stage * 2 + 1, thr);
+                                                                          call_dev, stage * 2 + 1, thr);
     return check_launch("edge_mask");
 }
 

@@ -175,10 +175,11 @@ constexpr uint32_t SAMPLER_TAG = 0x5A17u;
 
 __global__ void sample_pairs_kernel(const int* __restrict__ rows_user, const int* __restrict__ train_ptr, const int* __restrict__ train_items,
                                     const int* __restrict__ train_rank, const int* __restrict__ pool, int P, int64_t row_begin, int64_t n,
-                                    uint32_t k0, uint32_t k1, uint32_t epoch, int64_t* __restrict__ users, int64_t* __restrict__ pos,
+                                    const int64_t* __restrict__ row_dev, uint32_t k0, uint32_t k1, uint32_t epoch, int64_t* __restrict__ users, int64_t* __restrict__ pos,
                                     int64_t* __restrict__ neg) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
+    if (row_dev) { row_begin += row_dev[0]; epoch += (uint32_t)row_dev[1]; }
     const uint64_t r = (uint64_t)(row_begin + b);
     uint32_t w[4];
     philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), epoch, SAMPLER_TAG, k0, k1, w);
@@ -198,9 +199,17 @@ __global__ void sample_pairs_kernel(const int* __restrict__ rows_user, const int
     neg[b] = pool[k + lo];
 }
 
+__global__ void counter_add_kernel(int64_t* c, int64_t d) { *c += d; }
+
 }  // namespace ngacf
 
 using namespace ngacf;
+
+extern "C" int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream) {
+    NGACF_REQUIRE(counter, "counter_add: null argument");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+    return check_launch("counter_add");
+}
 
 extern "C" int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream) {
     NGACF_REQUIRE(Z && users && items && scores && B >= 0, "score_pairs: null argument");
@@ -259,13 +268,13 @@ extern "C" int ngacf_adam_step_dev(const uint64_t* tab, int32_t n_tensors, int64
 
 extern "C" int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr, const int32_t* train_items,
                                   const int32_t* train_rank, const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end,
-                                  uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream) {
+                                  const int64_t* row_dev, uint64_t seed, uint32_t epoch, int64_t* users, int64_t* pos, int64_t* neg, void* stream) {
     NGACF_REQUIRE(train_rows_user && train_ptr && train_items && train_rank && pool && users && pos && neg, "sample_pairs: null argument");
     NGACF_REQUIRE(row_end >= row_begin && P > 0, "sample_pairs: bad range");
     const int64_t n = row_end - row_begin;
     if (n == 0) return NGACF_OK;
     sample_pairs_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(train_rows_user, train_ptr, train_items, train_rank, pool, P,
-                                                                             row_begin, n, (uint32_t)seed, (uint32_t)(seed >> 32), epoch,
+                                                                             row_begin, n, row_dev, (uint32_t)seed, (uint32_t)(seed >> 32), epoch,
                                                                              users, pos, neg);
     return check_launch("sample_pairs");
 }

@@ -34,12 +34,16 @@ def pointer_table(tensors):
     return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(dev, non_blocking=False)
 
 
-def feature_mask(out, seed, call, stage, droprate):
-    _lib.call("ngacf_feature_mask", _p(out), out.numel(), int(seed), int(call), int(stage), float(droprate), _s())
+def feature_mask(out, seed, call, stage, droprate, call_dev=None):
+    _lib.call("ngacf_feature_mask", _p(out), out.numel(), int(seed), int(call) & 0xFFFFFFFF, _p(call_dev), int(stage), float(droprate), _s())
 
 
-def edge_mask(out, H, seed, call, stage, droprate):
-    _lib.call("ngacf_edge_mask", _p(out), out.numel(), int(H), int(seed), int(call), int(stage), float(droprate), _s())
+def edge_mask(out, H, seed, call, stage, droprate, call_dev=None):
+    _lib.call("ngacf_edge_mask", _p(out), out.numel(), int(H), int(seed), int(call) & 0xFFFFFFFF, _p(call_dev), int(stage), float(droprate), _s())
+
+
+def counter_add(counter, delta):
+    _lib.call("ngacf_counter_add", _p(counter), int(delta), _s())
 
 
 def transform_fwd(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s):
@@ -95,9 +99,10 @@ def adam_step_dev(tab, n_tensors, total_numel, lr, beta1, beta2, eps, weight_dec
     _lib.call("ngacf_adam_step_dev", _p(tab), n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, _p(state), _s())
 
 
-def sample_pairs(inter, row_begin, row_end, seed, epoch, users, pos, neg):
+def sample_pairs(inter, row_begin, row_end, seed, epoch, users, pos, neg, row_dev=None):
     _lib.call("ngacf_sample_pairs", _p(inter.train_rows_user), _p(inter.train_ptr), _p(inter.train_items), _p(inter.train_rank),
-              _p(inter.pool), inter.pool.numel(), int(row_begin), int(row_end), int(seed), int(epoch), _p(users), _p(pos), _p(neg), _s())
+              _p(inter.pool), inter.pool.numel(), int(row_begin), int(row_end), _p(row_dev), int(seed), int(epoch), _p(users), _p(pos),
+              _p(neg), _s())
 
 
 def score_topk_exact(F, U, I, users, inter, top_ids, top_scores):

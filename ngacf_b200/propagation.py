@@ -47,7 +47,7 @@ class Propagation:
                                [torch.empty(max(self.g.E, 1), dtype=torch.uint8, device=dev) for _ in self.stages])
         return self._own_masks
 
-    def set_dropout(self, droprate: float, seed: int = 0, call: int = 0, injected=None):
+    def set_dropout(self, droprate: float, seed: int = 0, call: int = 0, injected=None, call_dev=None):
         """droprate 0 -> no masks.  injected = dict(feat=[uint64/int64 [N]]*S, edge=[uint8 [E]]*S) device tensors
         (parity tests inject masks captured from the reference); else Philox(seed, call)."""
         S = len(self.stages)
@@ -61,8 +61,8 @@ class Propagation:
             return
         fm, em = self._mask_buffers()
         for k, (H, _) in enumerate(self.stages):
-            ops.feature_mask(fm[k], seed, call, k, droprate)
-            ops.edge_mask(em[k][:self.g.E], H, seed, call, k, droprate)
+            ops.feature_mask(fm[k], seed, call, k, droprate, call_dev)
+            ops.edge_mask(em[k][:self.g.E], H, seed, call, k, droprate, call_dev)
         self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
 
     # ------------------------------------------------------------------------------------------

@@ -1,0 +1,294 @@
+"""Fused PairSampling training step (train_eval_Gowalla.py:109-139 of the reference), resident on the GPU:
+
+    sampler -> dropout masks x2 -> propagation x2 -> pair scores -> BPR loss + dscore -> gradient scatter
+    -> backward x2 -> Adam
+
+over persistent HBM buffers, with no host synchronisation (the reference has 55 per step) and, for the
+full-size batches, replayed from ONE captured CUDA graph whose train-row cursor and dropout-stream
+counter live in device memory.  The reference's semantics are kept: two full propagations with
+independent dropout per step, gradients of both summed, Adam with L2 weight decay on all parameters.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .data import Interactions
+from .graph import BipartiteGraph
+from .propagation import Propagation
+
+
+class FusedTrainer:
+    def __init__(self, model, inter: Interactions, graph: BipartiteGraph, batch_size: int, optim, sample_seed: int,
+                 use_cuda_graph: bool = True, two_streams: bool = True):
+        self.model, self.inter, self.g = model, inter, graph
+        self.B = int(batch_size)
+        self.optim = optim
+        self.sample_seed = int(sample_seed)
+        self.use_cuda_graph = use_cuda_graph
+        self.two_streams = two_streams
+        dev = graph.device
+        self.dev = dev
+        self.props = [Propagation(graph), Propagation(graph)]      # pos / neg
+        for p in self.props:
+            p._bwd_buffers()
+        i64 = dict(dtype=torch.int64, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.users = torch.zeros(self.B, **i64)
+        self.pos = torch.zeros(self.B, **i64)
+        self.neg = torch.zeros(self.B, **i64)
+        self.sc_pos = torch.zeros(self.B, **f32)
+        self.sc_neg = torch.zeros(self.B, **f32)
+        self.dpos = torch.zeros(self.B, **f32)
+        self.dneg = torch.zeros(self.B, **f32)
+        self.loss = torch.zeros((), **f32)
+        self.total = torch.zeros((), dtype=torch.float64, device=dev)
+        self.row_dev = torch.zeros(2, **i64)       # {train-row cursor, epoch} of the captured step
+        self.call_dev = torch.zeros(1, **i64)      # dropout call counter (two calls per step)
+        self.side = torch.cuda.Stream(device=dev) if two_streams else None
+        self._graph = None
+        self._setup_params()
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_params(self):
+        m = self.model
+        self.params = [m.uEmbd.weight, m.iEmbd.weight] + m._flat_stage_params()
+        for p in self.params:
+            if p.grad is None or not p.grad.is_contiguous():
+                p.grad = torch.zeros_like(p)
+        stage_params = m.gat.stage_parameters()
+        self.wtabs = [ops.pointer_table([p.detach() for p in st]) for st in stage_params]
+        self.gtabs = [ops.pointer_table([p.grad for p in st]) for st in stage_params]
+        # Adam state lives in the optimizer (torch.optim.Adam's keys), so checkpoints stay interchangeable
+        group = self.optim.param_groups[0]
+        self.hyper = dict(lr=float(group["lr"]), b1=float(group["betas"][0]), b2=float(group["betas"][1]), eps=float(group["eps"]),
+                          wd=float(group["weight_decay"]))
+        rows, step0 = [], 0
+        for p in self.params:
+            st = self.optim.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            step0 = int(float(st["step"]))
+            rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()])
+        self.adam_tab = torch.tensor(rows, dtype=torch.int64).to(self.dev)
+        self.adam_total = sum(p.numel() for p in self.params)
+        self.adam_state = torch.tensor([float(step0), 0.0, 0.0, 0.0], dtype=torch.float64, device=self.dev)
+        self._ptr_key = tuple(tuple(r[:4]) for r in rows)
+
+    def _sync_optimizer_state(self):
+        step = float(self.adam_state[0].item())
+        for p in self.params:
+            self.optim.state[p]["step"] = torch.tensor(step)
+            torch.autograd.graph.increment_version(p)
+
+    # ------------------------------------------------------------------------------------------
+    def _validate(self):
+        """Pointer tables (and a captured graph) are only valid while params/grads/Adam state stay in place."""
+        rows = []
+        for p in self.params:
+            st = self.optim.state.get(p, {})
+            if p.grad is None or len(st) == 0:
+                rows = None
+                break
+            rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()])
+        if rows is None or tuple(tuple(r) for r in rows) != tuple(tuple(r) for r in self._ptr_key):
+            self._setup_params()
+            self._graph = None
+
+    def _step_body(self, b: int, epoch: int, droprate: float, seed: int, row0: int, call0: int, dev_counters: bool):
+        m, g = self.model, self.g
+        uE, iE = m.uEmbd.weight.detach(), m.iEmbd.weight.detach()
+        rd = self.row_dev if dev_counters else None
+        cd = self.call_dev if dev_counters else None
+        ops.sample_pairs(self.inter, row0, row0 + b, self.sample_seed, 0 if dev_counters else epoch, self.users, self.pos, self.neg, rd)
+        cur = torch.cuda.current_stream()
+        items = (self.pos, self.neg)
+        scores = (self.sc_pos, self.sc_neg)
+
+        def fwd(k):
+            self.props[k].set_dropout(droprate, seed, call0 + k, None, cd)
+            Z = self.props[k].forward(uE, iE, self.wtabs)
+            ops.score_pairs(Z, g.U, self.users[:b], items[k][:b], scores[k][:b])
+        if self.side is not None:
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                fwd(1)
+            fwd(0)
+            cur.wait_stream(self.side)
+        else:
+            fwd(0)
+            fwd(1)
+        ops.bpr_loss(self.sc_pos[:b], self.sc_neg[:b], 1.0, self.loss, self.dpos[:b], self.dneg[:b])
+        dsc = (self.dpos, self.dneg)
+
+        def scatter(k):
+            G = self.props[k].grad_in()
+            G.zero_()
+            ops.score_pairs_bwd(self.props[k].Z[-1], g.U, self.users[:b], items[k][:b], dsc[k][:b], G)
+        # the two backward passes accumulate into the same gradient buffers -> they run in order; the
+        # neg propagation's gradient scatter overlaps the pos backward on the side stream
+        if self.side is not None:
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                scatter(1)
+            scatter(0)
+        else:
+            scatter(0)
+            scatter(1)
+        self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, False)
+        if self.side is not None:
+            cur.wait_stream(self.side)
+        self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, True)
+        h = self.hyper
+        ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
+        self.total.add_(self.loss.double())
+        if dev_counters:
+            ops.counter_add(self.row_dev, b)
+            ops.counter_add(self.call_dev, 2)
+
+    # ------------------------------------------------------------------------------------------
+    def launches_per_step(self, droprate: float) -> int:
+        """Number of OUR kernels launched per step (bench.py's gpu_launches claim)."""
+        S = len(self.props[0].stages)
+        per_prop_fwd = (2 * S if droprate > 0 else 0) + 2 * S + 1          # masks, transform+aggregate, score
+        per_prop_bwd = 1 + S * (1 + 2 + 2)                                   # scatter, prep + 2 edge passes + transform_bwd(2 kernels)
+        return 1 + 2 * (per_prop_fwd + per_prop_bwd) + 1 + 2 + 2             # sampler, ..., loss, adam(2), counters(2)
+
+    def train_epoch(self, epoch: int = 0, max_steps=None) -> float:
+        """Returns sum(batch-mean loss)/len(train_df) (train_eval_Gowalla.py:139,144)."""
+        m = self.model
+        m.train()
+        self._validate()
+        droprate = m.droprate if m.droprate > 0 else 0.0
+        seed = m._seed()
+        n = len(self.inter)
+        n_batches = n // self.B + 1
+        if max_steps is not None:
+            n_batches = min(n_batches, max_steps)
+        self.total.zero_()
+        n_full = min(n // self.B, n_batches)
+        if self.use_cuda_graph and n_full > 0:
+            if self._graph is None or self._graph_key != (droprate, seed):
+                self._capture(droprate, seed)
+            self.row_dev.copy_(torch.tensor([0, epoch], dtype=torch.int64), non_blocking=False)
+            self.call_dev.fill_(m._call)
+            for _ in range(n_full):
+                self._graph.replay()
+            m._call += 2 * n_full
+        else:
+            for bi in range(n_full):
+                self._step_body(self.B, epoch, droprate, seed, bi * self.B, m._call, False)
+                m._call += 2
+        if n_batches > n_full:         # tail batch (len % B rows), eager
+            lo = n_full * self.B
+            if n - lo > 0:
+                self._step_body(n - lo, epoch, droprate, seed, lo, m._call, False)
+                m._call += 2
+        self._sync_optimizer_state()
+        return float(self.total.item()) / n
+
+    def _capture(self, droprate, seed):
+        epoch = 0
+        # warm-up on a side stream (allocations, lazy module state), restoring everything it touched
+        snap = [p.detach().clone() for p in self.params]
+        opt_snap = [(self.optim.state[p]["exp_avg"].clone(), self.optim.state[p]["exp_avg_sq"].clone()) for p in self.params]
+        adam_snap, total_snap = self.adam_state.clone(), self.total.clone()
+        row_snap, call_snap = self.row_dev.clone(), self.call_dev.clone()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_body(self.B, epoch, droprate, seed, 0, 0, True)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_body(self.B, epoch, droprate, seed, 0, 0, True)
+        with torch.no_grad():
+            for p, sp, (a, b) in zip(self.params, snap, opt_snap):
+                p.copy_(sp)
+                self.optim.state[p]["exp_avg"].copy_(a)
+                self.optim.state[p]["exp_avg_sq"].copy_(b)
+            self.adam_state.copy_(adam_snap)
+            self.total.copy_(total_snap)
+            self.row_dev.copy_(row_snap)
+            self.call_dev.copy_(call_snap)
+        self._graph, self._graph_key = graph, (droprate, seed)
+
+    # ------------------------------------------------------------------------------------------
+    # step-level driver used by bench.py
+    # ------------------------------------------------------------------------------------------
+    def run_steps(self, n_steps: int, host_rows=None, read_loss: bool = False):
+        """n_steps full-batch steps through the captured graph, wrapping around the train rows.
+        host_rows: pinned int32 host tensor of the train rows' users -- the batch's rows are copied H2D every
+        step (end-to-end mode); read_loss: D2H read of the step loss every step (the reference's .item())."""
+        m = self.model
+        m.train()
+        self._validate()
+        droprate = m.droprate if m.droprate > 0 else 0.0
+        seed = m._seed()
+        n = len(self.inter)
+        if n < self.B:
+            raise ValueError("fewer train rows than one batch")
+        if self._graph is None or self._graph_key != (droprate, seed):
+            self._capture(droprate, seed)
+        if not hasattr(self, "_cursor"):
+            self._cursor = 0
+        self.row_dev.copy_(torch.tensor([self._cursor, 0], dtype=torch.int64))
+        self.call_dev.fill_(m._call)
+        losses = []
+        for _ in range(n_steps):
+            if self._cursor + self.B > n:
+                self._cursor = 0
+                self.row_dev.zero_()
+            if host_rows is not None:
+                lo = self._cursor
+                self.inter.train_rows_user[lo:lo + self.B].copy_(host_rows[lo:lo + self.B], non_blocking=True)
+            self._graph.replay()
+            self._cursor += self.B
+            if read_loss:
+                losses.append(float(self.loss.item()))
+        m._call += 2 * n_steps
+        return losses
+
+    def units_per_step(self) -> int:
+        return 2 * self.g.E          # propagated edges: two full-graph propagations per step
+
+    def parallelism(self) -> str:
+        return "single GPU"
+
+    def working_set_bytes(self) -> int:
+        N, E = self.g.N, self.g.E
+        per_prop = 4 * N * 256 + 4 * N * 256 + 8 * E * 4 + 2 * (N * 8 + E)    # h,Z x2 stages; G x2, Ghat, dh; ds_store; masks
+        return 2 * per_prop + 7 * sum(p.numel() for p in self.params) * 4 + self.g.structure_bytes()
+
+    def profile_kernels(self, n_steps: int = 3):
+        """Per-kernel CUDA-event durations of n eager single-stream steps: [(entry point, args, ms)].
+        Parameters/optimizer state are restored afterwards."""
+        from . import _lib
+        m = self.model
+        droprate = m.droprate if m.droprate > 0 else 0.0
+        snap = [p.detach().clone() for p in self.params]
+        opt_snap = [(self.optim.state[p]["exp_avg"].clone(), self.optim.state[p]["exp_avg_sq"].clone()) for p in self.params]
+        adam_snap, total_snap = self.adam_state.clone(), self.total.clone()
+        side, self.side = self.side, None
+        self._step_body(self.B, 0, droprate, m._seed(), 0, 0, False)     # warm
+        torch.cuda.synchronize(self.dev)
+        _lib.PROFILE = []
+        try:
+            for k in range(n_steps):
+                self._step_body(self.B, 0, droprate, m._seed(), k * self.B, 2 * k, False)
+            torch.cuda.synchronize(self.dev)
+            out = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in _lib.PROFILE]
+        finally:
+            _lib.PROFILE = None
+            self.side = side
+        with torch.no_grad():
+            for p, sp, (a, b) in zip(self.params, snap, opt_snap):
+                p.copy_(sp)
+                self.optim.state[p]["exp_avg"].copy_(a)
+                self.optim.state[p]["exp_avg_sq"].copy_(b)
+            self.adam_state.copy_(adam_snap)
+            self.total.copy_(total_snap)
+        return out

@@ -257,7 +257,8 @@ def test_adam_matches_torch():
     b.load_state_dict(sd)          # state layout is torch.optim.Adam's (checkpoint compatibility)
 
 
-def test_train_epochs_vs_reference(golden):
+@pytest.mark.parametrize("fused", [False, True])
+def test_train_epochs_vs_reference(golden, fused):
     """Two PairSampling epochs (dropout 0.2, Adam, GPU sampler + GPU Philox masks) vs the reference run that
     had the same samples and masks injected (tests/golden/train_eval_small.npz)."""
     import train_eval_Gowalla as T
@@ -272,9 +273,10 @@ def test_train_epochs_vs_reference(golden):
     optim = FusedAdam(model.parameters(), lr=float(gz["lr"]), weight_decay=float(gz["wd"]))
     model.drop_seed = int(gz["drop_seed"])
     losses = []
+    lossfn = BPRLoss()
     for ep in range(int(gz["epochs"])):
-        losses.append(T.train_bpr(model, int(gz["batch"]), dit, dit, adj, optim, BPRLoss(), False,
-                                  epoch=ep, sample_seed=int(gz["sample_seed"])))
+        losses.append(T.train_bpr(model, int(gz["batch"]), dit, dit, adj, optim, lossfn, False,
+                                  epoch=ep, sample_seed=int(gz["sample_seed"]), fused=fused))
     assert rel_err(np.array(losses), gz["epoch_losses"]) < 1e-4
     sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     for k in sd:

@@ -7,6 +7,7 @@ converted once into CSR arrays in HBM and never consulted again.
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -47,7 +48,22 @@ def _device_adj(model, adj):
     return t
 
 
-def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is_parallel, epoch=0, sample_seed=None):
+def _fused_ok(m, optim, lossfn):
+    from ngacf_b200.loss import BPRLoss
+    from ngacf_b200.model import SPUIGACF
+    from ngacf_b200.optim import FusedAdam
+    if not isinstance(m, SPUIGACF) or not isinstance(lossfn, BPRLoss) or len(optim.param_groups) != 1:
+        return False
+    if not isinstance(optim, (torch.optim.Adam, FusedAdam)) or isinstance(optim, torch.optim.AdamW):
+        return False
+    g = optim.param_groups[0]
+    if g.get("amsgrad") or g.get("maximize") or g.get("decoupled_weight_decay"):
+        return False
+    return {id(p) for p in g["params"]} == {id(p) for p in m.parameters()}
+
+
+def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is_parallel, epoch=0, sample_seed=None, fused=None,
+              max_steps=None):
     """One epoch over train_df in file order (train_eval_Gowalla.py:108-115): per batch, one (u,pos,neg)
     triple per train row from the GPU sampler, two full propagations with independent dropout, BPR,
     backward, optimizer step.  Returns sum(batch-mean loss) / len(train_df) like the reference (:139,144).
@@ -63,8 +79,22 @@ def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is
     graph = m.graph_for(adj_t)
     if sample_seed is None:
         sample_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    if fused is None:
+        fused = os.environ.get("NGACF_FUSED", "1") != "0"
+    if fused and _fused_ok(m, optim, lossfn):
+        # whole step on the GPU (sampler .. Adam), CUDA-graph replayed; same maths as the generic loop below
+        from ngacf_b200.train import FusedTrainer
+        tr = getattr(m, "_trainer", None)
+        key = (id(inter), id(graph), int(batch_size), id(optim), int(sample_seed))
+        if tr is None or tr.key != key:
+            tr = FusedTrainer(m, inter, graph, batch_size, optim, sample_seed)
+            tr.key = key
+            m._trainer = tr
+        return tr.train_epoch(epoch, max_steps)
     n = len(inter)
     n_batches = n // batch_size + 1
+    if max_steps is not None:
+        n_batches = min(n_batches, max_steps)
     users = torch.empty(batch_size, dtype=torch.int64, device=dev)
     pos = torch.empty_like(users)
     neg = torch.empty_like(users)
