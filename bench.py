@@ -219,9 +219,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.profile_only:
-        trainer.run_steps(W + 3)
+    if args.profile_only:      # eager, single stream: the launch list ncu sees is the step's kernel sequence
+        trainer.side = None
+        for k in range(W + 2):
+            trainer._step_body(B, 0, HYPER["droprate"], model._seed(), k * B, 2 * k, False)
         torch.cuda.synchronize()
+        if not args.no_eval:
+            model.eval()
+            with torch.no_grad():
+                AllNegEvaluator(inter, args.eval_mode)(model.propagate(graph))
+            torch.cuda.synchronize()
         return
 
     clocks = ClockSampler(local) if rank == 0 else None

@@ -38,41 +38,71 @@ __global__ void final_features_kernel(const float* __restrict__ Z, int64_t n4, f
     st_stream4(F + i * 4, elu4(ld_stream4(Z + i * 4)));
 }
 
+// Gradient scatter of the pair scores, deterministic and atomic-free.
 // entry e in [0,2B): e<B -> (row = users[e], other = U+items[e]); else (row = U+items[e-B], other = users[e-B]).
-// The group of the FIRST entry of each distinct row sums all entries of that row in entry order and
-// stores G[row] with a plain store: deterministic, no atomics, no sort.
+// One CTA per entry; only the CTA of the FIRST entry of each distinct row survives.  It walks the batch
+// in 256-key chunks, compacts the matching entries in order, and its 16 lane-groups gather the matching
+// rows in parallel (4 loads in flight each); the 16 partial sums are combined in a fixed order.
+// A PairSampling batch is user-sorted, so a heavy user can own a whole batch: this keeps that case parallel.
 __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
                                                               const int64_t* __restrict__ items, const float* __restrict__ dscore, int B,
                                                               float* __restrict__ G) {
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    if (e >= 2 * B) return;
-    const int lane16 = threadIdx.x & 15;
-    const unsigned gm = group_mask();
-    const int64_t row = e < B ? users[e] : items[e - B] + U;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    __shared__ int list[256];
+    __shared__ int warp_cnt[8];
+    __shared__ float part[16][D];
+    const int e = blockIdx.x;
     const bool user_row = e < B;
-    // only entries of the same kind can match (user rows < U <= item rows)
-    const int64_t* keys = user_row ? users : items;
-    const int64_t key = user_row ? row : row - U;
-    for (int base = 0; base < B; base += 16) {
-        const int j = base + lane16;
+    const int eb = user_row ? e : e - B;
+    const int64_t* keys = user_row ? users : items;      // only entries of the same kind can match
+    const int64_t* others = user_row ? items : users;
+    const int64_t key = keys[eb];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 4, lane16 = tid & 15;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < B; base += 256) {
+        const int j = base + tid;
         const bool match = j < B && keys[j] == key;
-        unsigned bal = __ballot_sync(gm, match) >> (threadIdx.x & 16);   // this group's 16 bits
-        bal &= 0xFFFFu;
-        while (bal) {
-            const int jj = base + __ffs(bal) - 1;
-            bal &= bal - 1;
-            const int eb = user_row ? e : e - B;
-            if (jj < eb) return;                       // an earlier entry owns this row (group-uniform)
-            const int64_t other = user_row ? items[jj] + U : users[jj];
-            const float c = dscore[jj];
-            const float4 fo = elu4(ld_gather4(Z + other * D + lane16 * 4));
-            acc.x = fmaf(c, fo.x, acc.x); acc.y = fmaf(c, fo.y, acc.y); acc.z = fmaf(c, fo.z, acc.z); acc.w = fmaf(c, fo.w, acc.w);
+        const unsigned bal = __ballot_sync(0xffffffffu, match);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; if (w < warp) off += c; total += c; }
+        if (match) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+        __syncthreads();
+        if (total > 0 && list[0] < eb) return;           // an earlier entry owns this row (block-uniform)
+        for (int q0 = grp; q0 < total; q0 += 64) {       // group g takes matches g, g+16, g+32, g+48 per round
+            int jj[4]; float c[4]; float4 f[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int qi = q0 + 16 * q;
+                jj[q] = qi < total ? list[qi] : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (jj[q] >= 0) {
+                    const int64_t other = others[jj[q]] + (user_row ? U : 0);
+                    c[q] = dscore[jj[q]];
+                    f[q] = ld_gather4(Z + other * D + lane16 * 4);
+                } else { c[q] = 0.f; f[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 fo = elu4(f[q]);
+                acc.x = fmaf(c[q], fo.x, acc.x); acc.y = fmaf(c[q], fo.y, acc.y); acc.z = fmaf(c[q], fo.z, acc.z); acc.w = fmaf(c[q], fo.w, acc.w);
+            }
         }
+        __syncthreads();                                  // list is rewritten by the next chunk
     }
-    const float4 z = ld_gather4(Z + row * D + lane16 * 4);
-    *reinterpret_cast<float4*>(G + row * D + lane16 * 4) =
-        make_float4(acc.x * elu_grad(z.x), acc.y * elu_grad(z.y), acc.z * elu_grad(z.z), acc.w * elu_grad(z.w));
+    *reinterpret_cast<float4*>(&part[grp][lane16 * 4]) = acc;
+    __syncthreads();
+    if (tid < D) {
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) sum += part[g][tid];
+        const int64_t row = user_row ? key : key + U;
+        G[row * D + tid] = sum * elu_grad(Z[row * D + tid]);
+    }
 }
 
 // single-block loss: deterministic tree reduction
@@ -229,7 +259,7 @@ extern "C" int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* u
                                      float* G, void* stream) {
     NGACF_REQUIRE(Z && users && items && dscore && G && B >= 0, "score_pairs_bwd: null argument");
     if (B == 0) return NGACF_OK;
-    score_pairs_bwd_kernel<<<ceil_div((int64_t)B * 2 * 16, 256), 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, dscore, B, G);
+    score_pairs_bwd_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, dscore, B, G);
     return check_launch("score_pairs_bwd");
 }
 
