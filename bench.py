@@ -44,10 +44,10 @@ def log(*a):
 
 
 def make_data(workload):
-    from oracle import port   # synthetic graph generator only (not on the timed path)
+    from ngacf_b200 import hostdata
     U, I, E = SHAPES[workload]
-    u, i = port.synth_bipartite(U, I, E, 0)
-    (tu, ti), (su, si) = port.split_train_test(u, i, U, 1)
+    u, i = hostdata.synth_bipartite(U, I, E, 0)
+    (tu, ti), (su, si) = hostdata.split_per_user(u, i, U, 1)
     return U, I, u, i, tu, ti, su, si
 
 
@@ -206,9 +206,9 @@ def main():
     optim = FusedAdam(model.parameters(), lr=HYPER["lr"], weight_decay=HYPER["weight_decay"])
 
     if world > 1:
-        from ngacf_b200.dist import ShardedTrainer
+        from ngacf_b200.dist import ReplicaTrainer
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
-        trainer = ShardedTrainer(model, inter, graph, B, optim, sample_seed=0)
+        trainer = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=0)
     else:
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
         trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0)
@@ -300,7 +300,8 @@ def main():
     ev_out = None
     if not args.no_eval:
         model.eval()
-        ev = AllNegEvaluator(inter, args.eval_mode)
+        from ngacf_b200.dist import shard_eval_users
+        ev = AllNegEvaluator(inter, args.eval_mode, users=shard_eval_users(inter.eval_users, rank, world))
         n_eval = int(inter.eval_users.numel())
 
         def eval_once(to_host):

@@ -14,12 +14,14 @@ K = 20
 
 
 class AllNegEvaluator:
-    def __init__(self, inter: Interactions, mode: str = "auto"):
-        """mode: 'exact' (fp32 CUDA cores, bit-reproducible), 'tc' (tcgen05 + exact re-score), 'auto' = tc when available."""
+    def __init__(self, inter: Interactions, mode: str = "auto", users=None):
+        """mode: 'exact' (fp32 CUDA cores, bit-reproducible), 'tc' (tcgen05 + exact re-score), 'auto' = tc when available.
+        users: int32 device tensor of the users this rank evaluates (default: every evaluable user)."""
         self.inter = inter
         self.mode = mode
+        self.users = inter.eval_users if users is None else users.to(torch.int32).contiguous()
         dev = inter.device
-        n = inter.eval_users.numel()
+        n = self.users.numel()
         self.top_ids = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
         self.top_scores = torch.empty((max(n, 1), K), dtype=torch.float32, device=dev)
         self.hits = torch.empty((max(n, 1), K), dtype=torch.uint8, device=dev)
@@ -44,16 +46,16 @@ class AllNegEvaluator:
         if self.F is None or self.F.shape != Z.shape:
             self.F = torch.empty_like(Z)
         ops.final_features(Z, self.F)
-        n = it.eval_users.numel()
+        n = self.users.numel()
         if n == 0:
             return
         if self._use_tc():
             if self._tc_ws is None:
                 self._tc_ws = torch.empty(ops.score_topk_tc_workspace_bytes(it.I, n), dtype=torch.uint8, device=Z.device)
-            ops.score_topk_tc(self.F, it.U, it.I, it.eval_users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws)
+            ops.score_topk_tc(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws)
             bad = torch.nonzero(self.fallback[:n]).flatten()
             if bad.numel():       # rows whose error guard failed: recompute exactly
-                users = it.eval_users[bad].contiguous()
+                users = self.users[bad].contiguous()
                 ids = torch.empty((bad.numel(), K), dtype=torch.int32, device=Z.device)
                 sc = torch.empty((bad.numel(), K), dtype=torch.float32, device=Z.device)
                 ops.score_topk_exact(self.F, it.U, it.I, users, it, ids, sc)
@@ -61,13 +63,15 @@ class AllNegEvaluator:
                 self.top_scores[bad] = sc
             self.n_fallback = int(bad.numel())
         else:
-            ops.score_topk_exact(self.F, it.U, it.I, it.eval_users, it, self.top_ids, self.top_scores)
+            ops.score_topk_exact(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores)
             self.n_fallback = 0
 
     def metrics(self):
         """dict in the reference's format (train_eval_Gowalla.py:277-278,354)."""
         it = self.inter
-        ops.eval_metrics(self.top_ids, it.eval_users, it, self.hits, self.sums, self.metric_ws)
+        ops.eval_metrics(self.top_ids, self.users, it, self.hits, self.sums, self.metric_ws)
+        from .dist import allreduce_sums
+        allreduce_sums(self.sums)                                   # multi-GPU: users are sharded, only 16 sums are merged
         s = self.sums.cpu().numpy() / max(it.n_train_users, 1)      # divisor = users with train data (:283)
         return {"precision": s[0:4].copy(), "recall": s[4:8].copy(), "ndcg": s[8:12].copy(), "hit_ratio": s[12:16].copy(), "auc": 0.0}
 

@@ -77,6 +77,19 @@ class FusedTrainer:
         self.adam_state = torch.tensor([float(step0), 0.0, 0.0, 0.0], dtype=torch.float64, device=self.dev)
         self._ptr_key = tuple(tuple(r[:4]) for r in rows)
 
+    # hooks overridden by dist.ReplicaTrainer ------------------------------------------------------
+    def _row_offset(self):
+        return 0
+
+    def _row_stride(self):
+        return self.B
+
+    def _dropout_seed(self, seed):
+        return seed
+
+    def _reduce_grads(self):
+        pass
+
     def _sync_optimizer_state(self):
         step = float(self.adam_state[0].item())
         for p in self.params:
@@ -102,6 +115,7 @@ class FusedTrainer:
         uE, iE = m.uEmbd.weight.detach(), m.iEmbd.weight.detach()
         rd = self.row_dev if dev_counters else None
         cd = self.call_dev if dev_counters else None
+        row0 = row0 + (self._row_offset() if dev_counters else 0)
         ops.sample_pairs(self.inter, row0, row0 + b, self.sample_seed, 0 if dev_counters else epoch, self.users, self.pos, self.neg, rd)
         cur = torch.cuda.current_stream()
         items = (self.pos, self.neg)
@@ -141,11 +155,12 @@ class FusedTrainer:
         if self.side is not None:
             cur.wait_stream(self.side)
         self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, True)
+        self._reduce_grads()
         h = self.hyper
         ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
         self.total.add_(self.loss.double())
         if dev_counters:
-            ops.counter_add(self.row_dev, b)
+            ops.counter_add(self.row_dev, self._row_stride())
             ops.counter_add(self.call_dev, 2)
 
     # ------------------------------------------------------------------------------------------
@@ -162,13 +177,14 @@ class FusedTrainer:
         m.train()
         self._validate()
         droprate = m.droprate if m.droprate > 0 else 0.0
-        seed = m._seed()
+        seed = self._dropout_seed(m._seed())
         n = len(self.inter)
-        n_batches = n // self.B + 1
+        stride = self._row_stride()
+        n_batches = n // stride + 1
         if max_steps is not None:
             n_batches = min(n_batches, max_steps)
         self.total.zero_()
-        n_full = min(n // self.B, n_batches)
+        n_full = min(n // stride, n_batches)
         if self.use_cuda_graph and n_full > 0:
             if self._graph is None or self._graph_key != (droprate, seed):
                 self._capture(droprate, seed)
@@ -179,15 +195,30 @@ class FusedTrainer:
             m._call += 2 * n_full
         else:
             for bi in range(n_full):
-                self._step_body(self.B, epoch, droprate, seed, bi * self.B, m._call, False)
+                self._step_body(self.B, epoch, droprate, seed, bi * stride + self._row_offset(), m._call, False)
                 m._call += 2
-        if n_batches > n_full:         # tail batch (len % B rows), eager
-            lo = n_full * self.B
-            if n - lo > 0:
-                self._step_body(n - lo, epoch, droprate, seed, lo, m._call, False)
+        if n_batches > n_full:         # tail step (len % stride rows), eager; a rank may get fewer rows or none
+            lo = min(n, n_full * stride + self._row_offset())
+            hi = min(n, lo + self.B)
+            if n - n_full * stride > 0:
+                if hi > lo:
+                    self._step_body(hi - lo, epoch, droprate, seed, lo, m._call, False)
+                else:
+                    self._empty_step()
                 m._call += 2
         self._sync_optimizer_state()
+        return self._epoch_loss(n)
+
+    def _epoch_loss(self, n):
         return float(self.total.item()) / n
+
+    def _empty_step(self):
+        """A replica whose slice of the tail step is empty still joins the gradient all-reduce and the update."""
+        for p in self.params:
+            p.grad.zero_()
+        self._reduce_grads()
+        h = self.hyper
+        ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
 
     def _capture(self, droprate, seed):
         epoch = 0
@@ -227,10 +258,11 @@ class FusedTrainer:
         m.train()
         self._validate()
         droprate = m.droprate if m.droprate > 0 else 0.0
-        seed = m._seed()
+        seed = self._dropout_seed(m._seed())
         n = len(self.inter)
-        if n < self.B:
-            raise ValueError("fewer train rows than one batch")
+        stride = self._row_stride()
+        if n < stride:
+            raise ValueError("fewer train rows than one step consumes")
         if self._graph is None or self._graph_key != (droprate, seed):
             self._capture(droprate, seed)
         if not hasattr(self, "_cursor"):
@@ -239,14 +271,14 @@ class FusedTrainer:
         self.call_dev.fill_(m._call)
         losses = []
         for _ in range(n_steps):
-            if self._cursor + self.B > n:
+            if self._cursor + stride > n:
                 self._cursor = 0
                 self.row_dev.zero_()
             if host_rows is not None:
-                lo = self._cursor
+                lo = self._cursor + self._row_offset()
                 self.inter.train_rows_user[lo:lo + self.B].copy_(host_rows[lo:lo + self.B], non_blocking=True)
             self._graph.replay()
-            self._cursor += self.B
+            self._cursor += stride
             if read_loss:
                 losses.append(float(self.loss.item()))
         m._call += 2 * n_steps
@@ -278,7 +310,7 @@ class FusedTrainer:
         _lib.PROFILE = []
         try:
             for k in range(n_steps):
-                self._step_body(self.B, 0, droprate, m._seed(), k * self.B, 2 * k, False)
+                self._step_body(self.B, 0, droprate, self._dropout_seed(m._seed()), k * self.B, 2 * k, False)
             torch.cuda.synchronize(self.dev)
             out = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in _lib.PROFILE]
         finally:
