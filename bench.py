@@ -39,6 +39,9 @@ SHAPES = {   # U, I, E
 HYPER = dict(lr=0.01, weight_decay=1e-6, droprate=0.2, batch=2048)   # README.md:27 of the reference
 
 
+_STDOUT = sys.stdout
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -151,7 +154,8 @@ def run_reference(args):
                 config=dict(workload=args.workload + "-shape SPUIGACF PairSampling step", batch=HYPER["batch"], droprate=HYPER["droprate"]),
                 cpu_baseline=dict(value=val, unit="edges/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=val, unit="edges/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _STDOUT.write(json.dumps(line) + "\n")
+    _STDOUT.flush()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -167,6 +171,12 @@ def main():
     ap.add_argument("--eval-mode", default="auto")
     ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
     args = ap.parse_args()
+    # exactly ONE JSON line may reach stdout: anything native libraries print to fd 1 (e.g. NCCL's version banner) is
+    # diverted to stderr; the JSON line is written to the saved descriptor at the end
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -357,7 +367,8 @@ def main():
                     roofline=roof, cpu_baseline=cpu, clocks=clk,
                     e2e=dict(value=e2e_value, unit="edges/s", h2d_bytes_per_step=B * 4, d2h_bytes_per_step=4, ms_per_step=ms_e2e / K),
                     gpu_launches=launches_per_step * K, eval=ev_out)
-        print(json.dumps(line), flush=True)
+        _STDOUT.write(json.dumps(line) + "\n")
+        _STDOUT.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -98,6 +98,9 @@ class ReplicaTrainer(FusedTrainer):
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)      # sum of per-GPU mean-loss gradients
 
+    def _collective_between(self):
+        return self.world > 1
+
     def _epoch_loss(self, n):
         t = self.total.clone()
         allreduce_sums(t)          # the reference adds the per-GPU losses (loss.sum(), train_eval_Gowalla.py:139)

@@ -47,6 +47,7 @@ class FusedTrainer:
         self.call_dev = torch.zeros(1, **i64)      # dropout call counter (two calls per step)
         self.side = torch.cuda.Stream(device=dev) if two_streams else None
         self._graph = None
+        self._graph_update = None
         self._setup_params()
 
     # ------------------------------------------------------------------------------------------
@@ -90,6 +91,15 @@ class FusedTrainer:
     def _reduce_grads(self):
         pass
 
+    def _collective_between(self):
+        return False
+
+    def _replay(self):
+        self._graph.replay()
+        if self._graph_update is not None:
+            self._reduce_grads()
+            self._graph_update.replay()
+
     def _sync_optimizer_state(self):
         step = float(self.adam_state[0].item())
         for p in self.params:
@@ -110,7 +120,7 @@ class FusedTrainer:
             self._setup_params()
             self._graph = None
 
-    def _step_body(self, b: int, epoch: int, droprate: float, seed: int, row0: int, call0: int, dev_counters: bool):
+    def _step_body(self, b: int, epoch: int, droprate: float, seed: int, row0: int, call0: int, dev_counters: bool, part: str = "all"):
         m, g = self.model, self.g
         uE, iE = m.uEmbd.weight.detach(), m.iEmbd.weight.detach()
         rd = self.row_dev if dev_counters else None
@@ -155,7 +165,12 @@ class FusedTrainer:
         if self.side is not None:
             cur.wait_stream(self.side)
         self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, True)
+        if part == "compute":
+            return
         self._reduce_grads()
+        self._step_update(dev_counters)
+
+    def _step_update(self, dev_counters: bool):
         h = self.hyper
         ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
         self.total.add_(self.loss.double())
@@ -191,7 +206,7 @@ class FusedTrainer:
             self.row_dev.copy_(torch.tensor([0, epoch], dtype=torch.int64), non_blocking=False)
             self.call_dev.fill_(m._call)
             for _ in range(n_full):
-                self._graph.replay()
+                self._replay()
             m._call += 2 * n_full
         else:
             for bi in range(n_full):
@@ -234,8 +249,18 @@ class FusedTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize(self.dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._step_body(self.B, epoch, droprate, seed, 0, 0, True)
+        self._graph_update = None
+        if self._collective_between():
+            # the NCCL all-reduce of the gradients stays OUTSIDE the captured graphs (capturing it deadlocked on
+            # the B200 box): graph 1 = everything up to the gradients, eager all-reduce, graph 2 = Adam + counters
+            with torch.cuda.graph(graph):
+                self._step_body(self.B, epoch, droprate, seed, 0, 0, True, part="compute")
+            self._graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_update):
+                self._step_update(True)
+        else:
+            with torch.cuda.graph(graph):
+                self._step_body(self.B, epoch, droprate, seed, 0, 0, True)
         with torch.no_grad():
             for p, sp, (a, b) in zip(self.params, snap, opt_snap):
                 p.copy_(sp)
@@ -277,7 +302,7 @@ class FusedTrainer:
             if host_rows is not None:
                 lo = self._cursor + self._row_offset()
                 self.inter.train_rows_user[lo:lo + self.B].copy_(host_rows[lo:lo + self.B], non_blocking=True)
-            self._graph.replay()
+            self._replay()
             self._cursor += stride
             if read_loss:
                 losses.append(float(self.loss.item()))

@@ -24,10 +24,20 @@ model = model.to(dev)
 inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
 graph = BipartiteGraph(torch.from_numpy(np.stack([u, i])).to(dev), U, I)
 optim = FusedAdam(model.parameters(), lr=0.01, weight_decay=1e-6)
-tr = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=5)
+def say(*a):
+    print("[rank %d]" % rank, *a, flush=True)
+say("pg up")
+t = torch.ones(4, device=dev); dist.all_reduce(t); torch.cuda.synchronize(); say("eager all_reduce ok", t[0].item())
+use_graph = os.environ.get("NGACF_DIST_GRAPH", "1") != "0"
+tr = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=5, use_cuda_graph=use_graph)
 steps = 3
-tr.run_steps(steps)
+if use_graph:
+    tr.run_steps(steps)
+else:
+    for sidx in range(steps):
+        tr._step_body(B, 0, 0.0, tr._dropout_seed(model._seed()), sidx * B * world + rank * B, 2 * sidx, False)
 torch.cuda.synchronize()
+say("steps done, graph=%s" % use_graph)
 # oracle: same rows, summed per-replica mean-loss gradients, Adam
 g = port.build_graph(np.stack([u, i]), U, I)
 it = port.build_interactions(U, I, tu, ti, su, si)
