@@ -160,12 +160,21 @@ int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr,
  * (candidates = item_pool - train items; order = score desc, item id asc) straight from the
  * propagated features; the dense score matrix never exists in HBM.
  *   exact: fp32 CUDA-core scores with the fixed summation tree (bit-reproducible).
+ *   tc:    tcgen05 bf16x3 user x item GEMM (fp32 accumulators in TMEM) with a top-32 candidate selection fused on
+ *          the accumulators, then exact re-scoring + ordering of the candidates and an error-bound proof that no
+ *          other item can enter the top-20; rows whose proof fails are flagged in `fallback` (the caller recomputes
+ *          them through the exact entry point), so the returned ids are always the exact ones.
  * F = ELU(Z_last) (N,64) final features (ngacf_final_features).  in_pool: uint8[I].
  * top_ids int32 [n_users][20] (-1 padded), top_scores fp32 likewise.
  * ------------------------------------------------------------------------------------------- */
 int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
                            const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
                            int32_t* top_ids, float* top_scores, void* stream);
+size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users);
+int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
+                        const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
+                        int32_t* top_ids, float* top_scores, int32_t* fallback, void* workspace, size_t workspace_bytes,
+                        void* stream);
 /* hits + metric sums (metrics.py:10-86 via get_performance, train_eval_Gowalla.py:419-429):
  * hits uint8 [n_users][20]; sums double[16] = {precision,recall,ndcg,hit}@{1,5,10,20} summed over users
  * (the caller divides by the reference's divisor, the number of users with train data, :283). */

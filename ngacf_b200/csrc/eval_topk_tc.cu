@@ -1,0 +1,397 @@
+// AllNeg evaluation, tensor-core path: users x items score contraction on the 5th-gen tensor cores
+// (tcgen05.mma, bf16 hi/lo split = "bf16x3", fp32 accumulators in TMEM) with the per-row top-K fused
+// on the accumulators as they are read back with tcgen05.ld -- the (users x items) score matrix never
+// touches shared memory or HBM.  The kernel keeps K'=32 approximate candidates per user; a second
+// kernel re-scores them exactly (fp32, specified summation tree), orders them (score desc, id asc),
+// and proves with an error bound that no non-candidate can enter the top-20; rows that fail the proof
+// are flagged and recomputed by the caller through the exact CUDA-core entry point.
+// Replaces train_eval_Gowalla.py:300-341,370-385 of the reference.
+//
+// Kernel structure (one CTA = 128 users, persistent over all item tiles; two CTAs per SM overlap):
+//   warps 0-3  epilogue: thread r owns user row r = TMEM lane r; tcgen05.ld 32 columns at a time,
+//              candidate mask (item pool minus train positives), threshold test, sorted insert
+//   warp 4     producer: one 32 KB cp.async.bulk (TMA engine, 1-D) per item tile, pre-tiled in HBM in
+//              the exact UMMA shared-memory image (K-major, no swizzle) by prep_items_kernel
+//   warp 5     TMEM allocator + single-thread MMA issuer: 12 tcgen05.mma (4 k-steps x {hi.hi, hi.lo, lo.hi})
+//              per tile into a double-buffered 128x128 fp32 accumulator
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace ngacf {
+namespace tc {
+
+constexpr int TM = 128;                 // users per CTA (UMMA M)
+constexpr int TN = 128;                 // items per tile (UMMA N)
+constexpr int KP = 32;                  // approximate candidates kept per user
+constexpr int K = NGACF_TOPK;
+constexpr int PANEL = TN * 16;          // bytes of one k-chunk panel: 128 rows x 16 B
+constexpr int HALF_BYTES = 8 * PANEL;   // 16 KB: one operand half (hi or lo), 8 k-chunks
+constexpr int TILE_BYTES = 2 * HALF_BYTES;   // 32 KB per item tile (hi + lo)
+constexpr int THREADS = 192;
+constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + TILE_BYTES /*B*/ + 2 * KP * TM * 4 /*lists*/ + 128 /*barriers*/ + 1024 /*align*/;
+constexpr float GUARD = 1e-4f;          // |approx - exact| <= GUARD * |u| * max|i|  (bf16x3: ~6e-5 worst case)
+
+// instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128  (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: core matrix = 8 rows x 16 B (contiguous 128 B);
+// LBO = byte distance between the two k-chunks of one MMA (= one panel), SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((PANEL >> 4) & 0x3FFF) << 16;     // leading byte offset
+    d |= (uint64_t)((128 >> 4) & 0x3FFF) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    return d;                                         // base_offset 0, layout_type 0 (no swizzle)
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_bf16x8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        h[k] = __float2bfloat16_rn(x[k]);
+        l[k] = __float2bfloat16_rn(x[k] - __bfloat162float(h[k]));
+    }
+    hi = *reinterpret_cast<uint4*>(h);
+    lo = *reinterpret_cast<uint4*>(l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// item table -> pre-tiled UMMA smem images (hi | lo) in HBM, pool bit words, max item norm
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_items_kernel(const float* __restrict__ F, int U, int I, const uint8_t* __restrict__ in_pool,
+                                                         uint8_t* __restrict__ img, uint32_t* __restrict__ pool_bits,
+                                                         unsigned int* __restrict__ maxnorm_bits, int n_tiles) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (item, k-chunk)
+    const int64_t item = idx >> 3;
+    const int c = (int)(idx & 7);
+    if (item >= (int64_t)n_tiles * TN) return;
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 0.f;
+    if (item < I) {
+        const float4 a = ld_stream4(F + (U + item) * D + c * 8), b = ld_stream4(F + (U + item) * D + c * 8 + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+    uint4 hi, lo;
+    split_bf16x8(x, hi, lo);
+    const int64_t tile = item / TN;
+    const int r = (int)(item % TN);
+    uint8_t* base = img + tile * TILE_BYTES + (size_t)c * PANEL + (size_t)r * 16;
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + HALF_BYTES) = lo;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss = fmaf(x[k], x[k], ss);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const unsigned pool = (item < I && in_pool[item]) ? 1u : 0u;
+    // lanes 0,8,16,24 hold four consecutive items; a 32-item word spans 8 warps -> atomicOr (bit set is order independent)
+    if (c == 0) {
+        atomicMax(maxnorm_bits, __float_as_uint(sqrtf(ss)));
+        if (pool) atomicOr(pool_bits + (item >> 5), 1u << (item & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* __restrict__ F, int U, const int* __restrict__ users,
+                                                                   int n_users, const int* __restrict__ train_ptr,
+                                                                   const int* __restrict__ train_items, const uint32_t* __restrict__ pool_bits,
+                                                                   const uint8_t* __restrict__ img, int n_tiles, int* __restrict__ cand_ids,
+                                                                   float* __restrict__ cand_thr) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = smem;                                   // hi | lo, 32 KB
+    unsigned char* sB = sA + 2 * HALF_BYTES;                    // hi | lo, 32 KB
+    float* Ls = reinterpret_cast<float*>(sB + TILE_BYTES);      // [KP][TM]
+    int* Li = reinterpret_cast<int*>(Ls + KP * TM);             // [KP][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Li + KP * TM); // full_b, empty_b, tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t bar_full = smem_u32(bars + 0), bar_empty = smem_u32(bars + 1);
+    const uint32_t bar_tfull0 = smem_u32(bars + 2), bar_tempty0 = smem_u32(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int u0 = blockIdx.x * TM;
+
+    // ---- one-time setup: user rows -> bf16 hi/lo UMMA image (generic-proxy stores) ----
+    for (int idx = tid; idx < TM * 8; idx += THREADS) {
+        const int r = idx >> 3, c = idx & 7;
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+        if (u0 + r < n_users) {
+            const int64_t u = users[u0 + r];
+            const float4 a = ld_gather4(F + u * D + c * 8), b = ld_gather4(F + u * D + c * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+        uint4 hi, lo;
+        split_bf16x8(x, hi, lo);
+        *reinterpret_cast<uint4*>(sA + (size_t)c * PANEL + (size_t)r * 16) = hi;
+        *reinterpret_cast<uint4*>(sA + HALF_BYTES + (size_t)c * PANEL + (size_t)r * 16) = lo;
+    }
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_empty, 1);
+        mbar_init(bar_tfull0, 1);
+        mbar_init(bar_tfull0 + 8, 1);
+        mbar_init(bar_tempty0, 4);
+        mbar_init(bar_tempty0 + 8, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {   // TMEM: 256 columns = two 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A image visible to the tensor-core (async) proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ================= producer =================
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                mbar_wait(bar_empty, (uint32_t)((t & 1) ^ 1));               // B buffer free (MMAs of tile t-1 retired)
+                mbar_expect_tx(bar_full, TILE_BYTES);
+                bulk_g2s(smem_u32(sB), img + (size_t)t * TILE_BYTES, TILE_BYTES, bar_full);
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t aH = smem_u32(sA), aL = aH + HALF_BYTES, bH = smem_u32(sB), bL = bH + HALF_BYTES;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int buf = t & 1;
+                mbar_wait(bar_full, (uint32_t)(t & 1));                                   // tile t landed in smem
+                mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + (uint32_t)(buf * TN);
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t a0 = term == 2 ? aL : aH;
+                    const uint32_t b0 = term == 1 ? bL : bH;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)            // K = 16 per MMA = two k-chunk panels
+                        umma_bf16(d, smem_desc(a0 + ks * 2 * PANEL), smem_desc(b0 + ks * 2 * PANEL), (term | ks) ? 1u : 0u);
+                }
+                umma_commit(bar_empty);                       // smem B reusable once these MMAs retire
+                umma_commit(bar_tfull0 + 8 * buf);            // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ================= epilogue: thread = user row = TMEM lane =================
+        const int r = tid;                                    // 0..127, warp w reads TMEM lanes 32w..32w+31
+        const int uslot = u0 + r;
+        const int user = uslot < n_users ? users[uslot] : -1;
+        int cur = user >= 0 ? train_ptr[user] : 0;
+        const int tend = user >= 0 ? train_ptr[user + 1] : 0;
+        float thr = -INFINITY;
+        int cnt = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t & 1;
+            const int item0 = t * TN;
+            unsigned tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;      // train positives of this user inside the tile
+            while (cur < tend) {
+                const int it = train_items[cur];
+                if (it >= item0 + TN) break;
+                const int off = it - item0;
+                if (off >= 0) {
+                    const unsigned bit = 1u << (off & 31);
+                    const int w = off >> 5;
+                    tw0 |= w == 0 ? bit : 0u; tw1 |= w == 1 ? bit : 0u; tw2 |= w == 2 ? bit : 0u; tw3 |= w == 3 ? bit : 0u;
+                }
+                ++cur;
+            }
+            mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((t >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TN + ch * 32), v);
+                const unsigned tw = ch == 0 ? tw0 : ch == 1 ? tw1 : ch == 2 ? tw2 : tw3;
+                unsigned allowed = user >= 0 ? (__ldg(pool_bits + t * 4 + ch) & ~tw) : 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    if (((allowed >> j) & 1u) && (cnt < KP || s > thr)) {
+                        int pos = cnt < KP ? cnt : KP - 1;
+                        while (pos > 0 && Ls[(pos - 1) * TM + r] < s) {
+                            Ls[pos * TM + r] = Ls[(pos - 1) * TM + r];
+                            Li[pos * TM + r] = Li[(pos - 1) * TM + r];
+                            --pos;
+                        }
+                        Ls[pos * TM + r] = s;
+                        Li[pos * TM + r] = item0 + ch * 32 + j;
+                        if (cnt < KP) ++cnt;
+                        if (cnt == KP) thr = Ls[(KP - 1) * TM + r];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty0 + 8 * buf);
+        }
+        if (user >= 0) {
+            for (int k = 0; k < KP; ++k) cand_ids[(int64_t)uslot * KP + k] = k < cnt ? Li[k * TM + r] : -1;
+            cand_thr[uslot] = cnt == KP ? thr : -INFINITY;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact re-score of the candidates + order + proof
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot64_tree_g(float4 a, float4 b, unsigned gm) {
+    float p0 = __fmul_rn(a.x, b.x), p1 = __fmul_rn(a.y, b.y), p2 = __fmul_rn(a.z, b.z), p3 = __fmul_rn(a.w, b.w);
+    float v = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 1, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 2, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 4, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(gm, v, 8, 16));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ F, int U, const int* __restrict__ users, int n_users,
+                                                      const int* __restrict__ cand_ids, const float* __restrict__ cand_thr,
+                                                      const unsigned int* __restrict__ maxnorm_bits, int* __restrict__ top_ids,
+                                                      float* __restrict__ top_scores, int* __restrict__ fallback) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (j >= n_users) return;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int64_t u = users[j];
+    const float4 fu = ld_gather4(F + u * D + lane16 * 4);
+    const float unorm = sqrtf(dot64_tree_g(fu, fu, gm));
+    const int id0 = cand_ids[(int64_t)j * KP + lane16], id1 = cand_ids[(int64_t)j * KP + 16 + lane16];
+    float s0 = -INFINITY, s1 = -INFINITY;
+#pragma unroll 4
+    for (int c = 0; c < KP; ++c) {
+        const int id = __shfl_sync(gm, c < 16 ? id0 : id1, c & 15, 16);
+        float s = -INFINITY;
+        if (id >= 0) {                                                   // group-uniform
+            const float4 fi = ld_gather4(F + (int64_t)(U + id) * D + lane16 * 4);
+            s = dot64_tree_g(fu, fi, gm);
+        }
+        if ((c & 15) == lane16) { if (c < 16) s0 = s; else s1 = s; }
+    }
+    // rank of my two candidates under (score desc, id asc); ids are distinct so ranks are a permutation
+    int rank0 = 0, rank1 = 0, nvalid = 0;
+#pragma unroll 4
+    for (int c = 0; c < KP; ++c) {
+        const int id = __shfl_sync(gm, c < 16 ? id0 : id1, c & 15, 16);
+        const float s = __shfl_sync(gm, c < 16 ? s0 : s1, c & 15, 16);
+        if (id >= 0) {
+            ++nvalid;
+            rank0 += (s > s0 || (s == s0 && id < id0)) ? 1 : 0;
+            rank1 += (s > s1 || (s == s1 && id < id1)) ? 1 : 0;
+        }
+    }
+    if (id0 >= 0 && rank0 < K) { top_ids[(int64_t)j * K + rank0] = id0; top_scores[(int64_t)j * K + rank0] = s0; }
+    if (id1 >= 0 && rank1 < K) { top_ids[(int64_t)j * K + rank1] = id1; top_scores[(int64_t)j * K + rank1] = s1; }
+    for (int k = nvalid + lane16; k < K; k += 16) { top_ids[(int64_t)j * K + k] = -1; top_scores[(int64_t)j * K + k] = 0.f; }
+    // proof: every non-candidate has approx <= thr, hence exact <= thr + delta; it cannot enter if that is < tau (exact 20th)
+    float tau = -INFINITY;
+    if (id0 >= 0 && rank0 == K - 1) tau = s0;
+    if (id1 >= 0 && rank1 == K - 1) tau = s1;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(gm, tau, o, 16));
+    const float thr = cand_thr[j];
+    const float delta = GUARD * unorm * __uint_as_float(*maxnorm_bits);
+    const bool ok = (thr == -INFINITY) || (nvalid >= K && thr + delta < tau);
+    if (lane16 == 0) fallback[j] = ok ? 0 : 1;
+}
+
+}  // namespace tc
+}  // namespace ngacf
+
+using namespace ngacf;
+
+static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users) {
+    const size_t n_tiles = (size_t)(I + tc::TN - 1) / tc::TN;
+    return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + al256((size_t)n_users * tc::KP * 4) + al256((size_t)n_users * 4) + 1024;
+}
+
+extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users, const int32_t* train_ptr,
+                                   const int32_t* train_items, const uint8_t* in_pool, int32_t* top_ids, float* top_scores,
+                                   int32_t* fallback, void* workspace, size_t workspace_bytes, void* stream) {
+    NGACF_REQUIRE(F && users && train_ptr && train_items && in_pool && top_ids && top_scores && fallback && workspace && U > 0 && I > 0,
+                  "score_topk_tc: null/empty argument");
+    if (workspace_bytes < ngacf_score_topk_tc_workspace_bytes(I, n_users)) { set_error("score_topk_tc: workspace too small"); return NGACF_ERR_WORKSPACE; }
+    if (n_users == 0) return NGACF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = (I + tc::TN - 1) / tc::TN;
+    char* w = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint8_t* img = (uint8_t*)w;                         w += al256((size_t)n_tiles * tc::TILE_BYTES);
+    uint32_t* pool_bits = (uint32_t*)w;                 w += al256((size_t)n_tiles * 4 * 4);
+    unsigned int* maxnorm = (unsigned int*)w;           w += 256;
+    int* cand_ids = (int*)w;                            w += al256((size_t)n_users * tc::KP * 4);
+    float* cand_thr = (float*)w;
+    cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
+    tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        attr_done = true;
+    }
+    tc::score_topk_tc_kernel<<<ceil_div(n_users, tc::TM), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, train_ptr, train_items, pool_bits,
+                                                                                             img, n_tiles, cand_ids, cand_thr);
+    tc::rescore_kernel<<<ceil_div((int64_t)n_users * 16, 256), 256, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, maxnorm, top_ids, top_scores,
+                                                                             fallback);
+    return check_launch("score_topk_tc");
+}
