@@ -144,55 +144,67 @@ __global__ void __launch_bounds__(EX_THREADS) score_topk_exact_kernel(const floa
 // ------------------------------------------------------------------------------------------------
 // hit lists + metrics (metrics.py:10-86 through get_performance, train_eval_Gowalla.py:419-429)
 // ------------------------------------------------------------------------------------------------
-__global__ void eval_metrics_kernel(const int* __restrict__ top_ids, const int* __restrict__ users, int n_users,
-                                    const int* __restrict__ test_ptr, const int* __restrict__ test_items, uint8_t* __restrict__ hits,
-                                    double* __restrict__ per_user /* [n_users][16] */) {
+__global__ void __launch_bounds__(128) eval_metrics_kernel(const int* __restrict__ top_ids, const int* __restrict__ users, int n_users,
+                                                           const int* __restrict__ test_ptr, const int* __restrict__ test_items,
+                                                           uint8_t* __restrict__ hits, double* __restrict__ partial /* [gridDim.x][16] */) {
+    __shared__ double red[128][17];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_users) return;
-    const int u = users[j];
-    const int beg = test_ptr[u], end = test_ptr[u + 1];
-    uint8_t r[K];
-    for (int k = 0; k < K; ++k) {
-        const int id = top_ids[(int64_t)j * K + k];
-        int lo = beg, hi = end;
-        bool hit = false;
-        while (id >= 0 && lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const int v = test_items[mid];
-            if (v == id) { hit = true; break; }
-            if (v < id) lo = mid + 1; else hi = mid;
+    double val[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) val[q] = 0.0;
+    if (j < n_users) {
+        const int u = users[j];
+        const int beg = test_ptr[u], end = test_ptr[u + 1];
+        unsigned r = 0;                                   // bit k = hit at rank k
+        for (int k = 0; k < K; ++k) {
+            const int id = top_ids[(int64_t)j * K + k];
+            int lo = beg, hi = end;
+            bool hit = false;
+            while (id >= 0 && lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const int v = test_items[mid];
+                if (v == id) { hit = true; break; }
+                if (v < id) lo = mid + 1; else hi = mid;
+            }
+            r |= (hit ? 1u : 0u) << k;
+            hits[(int64_t)j * K + k] = hit ? 1 : 0;
         }
-        r[k] = hit ? 1 : 0;
-        hits[(int64_t)j * K + k] = r[k];
+        const int Ks[4] = {1, 5, 10, 20};
+        const int total_hits = __popc(r);
+        const double npos = (double)(end - beg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int KK = Ks[q];
+            int h = 0;
+            double dcg = 0.0, idcg = 0.0;
+            for (int k = 0; k < KK; ++k) {
+                const double disc = 1.0 / log2((double)(k + 2));
+                if ((r >> k) & 1u) { ++h; dcg += disc; }
+                if (k < total_hits) idcg += disc;        // ideal = the top-20 hit list itself, sorted (metrics.py:69-73)
+            }
+            val[0 + q] = (double)h / (double)KK;                 // precision_at_k
+            val[4 + q] = npos > 0 ? (double)h / npos : 0.0;      // recall_at_k
+            val[8 + q] = idcg > 0 ? dcg / idcg : 0.0;            // ndcg_at_k
+            val[12 + q] = h > 0 ? 1.0 : 0.0;                     // hit_at_k
+        }
     }
-    const int Ks[4] = {1, 5, 10, 20};
-    int total_hits = 0;
-    for (int k = 0; k < K; ++k) total_hits += r[k];
-    const double npos = (double)(end - beg);
-    for (int q = 0; q < 4; ++q) {
-        const int KK = Ks[q];
-        int h = 0;
-        double dcg = 0.0, idcg = 0.0;
-        for (int k = 0; k < KK; ++k) {
-            const double disc = 1.0 / log2((double)(k + 2));
-            if (r[k]) { ++h; dcg += disc; }
-            if (k < total_hits) idcg += disc;        // ideal = the top-20 hit list itself, sorted (metrics.py:69-73)
-        }
-        per_user[(int64_t)j * 16 + 0 + q] = (double)h / (double)KK;                 // precision_at_k
-        per_user[(int64_t)j * 16 + 4 + q] = npos > 0 ? (double)h / npos : 0.0;      // recall_at_k
-        per_user[(int64_t)j * 16 + 8 + q] = idcg > 0 ? dcg / idcg : 0.0;            // ndcg_at_k
-        per_user[(int64_t)j * 16 + 12 + q] = h > 0 ? 1.0 : 0.0;                     // hit_at_k
+#pragma unroll
+    for (int q = 0; q < 16; ++q) red[threadIdx.x][q] = val[q];
+    __syncthreads();
+    if (threadIdx.x < 16) {                                // fixed-order sum over the block's users
+        double acc = 0.0;
+        for (int t = 0; t < 128; ++t) acc += red[t][threadIdx.x];
+        partial[(int64_t)blockIdx.x * 16 + threadIdx.x] = acc;
     }
 }
 
-// one block, column c handled by warp c: fixed-order pairwise reduction over users
-__global__ void __launch_bounds__(512) eval_metrics_reduce_kernel(const double* __restrict__ per_user, int n_users, double* __restrict__ sums) {
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// fixed-order sum of the block partials
+__global__ void eval_metrics_reduce_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ sums) {
+    const int c = threadIdx.x;
+    if (c >= 16) return;
     double acc = 0.0;
-    for (int j = lane; j < n_users; j += 32) acc += per_user[(int64_t)j * 16 + c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sums[c] = acc;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * 16 + c];
+    sums[c] = acc;
 }
 
 }  // namespace ngacf
@@ -223,6 +235,6 @@ extern "C" int ngacf_eval_metrics(const int32_t* top_ids, const int32_t* users, 
     cudaStream_t st = (cudaStream_t)stream;
     if (n_users == 0) { cudaMemsetAsync(sums, 0, 16 * sizeof(double), st); return NGACF_OK; }
     eval_metrics_kernel<<<ceil_div(n_users, 128), 128, 0, st>>>(top_ids, users, n_users, test_ptr, test_items, hits, (double*)workspace);
-    eval_metrics_reduce_kernel<<<1, 512, 0, st>>>((const double*)workspace, n_users, sums);
+    eval_metrics_reduce_kernel<<<1, 32, 0, st>>>((const double*)workspace, ceil_div(n_users, 128), sums);
     return check_launch("eval_metrics");
 }

@@ -28,7 +28,8 @@ constexpr int PANEL = TN * 16;          // bytes of one k-chunk panel: 128 rows 
 constexpr int HALF_BYTES = 8 * PANEL;   // 16 KB: one operand half (hi or lo), 8 k-chunks
 constexpr int TILE_BYTES = 2 * HALF_BYTES;   // 32 KB per item tile (hi + lo)
 constexpr int THREADS = 192;
-constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + TILE_BYTES /*B*/ + 2 * KP * TM * 4 /*lists*/ + 128 /*barriers*/ + 1024 /*align*/;
+constexpr int STAGES = 2;                // item-tile ring in shared memory
+constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + STAGES * TILE_BYTES /*B ring*/ + 32 * TM * 4 /*score staging*/ + 128 /*barriers*/ + 128 /*align*/;
 constexpr float GUARD = 1e-4f;          // |approx - exact| <= GUARD * |u| * max|i|  (bf16x3: ~6e-5 worst case)
 
 // instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128  (cute::UMMA::InstrDescriptor bit layout)
@@ -148,15 +149,14 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                                                                    const uint8_t* __restrict__ img, int n_tiles, int* __restrict__ cand_ids,
                                                                    float* __restrict__ cand_thr) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);   // no swizzle: 16 B would do
     unsigned char* sA = smem;                                   // hi | lo, 32 KB
-    unsigned char* sB = sA + 2 * HALF_BYTES;                    // hi | lo, 32 KB
-    float* Ls = reinterpret_cast<float*>(sB + TILE_BYTES);      // [KP][TM]
-    int* Li = reinterpret_cast<int*>(Ls + KP * TM);             // [KP][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Li + KP * TM); // full_b, empty_b, tmem_full[2], tmem_empty[2]
+    unsigned char* sB = sA + 2 * HALF_BYTES;                    // STAGES x (hi | lo), 32 KB each
+    float* Vs = reinterpret_cast<float*>(sB + STAGES * TILE_BYTES);   // [32 columns][TM rows] staging of one accumulator chunk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 32 * TM); // full[2], empty[2], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t bar_full = smem_u32(bars + 0), bar_empty = smem_u32(bars + 1);
-    const uint32_t bar_tfull0 = smem_u32(bars + 2), bar_tempty0 = smem_u32(bars + 4);
+    const uint32_t bar_full0 = smem_u32(bars + 0), bar_empty0 = smem_u32(bars + 2);
+    const uint32_t bar_tfull0 = smem_u32(bars + 4), bar_tempty0 = smem_u32(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int u0 = blockIdx.x * TM;
@@ -178,8 +178,10 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         *reinterpret_cast<uint4*>(sA + HALF_BYTES + (size_t)c * PANEL + (size_t)r * 16) = lo;
     }
     if (tid == 0) {
-        mbar_init(bar_full, 1);
-        mbar_init(bar_empty, 1);
+        mbar_init(bar_full0, 1);
+        mbar_init(bar_full0 + 8, 1);
+        mbar_init(bar_empty0, 1);
+        mbar_init(bar_empty0 + 8, 1);
         mbar_init(bar_tfull0, 1);
         mbar_init(bar_tfull0 + 8, 1);
         mbar_init(bar_tempty0, 4);
@@ -200,18 +202,20 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         // ================= producer =================
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
-                mbar_wait(bar_empty, (uint32_t)((t & 1) ^ 1));               // B buffer free (MMAs of tile t-1 retired)
-                mbar_expect_tx(bar_full, TILE_BYTES);
-                bulk_g2s(smem_u32(sB), img + (size_t)t * TILE_BYTES, TILE_BYTES, bar_full);
+                const int st = t & 1;
+                mbar_wait(bar_empty0 + 8 * st, (uint32_t)(((t >> 1) & 1) ^ 1));   // ring slot free (MMAs of tile t-2 retired)
+                mbar_expect_tx(bar_full0 + 8 * st, TILE_BYTES);
+                bulk_g2s(smem_u32(sB) + st * TILE_BYTES, img + (size_t)t * TILE_BYTES, TILE_BYTES, bar_full0 + 8 * st);
             }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t aH = smem_u32(sA), aL = aH + HALF_BYTES, bH = smem_u32(sB), bL = bH + HALF_BYTES;
+            const uint32_t aH = smem_u32(sA), aL = aH + HALF_BYTES;
             for (int t = 0; t < n_tiles; ++t) {
                 const int buf = t & 1;
-                mbar_wait(bar_full, (uint32_t)(t & 1));                                   // tile t landed in smem
+                const uint32_t bH = smem_u32(sB) + buf * TILE_BYTES, bL = bH + HALF_BYTES;
+                mbar_wait(bar_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));                 // tile t landed in its ring slot
                 mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                     for (int ks = 0; ks < 4; ++ks)            // K = 16 per MMA = two k-chunk panels
                         umma_bf16(d, smem_desc(a0 + ks * 2 * PANEL), smem_desc(b0 + ks * 2 * PANEL), (term | ks) ? 1u : 0u);
                 }
-                umma_commit(bar_empty);                       // smem B reusable once these MMAs retire
+                umma_commit(bar_empty0 + 8 * buf);            // ring slot reusable once these MMAs retire
                 umma_commit(bar_tfull0 + 8 * buf);            // accumulator ready for the epilogue
             }
         }
@@ -234,8 +238,12 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         const int user = uslot < n_users ? users[uslot] : -1;
         int cur = user >= 0 ? train_ptr[user] : 0;
         const int tend = user >= 0 ? train_ptr[user + 1] : 0;
-        float thr = -INFINITY;
-        int cnt = 0;
+        // candidate list: KP (score, id) pairs sorted by descending score, entirely in registers
+        float ls[KP];
+        int li[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) { ls[k] = -INFINITY; li[k] = -1; }
+        float thr = -INFINITY;                                // == ls[KP-1]
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
             const int item0 = t * TN;
@@ -258,21 +266,31 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TN + ch * 32), v);
                 const unsigned tw = ch == 0 ? tw0 : ch == 1 ? tw1 : ch == 2 ? tw2 : tw3;
-                unsigned allowed = user >= 0 ? (__ldg(pool_bits + t * 4 + ch) & ~tw) : 0u;
+                const unsigned allowed = user >= 0 ? (__ldg(pool_bits + t * 4 + ch) & ~tw) : 0u;
+                // threshold filter on the registers; the (rare) survivors are picked up again from a shared-memory
+                // copy so that the insertion code exists once instead of 32 times
+                unsigned hit = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]);
-                    if (((allowed >> j) & 1u) && (cnt < KP || s > thr)) {
-                        int pos = cnt < KP ? cnt : KP - 1;
-                        while (pos > 0 && Ls[(pos - 1) * TM + r] < s) {
-                            Ls[pos * TM + r] = Ls[(pos - 1) * TM + r];
-                            Li[pos * TM + r] = Li[(pos - 1) * TM + r];
-                            --pos;
+                    Vs[j * TM + r] = __uint_as_float(v[j]);
+                    hit |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+                }
+                hit &= allowed;
+                while (hit) {                                   // lanes work on their own survivors in parallel
+                    const int j = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const float sc = Vs[j * TM + r];
+                    const int id = item0 + ch * 32 + j;
+                    if (sc > thr) {
+#pragma unroll
+                        for (int k = KP - 1; k > 0; --k) {
+                            const bool shift = ls[k - 1] < sc;
+                            const bool here = ls[k] < sc;
+                            li[k] = shift ? li[k - 1] : (here ? id : li[k]);
+                            ls[k] = shift ? ls[k - 1] : (here ? sc : ls[k]);
                         }
-                        Ls[pos * TM + r] = s;
-                        Li[pos * TM + r] = item0 + ch * 32 + j;
-                        if (cnt < KP) ++cnt;
-                        if (cnt == KP) thr = Ls[(KP - 1) * TM + r];
+                        if (ls[0] < sc) { ls[0] = sc; li[0] = id; }
+                        thr = ls[KP - 1];
                     }
                 }
             }
@@ -281,8 +299,9 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             if (lane == 0) mbar_arrive(bar_tempty0 + 8 * buf);
         }
         if (user >= 0) {
-            for (int k = 0; k < KP; ++k) cand_ids[(int64_t)uslot * KP + k] = k < cnt ? Li[k * TM + r] : -1;
-            cand_thr[uslot] = cnt == KP ? thr : -INFINITY;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) cand_ids[(int64_t)uslot * KP + k] = li[k];
+            cand_thr[uslot] = li[KP - 1] >= 0 ? thr : -INFINITY;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

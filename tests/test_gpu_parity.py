@@ -325,6 +325,10 @@ def test_eval_topk_ids_bit_exact(mode, U, I, E, seed, dup):
         assert np.array_equal(top[j][:ref.shape[0]], ref), (mode, u)
         assert np.array_equal(tsc[j][:ref.shape[0]], sc[ref]), (mode, u)
         assert (top[j][ref.shape[0]:] == -1).all()
+    if mode == "tc":
+        # the tensor-core result itself must be the exact one for (nearly) every row: the exact fallback is an escape
+        # hatch for rows whose error-bound proof fails, not the path that makes this test pass
+        assert ev.n_fallback <= max(2, len(users) // 20), ev.n_fallback
 
 
 def test_eval_metrics_vs_reference_fixture(golden):
