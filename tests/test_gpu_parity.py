@@ -365,3 +365,28 @@ def test_eval_topk_on_reference_scores_fixture(golden):
     assert (top == gz["eval/top20"]).mean() > 0.995
     for k in ("precision", "recall", "ndcg", "hit_ratio"):
         assert np.allclose(res[k], gz["eval/" + k], rtol=1e-3, atol=1e-4), k
+
+
+def test_config1_ml100k_two_epochs_vs_reference(golden):
+    """BASELINE config 1 (the reference README's smoke test): SPUIGACF on the real ml100k split, PairSampling, AllNeg,
+    2 epochs, lr 0.002, wd 1e-6, droprate 0.2, B 2048 -- GPU run vs the UNMODIFIED reference's run with the same
+    sampler/dropout streams injected (tests/golden/ml100k_2epochs.npz, oracle/make_golden.py:case_ml100k)."""
+    import train_eval_Gowalla as T
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.loss import BPRLoss
+    gz = golden("ml100k_2epochs")
+    model = make_model(gz, "sd0/", float(gz["droprate"]))
+    U, I = int(gz["U"]), int(gz["I"])
+    dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)
+    adj = torch.from_numpy(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]), np.concatenate([gz["train_i"], gz["test_i"]])]).astype(np.int64))
+    optim = torch.optim.Adam(model.parameters(), lr=float(gz["lr"]), weight_decay=float(gz["wd"]))   # the reference's own optimizer class
+    model.drop_seed = int(gz["drop_seed"])
+    lossfn = BPRLoss()
+    losses = [T.train_bpr(model, int(gz["batch"]), dit, dit, adj, optim, lossfn, False, epoch=ep, sample_seed=int(gz["sample_seed"]))
+              for ep in range(int(gz["epochs"]))]
+    assert rel_err(np.array(losses), gz["epoch_losses"]) < 1e-3, (losses, gz["epoch_losses"])
+    res = T.eval_neg_all(model, int(gz["batch"]), dit, dit, adj, I, False)
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        assert np.allclose(res[k], gz["eval/" + k], rtol=3e-2, atol=3e-3), (k, res[k], gz["eval/" + k])
+    sd = model.state_dict()
+    assert rel_err(sd["uEmbd.weight"].cpu().numpy(), gz["sd1/uEmbd.weight"]) < 2e-2

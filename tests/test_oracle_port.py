@@ -243,3 +243,17 @@ def test_port_against_live_reference_fp64():
     p = port.params_from_state_dict(model.state_dict())
     F, _ = port.propagate(p, g)
     assert rel_err(port.scores(F, U, users, items).numpy(), sc.detach().numpy()) < 1e-12
+
+
+def test_config1_ml100k_first_epoch_matches_reference(golden):
+    """BASELINE config 1 on the real ml100k split: one epoch (40 steps, dropout 0.2, Adam) of the port vs the reference."""
+    gz = golden("ml100k_2epochs")
+    U, I = int(gz["U"]), int(gz["I"])
+    it = port.build_interactions(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"])
+    g = port.build_graph(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]), np.concatenate([gz["train_i"], gz["test_i"]])]), U, I)
+    assert g.E == 100000 and it.train_rows_user.shape[0] == 80000
+    p = port.params_from_state_dict(sd_from(gz, "sd0/"), torch.float32)
+    st = port.adam_init(p)
+    loss, _ = port.train_bpr(p, g, it, int(gz["batch"]), st, float(gz["lr"]), float(gz["wd"]), 0, int(gz["sample_seed"]),
+                             float(gz["droprate"]), int(gz["drop_seed"]), 0)
+    assert abs(loss - gz["epoch_losses"][0]) < 1e-4 * gz["epoch_losses"][0]
