@@ -105,69 +105,4 @@ __device__ __forceinline__ float head_reduce(float v, unsigned mask) {
     return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// 8-lane groups for the sparse kernels: one group per task (row or <=128-edge chunk), lane l owns
-// columns 8l..8l+7 (two 16-byte vector loads per gathered row).  With H=8 a lane IS a head: the
-// per-edge softmax weight is computed once per head and the backward's per-head dot products are
-// lane-local; with H=1 the eight lanes share the single head.
-// ---------------------------------------------------------------------------------------------
-struct f8 { float4 a, b; };
-__device__ __forceinline__ unsigned group8_mask() { return 0xFFu << (threadIdx.x & 24); }
-__device__ __forceinline__ f8 ld_gather8(const float* p) { f8 v; v.a = ld_gather4(p); v.b = ld_gather4(p + 4); return v; }
-__device__ __forceinline__ f8 ld_stream8(const float* p) { f8 v; v.a = ld_stream4(p); v.b = ld_stream4(p + 4); return v; }
-__device__ __forceinline__ void st_stream8(float* p, const f8& v) { st_stream4(p, v.a); st_stream4(p + 4, v.b); }
-__device__ __forceinline__ f8 zero8() { f8 v; v.a = make_float4(0.f, 0.f, 0.f, 0.f); v.b = v.a; return v; }
-__device__ __forceinline__ void fma8(f8& acc, float w, const f8& x) {
-    acc.a.x = fmaf(w, x.a.x, acc.a.x); acc.a.y = fmaf(w, x.a.y, acc.a.y); acc.a.z = fmaf(w, x.a.z, acc.a.z); acc.a.w = fmaf(w, x.a.w, acc.a.w);
-    acc.b.x = fmaf(w, x.b.x, acc.b.x); acc.b.y = fmaf(w, x.b.y, acc.b.y); acc.b.z = fmaf(w, x.b.z, acc.b.z); acc.b.w = fmaf(w, x.b.w, acc.b.w);
-}
-__device__ __forceinline__ float dot8(const f8& x, const f8& y) {
-    return x.a.x * y.a.x + x.a.y * y.a.y + x.a.z * y.a.z + x.a.w * y.a.w + x.b.x * y.b.x + x.b.y * y.b.y + x.b.z * y.b.z + x.b.w * y.b.w;
-}
-template <int H>
-__device__ __forceinline__ float head_reduce8(float v, unsigned mask) {     // H=8: lane-local; H=1: sum over the 8 lanes
-    if (H == 1) {
-        v += __shfl_xor_sync(mask, v, 1, 8);
-        v += __shfl_xor_sync(mask, v, 2, 8);
-        v += __shfl_xor_sync(mask, v, 4, 8);
-    }
-    return v;
-}
-template <int H>
-__device__ __forceinline__ bool head_writer8(int l8) { return H == 8 ? true : l8 == 0; }
-
-// Partial sums of a row longer than CHUNK edges: every chunk's group parks (acc, per-head sum) in its scratch
-// slot; the group that arrives LAST re-reads all slots in slot order (deterministic) and finishes the row.
-template <int H>
-__device__ __forceinline__ bool long_row_combine8(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
-                                                  float* scratch, int l8, unsigned gm, f8& acc, float& sum) {
-    const int head = H == 8 ? l8 : 0;
-    const int first = long_first_slot[lid];
-    const int nslots = long_first_slot[lid + 1] - first;
-    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
-    *reinterpret_cast<float4*>(slot + l8 * 8) = acc.a;
-    *reinterpret_cast<float4*>(slot + l8 * 8 + 4) = acc.b;
-    if (head_writer8<H>(l8)) slot[D + head] = sum;
-    __threadfence();
-    __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
-    int old = 0;
-    if (l8 == 0) old = atomicAdd(long_counter + lid, 1);
-    old = __shfl_sync(gm, old, 0, 8);
-    if (old != nslots - 1) return false;
-    __threadfence();
-    f8 t = zero8();
-    float ts = 0.f;
-    for (int c = 0; c < nslots; ++c) {
-        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
-        const float4 va = ld_cg4(sl + l8 * 8), vb = ld_cg4(sl + l8 * 8 + 4);
-        t.a.x += va.x; t.a.y += va.y; t.a.z += va.z; t.a.w += va.w;
-        t.b.x += vb.x; t.b.y += vb.y; t.b.z += vb.z; t.b.w += vb.w;
-        ts += __ldcg(sl + D + head);
-    }
-    acc = t;
-    sum = ts;
-    if (l8 == 0) long_counter[lid] = 0;      // re-arm for the next launch
-    return true;
-}
-
 }  // namespace ngacf

@@ -38,8 +38,45 @@ __global__ void __launch_bounds__(256) stage_bwd_prep_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// edge passes: 8-lane groups, lane l owns columns 8l..8l+7 (with H=8 a lane is a head)
-// ------------------------------------------------------------------------------------------------
+// defined in propagate_fwd.cu's translation unit as a template; re-declared here (same body) to keep
+// the two .cu files independently compilable
+template <int H, int NSUM>
+__device__ __forceinline__ bool long_row_combine_b(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
+                                                   float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
+    const int head = lane_head_b<H>(lane16);
+    const int first = long_first_slot[lid];
+    const int nslots = long_first_slot[lid + 1] - first;
+    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
+    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
+    if (head_writer<H>(lane16)) {
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
+    }
+    __threadfence();
+    __syncwarp(gm);
+    int old = 0;
+    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
+    old = __shfl_sync(gm, old, 0, 16);
+    if (old != nslots - 1) return false;
+    __threadfence();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ts[NSUM];
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
+    for (int c = 0; c < nslots; ++c) {
+        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
+        float4 v = ld_cg4(sl + lane16 * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
+    }
+    acc = t;
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
+    if (lane16 == 0) long_counter[lid] = 0;
+    return true;
+}
+
 template <int H, int MODE, bool DROP>
 __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
                                                               const int* __restrict__ adj_ptr, const int* __restrict__ adj_idx,
@@ -51,26 +88,26 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
                                                               const float* const* __restrict__ wtab, int U,
                                                               float* ds_store, float* __restrict__ dh, float* __restrict__ dS) {
     constexpr int DH = D / H;
-    const int t = T_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const int t = T_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     if (t >= T_end) return;
-    const int l8 = threadIdx.x & 7;
-    const unsigned gm = group8_mask();
-    const int head = H == 8 ? l8 : 0;
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int head = lane_head_b<H>(lane16);
     const int4 tk = __ldg(tasks + t);
     const int node = tk.x, beg = tk.y, end = tk.z, lid = tk.w;
-    const float sn = __ldg(s + (unsigned)node * H + head);
+    const float sn = __ldg(s + (int64_t)node * H + head);
     const float sc = DROP ? scale : 1.f;
-    f8 ghn = zero8(), hn = zero8();
+    float4 ghn = make_float4(0.f, 0.f, 0.f, 0.f), hn = ghn;
     float dNn = 0.f;
     if (MODE == 0) {
-        ghn = ld_stream8(Ghat + (size_t)node * D + l8 * 8);
-        hn = ld_stream8(h + (size_t)node * D + l8 * 8);
-        dNn = __ldg(dN + (unsigned)node * H + head);
+        ghn = ld_stream4(Ghat + (int64_t)node * D + lane16 * 4);
+        hn = ld_stream4(h + (int64_t)node * D + lane16 * 4);
+        dNn = __ldg(dN + (int64_t)node * H + head);
     }
-    f8 acc = zero8();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float dSacc = 0.f;
-    for (int base = beg; base < end; base += 8) {
-        const int idx = base + l8;
+    for (int base = beg; base < end; base += 16) {
+        const int idx = base + lane16;
         int m_l = 0, eid_l = 0;
         unsigned mk_l = 0xFFu;
         if (idx < end) {
@@ -78,47 +115,50 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
             eid_l = ld_stream_i32(adj_eid + idx);
             if (DROP) mk_l = edgemask[eid_l];
         }
-        const int cnt = min(8, end - base);
+        const int cnt = min(16, end - base);
 #pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
-            const unsigned m = (unsigned)__shfl_sync(gm, m_l, j, 8);
-            const unsigned eid = (unsigned)__shfl_sync(gm, eid_l, j, 8);
-            const float sm = __ldg(s + m * H + head);
-            const f8 gmr = ld_gather8(Ghat + (size_t)m * D + l8 * 8);
+            const int m = __shfl_sync(gm, m_l, j, 16);
+            const int eid = __shfl_sync(gm, eid_l, j, 16);
+            const float sm = __ldg(s + (int64_t)m * H + head);
+            const float4 gm4 = ld_gather4(Ghat + (int64_t)m * D + lane16 * 4);
             const float x = sn + sm;
             const float e = edge_weight(x);
             float keepsc = sc;
             if (DROP) {
-                const unsigned mk = __shfl_sync(gm, mk_l, j, 8);
+                const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
                 keepsc = ((mk >> head) & 1u) ? sc : 0.f;
             }
-            fma8(acc, e * keepsc, gmr);
+            const float et = e * keepsc;
+            acc.x = fmaf(et, gm4.x, acc.x); acc.y = fmaf(et, gm4.y, acc.y);
+            acc.z = fmaf(et, gm4.z, acc.z); acc.w = fmaf(et, gm4.w, acc.w);
             float ds;
             if (MODE == 0) {
-                const f8 hm = ld_gather8(h + (size_t)m * D + l8 * 8);
-                const float det = head_reduce8<H>(dot8(ghn, hm) + dot8(gmr, hn), gm);
-                const float de = fmaf(det, keepsc, dNn + __ldg(dN + m * H + head));
+                const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                float part = ghn.x * hm.x + ghn.y * hm.y + ghn.z * hm.z + ghn.w * hm.w
+                           + gm4.x * hn.x + gm4.y * hn.y + gm4.z * hn.z + gm4.w * hn.w;
+                const float det = head_reduce<H>(part, gm);
+                const float de = fmaf(det, keepsc, dNn + __ldg(dN + (int64_t)m * H + head));
                 ds = de * (-e) * (x > 0.f ? 1.f : LRELU_ALPHA);
-                if (head_writer8<H>(l8)) ds_store[(size_t)eid * H + head] = ds;
+                if (head_writer<H>(lane16)) ds_store[(int64_t)eid * H + head] = ds;
             } else {
-                ds = __ldg(ds_store + (size_t)eid * H + head);
+                ds = __ldg(ds_store + (int64_t)eid * H + head);
             }
             dSacc += ds;
         }
     }
     if (lid >= 0) {
+        float sums[1] = {dSacc};
         const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
-        if (!long_row_combine8<H>(lid, chunk, long_first_slot, long_counter, scratch, l8, gm, acc, dSacc)) return;
+        if (!long_row_combine_b<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        dSacc = sums[0];
     }
-    const f8 gn = ld_stream8(G + (size_t)node * D + l8 * 8);
-    const float* ap = wtab[2 * H + head] + (node >= U ? DH : 0) + (H == 8 ? 0 : l8 * 8);
-    f8 o;
-    o.a = make_float4(gn.a.x + acc.a.x + dSacc * __ldg(ap + 0), gn.a.y + acc.a.y + dSacc * __ldg(ap + 1),
-                      gn.a.z + acc.a.z + dSacc * __ldg(ap + 2), gn.a.w + acc.a.w + dSacc * __ldg(ap + 3));
-    o.b = make_float4(gn.b.x + acc.b.x + dSacc * __ldg(ap + 4), gn.b.y + acc.b.y + dSacc * __ldg(ap + 5),
-                      gn.b.z + acc.b.z + dSacc * __ldg(ap + 6), gn.b.w + acc.b.w + dSacc * __ldg(ap + 7));
-    st_stream8(dh + (size_t)node * D + l8 * 8, o);
-    if (head_writer8<H>(l8)) dS[(size_t)node * H + head] = dSacc;
+    const float4 gn = ld_stream4(G + (int64_t)node * D + lane16 * 4);
+    const float* ap = wtab[2 * H + head] + (node >= U ? DH : 0) + ((lane16 * 4) % DH);
+    const float4 a4 = make_float4(__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3));
+    st_stream4(dh + (int64_t)node * D + lane16 * 4,
+               make_float4(gn.x + acc.x + dSacc * a4.x, gn.y + acc.y + dSacc * a4.y, gn.z + acc.z + dSacc * a4.z, gn.w + acc.w + dSacc * a4.w));
+    if (head_writer<H>(lane16)) dS[(int64_t)node * H + head] = dSacc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,7 +352,7 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
                   "stage_bwd_edges: null argument");
     NGACF_REQUIRE((mode == 0 || mode == 1) && (H == 1 || H == 8) && T_end >= T_begin, "stage_bwd_edges: bad mode/H/range");
     if (T_end == T_begin) return NGACF_OK;
-    const int blocks = ceil_div((int64_t)(T_end - T_begin) * 8, 256);
+    const int blocks = ceil_div((int64_t)(T_end - T_begin) * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
 #define LAUNCH(HH, MM, DR)                                                                                                              \

@@ -159,9 +159,52 @@ __global__ void __launch_bounds__(256, 4) transform_fwd_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused edge softmax + aggregation.  One 8-lane group per task (a row, or a <=128-edge chunk of a
-// long row); lane l owns columns 8l..8l+7 (two 16-byte vector loads of every gathered row).
+// fused edge softmax + aggregation.  One 16-lane group per task (a row, or a <=128-edge chunk of a
+// long row); lane l owns columns 4l..4l+3 (16-byte vector loads of the gathered rows).
 // ------------------------------------------------------------------------------------------------
+template <int H>
+__device__ __forceinline__ int lane_head(int lane16) { return H == 8 ? (lane16 >> 1) : 0; }
+
+// combine the partials of a long row: called by every group that finishes a chunk; returns true for
+// the group that arrived last (which then holds the totals, summed in slot order -> deterministic)
+template <int H, int NSUM>
+__device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
+                                                 float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
+    const int head = lane_head<H>(lane16);
+    const int first = long_first_slot[lid];
+    const int nslots = long_first_slot[lid + 1] - first;
+    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
+    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
+    // per-head scalars: NSUM values per head, stored at [64 + j*H... ]: slot has 8 floats of room => NSUM*H <= 8
+    if ((H == 8 && (lane16 & 1) == 0) || (H == 1 && lane16 == 0)) {
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
+    }
+    __threadfence();
+    __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
+    int old = 0;
+    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
+    old = __shfl_sync(gm, old, 0, 16);
+    if (old != nslots - 1) return false;
+    __threadfence();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ts[NSUM];
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
+    for (int c = 0; c < nslots; ++c) {
+        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
+        float4 v = ld_cg4(sl + lane16 * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
+    }
+    acc = t;
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
+    if (lane16 == 0) long_counter[lid] = 0;    // re-arm for the next launch
+    return true;
+}
+
 template <int H, bool DROP>
 __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ adj_ptr,
                                                             const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
@@ -169,52 +212,54 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
                                                             const float* __restrict__ h, const float* __restrict__ s,
                                                             const uint8_t* __restrict__ edgemask, float scale,
                                                             float* __restrict__ Z, float* __restrict__ norm) {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (t >= T) return;                                  // whole 8-lane groups exit together
-    const int l8 = threadIdx.x & 7;
-    const unsigned gm = group8_mask();
-    const int head = H == 8 ? l8 : 0;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (t >= T) return;                                  // whole 16-lane groups exit together
+    const int lane16 = threadIdx.x & 15;
+    const unsigned gm = group_mask();
+    const int head = lane_head<H>(lane16);
     const int4 tk = __ldg(tasks + t);
     const int node = tk.x, beg = tk.y, end = tk.z, lid = tk.w;
-    const float sn = __ldg(s + (unsigned)node * H + head);
-    f8 acc = zero8();
+    const float sn = __ldg(s + (int64_t)node * H + head);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 0.f;
-    for (int base = beg; base < end; base += 8) {
-        const int idx = base + l8;
+    for (int base = beg; base < end; base += 16) {
+        const int idx = base + lane16;
         int m_l = 0;
         unsigned mk_l = 0xFFu;
         if (idx < end) {
             m_l = ld_stream_i32(adj_idx + idx);
             if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + idx)];
         }
-        const int cnt = min(8, end - base);
+        const int cnt = min(16, end - base);
 #pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
-            const unsigned m = (unsigned)__shfl_sync(gm, m_l, j, 8);
-            const float sm = __ldg(s + m * H + head);
-            const f8 hm = ld_gather8(h + (size_t)m * D + l8 * 8);
+            const int m = __shfl_sync(gm, m_l, j, 16);
+            const float sm = __ldg(s + (int64_t)m * H + head);
+            const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
             const float w = edge_weight(sn + sm);
             rs += w;
             float wd = w;
             if (DROP) {
-                const unsigned mk = __shfl_sync(gm, mk_l, j, 8);
+                const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
                 wd = ((mk >> head) & 1u) ? w * scale : 0.f;
             }
-            fma8(acc, wd, hm);
+            acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
+            acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
         }
     }
     if (lid >= 0) {
+        float sums[1] = {rs};
         const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
-        if (!long_row_combine8<H>(lid, chunk, long_first_slot, long_counter, scratch, l8, gm, acc, rs)) return;
+        if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        rs = sums[0];
     }
     // epilogue: Z = h + agg / norm, NaN -> 0 for isolated nodes (SPUIGACF.py:383,388-390)
     const float inv = rs != 0.f ? 1.0f / rs : 0.f;
-    const f8 hn = ld_stream8(h + (size_t)node * D + l8 * 8);
-    f8 z;
-    z.a = make_float4(fmaf(acc.a.x, inv, hn.a.x), fmaf(acc.a.y, inv, hn.a.y), fmaf(acc.a.z, inv, hn.a.z), fmaf(acc.a.w, inv, hn.a.w));
-    z.b = make_float4(fmaf(acc.b.x, inv, hn.b.x), fmaf(acc.b.y, inv, hn.b.y), fmaf(acc.b.z, inv, hn.b.z), fmaf(acc.b.w, inv, hn.b.w));
-    st_stream8(Z + (size_t)node * D + l8 * 8, z);
-    if (head_writer8<H>(l8)) norm[(size_t)node * H + head] = rs;
+    const float4 hn = ld_stream4(h + (int64_t)node * D + lane16 * 4);
+    st_stream4(Z + (int64_t)node * D + lane16 * 4,
+               make_float4(fmaf(acc.x, inv, hn.x), fmaf(acc.y, inv, hn.y), fmaf(acc.z, inv, hn.z), fmaf(acc.w, inv, hn.w)));
+    if (H == 8) { if ((lane16 & 1) == 0) norm[(int64_t)node * 8 + head] = rs; }
+    else        { if (lane16 == 0) norm[node] = rs; }
 }
 
 }  // namespace ngacf
@@ -265,7 +310,7 @@ extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_
     NGACF_REQUIRE(tasks && adj_ptr && adj_idx && h && s && Z && norm && T > 0, "aggregate_fwd: null/empty argument");
     NGACF_REQUIRE(H == 1 || H == 8, "aggregate_fwd: H must be 1 or 8 (got %d)", H);
     NGACF_REQUIRE(!edgemask || adj_eid, "aggregate_fwd: edge dropout needs adj_eid");
-    const int blocks = ceil_div((int64_t)T * 8, 256);
+    const int blocks = ceil_div((int64_t)T * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
 #define LAUNCH(HH, DR) aggregate_fwd_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
