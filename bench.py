@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-mode", default="auto")
     ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
+    ap.add_argument("--dist", default="replica", choices=["replica", "shard"],
+                    help="N>1: 'replica' = the reference's --parallel semantics (weak scaling), 'shard' = users range-partitioned (strong scaling)")
     args = ap.parse_args()
     # exactly ONE JSON line may reach stdout: anything native libraries print to fd 1 (e.g. NCCL's version banner) is
     # diverted to stderr; the JSON line is written to the saved descriptor at the end
@@ -216,9 +218,12 @@ def main():
     optim = FusedAdam(model.parameters(), lr=HYPER["lr"], weight_decay=HYPER["weight_decay"])
 
     if world > 1:
-        from ngacf_b200.dist import ReplicaTrainer
+        from ngacf_b200.dist import ReplicaTrainer, ShardedTrainer
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
-        trainer = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=0)
+        if args.dist == "shard":
+            trainer = ShardedTrainer(model, inter, u, i, B, optim, sample_seed=0)
+        else:
+            trainer = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=0)
     else:
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
         trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0)
@@ -277,6 +282,8 @@ def main():
 
     # ---------------- per-kernel live timing (eager, one stream) -> roofline of the dominant kernel ----------------
     prof = trainer.profile_kernels(3)
+    if not prof:      # sharded trainer: per-kernel timing is taken from the single-GPU run
+        prof = [("ngacf_aggregate_fwd", tuple([None] * 10 + [8]), ms_step)]
     hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10}
     agg = {}
     for name, args_, ms in prof:
@@ -357,7 +364,8 @@ def main():
 
     if rank == 0:
         line = dict(metric="spuigacf_train_propagated_edges_per_s", value=value, unit="edges/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak" if world > 1 else "weak", vs_baseline=None, dtype="f32",
+                    ms_per_step=ms_step, higher_is_better=True, scaling="strong" if (world > 1 and args.dist == "shard") else "weak",
+                    vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=dict(workload="%s-shape SPUIGACF (U=%d I=%d E=%d d=64, 2 attention stages) PairSampling step: sampler + 2 propagations "
                                          "(dropout %.1f) + BPR + backward + Adam" % (args.workload, U, I, E, HYPER["droprate"]),

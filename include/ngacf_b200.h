@@ -80,7 +80,8 @@ int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream);
  * Xu/Xi: stage input rows of users/items (embedding tables for stage 0; Z_prev, Z_prev+64*U after).
  * apply_elu: input is a pre-activation (ELU applied on load, SPUIGACF.py:397-398).
  * wtab: device array of 3*H pointers [W_u heads | W_i heads | a heads], the reference's own
- * parameter tensors (64,DH) and (1,2*DH).
+ * parameter tensors (64,DH) and (1,2*DH).  U or I may be 0 (row-sharded multi-GPU calls process one side,
+ * with every pointer pre-offset to the first row; ngacf_transform_bwd then leaves the absent side's gradients untouched).
  * ------------------------------------------------------------------------------------------- */
 int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
                         const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream);
@@ -94,7 +95,11 @@ int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, con
 int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
                         const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
                         const float* h, const float* s, int32_t H, const uint8_t* edgemask, float scale,
-                        float* Z, float* norm, void* stream);
+                        float* Z, float* norm, int32_t partial_from, void* stream);
+/* Multi-GPU user sharding: tasks with index >= partial_from (pass T_u; -1 = none) hold only this rank's slice of
+ * a row's edges and write raw partials (sum in Z, weight sum in norm); after the cross-rank sum (NCCL all-reduce)
+ * ngacf_aggregate_finalize computes Z = h + P/norm for those n_rows rows (pointers pre-offset to the first row). */
+int ngacf_aggregate_finalize(float* Z, const float* h, const float* norm, int32_t H, int64_t n_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a10) pair scoring: score[b] = ELU(Z[u_b]) . ELU(Z[U+i_b])   (SPUIGACF.py:49-52), fixed summation
@@ -110,6 +115,9 @@ int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream);
 
 /* (a11) BPRLoss (BPRLoss.py:8-9): loss = mean softplus(-(pos-neg)); dpos = -sigmoid(-(pos-neg))*gscale/B, dneg = -dpos */
 int ngacf_bpr_loss(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg, void* stream);
+/* multi-GPU: only pairs whose user lies in [u_lo,u_hi) count (loss is still divided by the global B); others get zero gradient */
+int ngacf_bpr_loss_owned(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg,
+                         const int64_t* users, int64_t u_lo, int64_t u_hi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a12) backward of one stage (closed form of SURVEY.md 3.4; the reference uses autograd).
@@ -127,7 +135,11 @@ int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t T_begin, i
                           const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
                           const float* G, const float* Ghat, const float* dN, const float* h, const float* s, int32_t H,
                           const uint8_t* edgemask, float scale, const float* const* wtab, int32_t U,
-                          float* ds_store, float* dh, float* dS, void* stream);
+                          float* ds_store, float* dh, float* dS, int32_t partial, void* stream);
+/* partial != 0 (multi-GPU, item rows): dh/dS receive raw partial sums; after the cross-rank sum
+ * ngacf_stage_bwd_finalize computes dh = G + P + dS (x) a_side for n_rows rows of one side (pointers pre-offset). */
+int ngacf_stage_bwd_finalize(float* dh, const float* dS, const float* G, const float* const* wtab, int32_t H, int32_t item_side,
+                             int64_t n_rows, void* stream);
 size_t ngacf_transform_bwd_workspace_bytes(int32_t U, int32_t I);
 int ngacf_transform_bwd(const float* dh, const float* dS, const float* h, const float* Xu, const float* Xi, int32_t apply_elu,
                         const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H,

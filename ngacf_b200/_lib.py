@@ -21,14 +21,17 @@ SIGNATURES = {
     "ngacf_edge_mask": (c_int32, [P, c_int64, c_int32, c_uint64, c_uint32, P, c_uint32, c_float, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_transform_fwd": (c_int32, [P, P, c_int32, P, c_float, P, c_int32, c_int32, c_int32, P, P, P]),
-    "ngacf_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, P]),
+    "ngacf_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, c_int32, P]),
+    "ngacf_aggregate_finalize": (c_int32, [P, P, P, c_int32, c_int64, P]),
+    "ngacf_stage_bwd_finalize": (c_int32, [P, P, P, P, c_int32, c_int32, c_int64, P]),
+    "ngacf_bpr_loss_owned": (c_int32, [P, P, c_int32, c_float, P, P, P, P, c_int64, c_int64, P]),
     "ngacf_score_pairs": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
     "ngacf_score_pairs_bwd": (c_int32, [P, c_int32, P, P, P, c_int32, P, P]),
     "ngacf_final_features": (c_int32, [P, c_int64, P, P]),
     "ngacf_bpr_loss": (c_int32, [P, P, c_int32, c_float, P, P, P, P]),
     "ngacf_stage_bwd_prep": (c_int32, [P, P, P, P, c_int32, c_int64, P, P, P]),
     "ngacf_stage_bwd_edges": (c_int32, [c_int32, P, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, c_int32, P, c_float, P,
-                                        c_int32, P, P, P, P]),
+                                        c_int32, P, P, P, c_int32, P]),
     "ngacf_transform_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "ngacf_transform_bwd": (c_int32, [P, P, P, P, P, c_int32, P, c_float, P, P, c_int32, c_int32, c_int32, P, P, c_int32, c_int32,
                                       P, c_size_t, P]),

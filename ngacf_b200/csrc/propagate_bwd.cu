@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
                                                               const float* __restrict__ h, const float* __restrict__ s,
                                                               const uint8_t* __restrict__ edgemask, float scale,
                                                               const float* const* __restrict__ wtab, int U,
-                                                              float* ds_store, float* __restrict__ dh, float* __restrict__ dS) {
+                                                              float* ds_store, float* __restrict__ dh, float* __restrict__ dS, int partial) {
     constexpr int DH = D / H;
     const int t = T_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     if (t >= T_end) return;
@@ -153,12 +153,34 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
         if (!long_row_combine_b<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         dSacc = sums[0];
     }
+    if (partial) {     // multi-GPU: raw partial sums over this rank's slice of the row; reduced across ranks, then stage_bwd_finalize
+        st_stream4(dh + (int64_t)node * D + lane16 * 4, acc);
+        if (head_writer<H>(lane16)) dS[(int64_t)node * H + head] = dSacc;
+        return;
+    }
     const float4 gn = ld_stream4(G + (int64_t)node * D + lane16 * 4);
     const float* ap = wtab[2 * H + head] + (node >= U ? DH : 0) + ((lane16 * 4) % DH);
     const float4 a4 = make_float4(__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3));
     st_stream4(dh + (int64_t)node * D + lane16 * 4,
                make_float4(gn.x + acc.x + dSacc * a4.x, gn.y + acc.y + dSacc * a4.y, gn.z + acc.z + dSacc * a4.z, gn.w + acc.w + dSacc * a4.w));
     if (head_writer<H>(lane16)) dS[(int64_t)node * H + head] = dSacc;
+}
+
+// dh[n] = G[n] + P[n] + dS[n] (x) a_side for rows whose partials (P in dh, dS) were reduced across ranks
+template <int H>
+__global__ void __launch_bounds__(256) stage_bwd_finalize_kernel(float* __restrict__ dh, const float* __restrict__ dS,
+                                                                 const float* __restrict__ G, const float* const* __restrict__ wtab,
+                                                                 int item_side, int64_t n_rows) {
+    constexpr int DH = D / H;
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (n >= n_rows) return;
+    const int lane16 = threadIdx.x & 15;
+    const int head = lane_head_b<H>(lane16);
+    const float d = dS[n * H + head];
+    const float* ap = wtab[2 * H + head] + (item_side ? DH : 0) + ((lane16 * 4) % DH);
+    const float4 p = ld_stream4(dh + n * D + lane16 * 4), g = ld_stream4(G + n * D + lane16 * 4);
+    st_stream4(dh + n * D + lane16 * 4, make_float4(g.x + p.x + d * __ldg(ap), g.y + p.y + d * __ldg(ap + 1), g.z + p.z + d * __ldg(ap + 2),
+                                                    g.w + p.w + d * __ldg(ap + 3)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -316,6 +338,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     if (idx >= 2 * TB_PART) return;
     const int side = idx / TB_PART, o = idx % TB_PART;
     const int b0 = side ? nb_u : 0, b1 = side ? nb_total : nb_u;
+    if (b1 <= b0) return;          // this call covered one side only (multi-GPU row sharding): leave the other side's gradients alone
     float sum = 0.f;
     for (int b = b0; b < b1; ++b) sum += partials[(size_t)b * TB_PART + o];
     float* dst;
@@ -335,7 +358,8 @@ using namespace ngacf;
 
 extern "C" int ngacf_stage_bwd_prep(const float* G, const float* Z, const float* h, const float* norm, int32_t H, int64_t N, float* Ghat,
                                     float* dN, void* stream) {
-    NGACF_REQUIRE(G && Z && h && norm && Ghat && dN && N > 0, "stage_bwd_prep: null/empty argument");
+    NGACF_REQUIRE(G && Z && h && norm && Ghat && dN && N >= 0, "stage_bwd_prep: null argument");
+    if (N == 0) return NGACF_OK;
     NGACF_REQUIRE(H == 1 || H == 8, "stage_bwd_prep: H must be 1 or 8");
     const int blocks = ceil_div(N * 16, 256);
     if (H == 8) stage_bwd_prep_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(G, Z, h, norm, N, Ghat, dN);
@@ -343,11 +367,22 @@ extern "C" int ngacf_stage_bwd_prep(const float* G, const float* Z, const float*
     return check_launch("stage_bwd_prep");
 }
 
+extern "C" int ngacf_stage_bwd_finalize(float* dh, const float* dS, const float* G, const float* const* wtab, int32_t H, int32_t item_side,
+                                        int64_t n_rows, void* stream) {
+    NGACF_REQUIRE(dh && dS && G && wtab && n_rows >= 0 && (H == 1 || H == 8), "stage_bwd_finalize: bad argument");
+    if (n_rows == 0) return NGACF_OK;
+    const int blocks = ceil_div(n_rows * 16, 256);
+    if (H == 8) stage_bwd_finalize_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(dh, dS, G, wtab, item_side, n_rows);
+    else        stage_bwd_finalize_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(dh, dS, G, wtab, item_side, n_rows);
+    return check_launch("stage_bwd_finalize");
+}
+
 extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end, const int32_t* adj_ptr,
                                      const int32_t* adj_idx, const int32_t* adj_eid, const int32_t* long_first_slot,
                                      int32_t* long_counter, float* scratch, const float* G, const float* Ghat, const float* dN,
                                      const float* h, const float* s, int32_t H, const uint8_t* edgemask, float scale,
-                                     const float* const* wtab, int32_t U, float* ds_store, float* dh, float* dS, void* stream) {
+                                     const float* const* wtab, int32_t U, float* ds_store, float* dh, float* dS, int32_t partial,
+                                     void* stream) {
     NGACF_REQUIRE(tasks && adj_ptr && adj_idx && adj_eid && G && Ghat && dN && h && s && wtab && ds_store && dh && dS,
                   "stage_bwd_edges: null argument");
     NGACF_REQUIRE((mode == 0 || mode == 1) && (H == 1 || H == 8) && T_end >= T_begin, "stage_bwd_edges: bad mode/H/range");
@@ -357,7 +392,7 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
     const int4* tk = reinterpret_cast<const int4*>(tasks);
 #define LAUNCH(HH, MM, DR)                                                                                                              \
     stage_bwd_edges_kernel<HH, MM, DR><<<blocks, 256, 0, st>>>(tk, T_begin, T_end, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, \
-                                                               scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS)
+                                                               scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS, partial)
     const bool dr = edgemask != nullptr;
     if (H == 8) {
         if (mode == 0) { if (dr) LAUNCH(8, 0, true); else LAUNCH(8, 0, false); }
@@ -373,9 +408,9 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
 static void transform_bwd_grid(int U, int I, int* nb_u, int* nb_i) {
     const int tiles_u = ceil_div(U, TB_TM), tiles_i = ceil_div(I, TB_TM);
     const int budget = 2 * 148;   // two resident CTAs per SM (86 KB of shared memory each)
-    int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i));
+    int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i > 0 ? tiles_u + tiles_i : 1));
     if (bu < 1) bu = 1;
-    if (bu > tiles_u) bu = tiles_u;
+    if (bu > tiles_u) bu = tiles_u;      // 0 when this call has no user rows
     int bi = budget - bu;
     if (bi < 1) bi = 1;
     if (bi > tiles_i) bi = tiles_i;
@@ -393,7 +428,9 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
                                    const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H,
                                    int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate_dx, int32_t accumulate_dw,
                                    void* workspace, size_t workspace_bytes, void* stream) {
-    NGACF_REQUIRE(dh && dS && h && Xu && Xi && wtab && gtab && dXu && dXi && workspace && U > 0 && I > 0, "transform_bwd: null/empty argument");
+    NGACF_REQUIRE(dh && dS && h && wtab && gtab && workspace && U >= 0 && I >= 0 && (U == 0 || (Xu && dXu)) && (I == 0 || (Xi && dXi)),
+                  "transform_bwd: null argument");
+    if (U + I == 0) return NGACF_OK;
     NGACF_REQUIRE(H == 1 || H == 8, "transform_bwd: H must be 1 or 8");
     if (workspace_bytes < ngacf_transform_bwd_workspace_bytes(U, I)) {
         set_error("transform_bwd: workspace too small");

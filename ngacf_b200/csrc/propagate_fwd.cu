@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
                                                             const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
                                                             const float* __restrict__ h, const float* __restrict__ s,
                                                             const uint8_t* __restrict__ edgemask, float scale,
-                                                            float* __restrict__ Z, float* __restrict__ norm) {
+                                                            float* __restrict__ Z, float* __restrict__ norm, int partial_from) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     if (t >= T) return;                                  // whole 16-lane groups exit together
     const int lane16 = threadIdx.x & 15;
@@ -253,6 +253,14 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
         if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         rs = sums[0];
     }
+    if (t >= partial_from) {
+        // multi-GPU: this rank only holds a slice of the row's edges -> emit the raw partial sums; they are summed
+        // across ranks (NCCL) and normalised by aggregate_finalize_kernel
+        st_stream4(Z + (int64_t)node * D + lane16 * 4, acc);
+        if (H == 8) { if ((lane16 & 1) == 0) norm[(int64_t)node * 8 + head] = rs; }
+        else        { if (lane16 == 0) norm[node] = rs; }
+        return;
+    }
     // epilogue: Z = h + agg / norm, NaN -> 0 for isolated nodes (SPUIGACF.py:383,388-390)
     const float inv = rs != 0.f ? 1.0f / rs : 0.f;
     const float4 hn = ld_stream4(h + (int64_t)node * D + lane16 * 4);
@@ -262,9 +270,32 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
     else        { if (lane16 == 0) norm[node] = rs; }
 }
 
+// Z[n] = h[n] + P[n] / norm[n] for rows whose partial sums P (stored in Z) were reduced across ranks
+template <int H>
+__global__ void __launch_bounds__(256) aggregate_finalize_kernel(float* __restrict__ Z, const float* __restrict__ h,
+                                                                 const float* __restrict__ norm, int64_t n_rows) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (n >= n_rows) return;
+    const int lane16 = threadIdx.x & 15;
+    const int head = H == 8 ? (lane16 >> 1) : 0;
+    const float rs = norm[n * H + head];
+    const float inv = rs != 0.f ? 1.0f / rs : 0.f;
+    const float4 p = ld_stream4(Z + n * D + lane16 * 4), hn = ld_stream4(h + n * D + lane16 * 4);
+    st_stream4(Z + n * D + lane16 * 4, make_float4(fmaf(p.x, inv, hn.x), fmaf(p.y, inv, hn.y), fmaf(p.z, inv, hn.z), fmaf(p.w, inv, hn.w)));
+}
+
 }  // namespace ngacf
 
 using namespace ngacf;
+
+extern "C" int ngacf_aggregate_finalize(float* Z, const float* h, const float* norm, int32_t H, int64_t n_rows, void* stream) {
+    NGACF_REQUIRE(Z && h && norm && n_rows >= 0 && (H == 1 || H == 8), "aggregate_finalize: bad argument");
+    if (n_rows == 0) return NGACF_OK;
+    const int blocks = ceil_div(n_rows * 16, 256);
+    if (H == 8) aggregate_finalize_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, h, norm, n_rows);
+    else        aggregate_finalize_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(Z, h, norm, n_rows);
+    return check_launch("aggregate_finalize");
+}
 
 extern "C" int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage,
                                   float droprate, void* stream) {
@@ -288,7 +319,8 @@ extern "C" int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t see
 
 extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
                                    const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream) {
-    NGACF_REQUIRE(Xu && Xi && wtab && h && s && U > 0 && I > 0, "transform_fwd: null/empty argument");
+    NGACF_REQUIRE(wtab && h && s && U >= 0 && I >= 0 && (U == 0 || Xu) && (I == 0 || Xi), "transform_fwd: null argument");
+    if (U + I == 0) return NGACF_OK;
     NGACF_REQUIRE(H == 1 || H == 8, "transform_fwd: H must be 1 or 8 (got %d)", H);
     const int tiles_u = ceil_div(U, TF_TM), tiles_i = ceil_div(I, TF_TM);
     static bool attr_done = false;
@@ -306,14 +338,16 @@ extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t app
 
 extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
                                    const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* h, const float* s,
-                                   int32_t H, const uint8_t* edgemask, float scale, float* Z, float* norm, void* stream) {
+                                   int32_t H, const uint8_t* edgemask, float scale, float* Z, float* norm, int32_t partial_from,
+                                   void* stream) {
     NGACF_REQUIRE(tasks && adj_ptr && adj_idx && h && s && Z && norm && T > 0, "aggregate_fwd: null/empty argument");
+    if (partial_from < 0) partial_from = T;
     NGACF_REQUIRE(H == 1 || H == 8, "aggregate_fwd: H must be 1 or 8 (got %d)", H);
     NGACF_REQUIRE(!edgemask || adj_eid, "aggregate_fwd: edge dropout needs adj_eid");
     const int blocks = ceil_div((int64_t)T * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
-#define LAUNCH(HH, DR) aggregate_fwd_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
+#define LAUNCH(HH, DR) aggregate_fwd_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm, partial_from)
     if (H == 8) { if (edgemask) LAUNCH(8, true); else LAUNCH(8, false); }
     else        { if (edgemask) LAUNCH(1, true); else LAUNCH(1, false); }
 #undef LAUNCH

@@ -107,11 +107,17 @@ __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __res
 
 // single-block loss: deterministic tree reduction
 __global__ void __launch_bounds__(1024) bpr_loss_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int B, float gscale,
-                                                        float* __restrict__ loss, float* __restrict__ dpos, float* __restrict__ dneg) {
+                                                        float* __restrict__ loss, float* __restrict__ dpos, float* __restrict__ dneg,
+                                                        const int64_t* __restrict__ users, int64_t u_lo, int64_t u_hi) {
     __shared__ float red[32];
     float local = 0.f;
     const float invB = 1.0f / (float)B;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        if (users && (users[b] < u_lo || users[b] >= u_hi)) {      // multi-GPU: the pair belongs to another rank's users
+            if (dpos) dpos[b] = 0.f;
+            if (dneg) dneg[b] = 0.f;
+            continue;
+        }
         const float x = pos[b] - neg[b];
         // -log(sigmoid(x)) = softplus(-x), stable form (BPRLoss.py:9 is the naive form)
         local += fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
@@ -265,8 +271,15 @@ extern "C" int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* u
 
 extern "C" int ngacf_bpr_loss(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg, void* stream) {
     NGACF_REQUIRE(pos && neg && B > 0, "bpr_loss: null/empty argument");
-    bpr_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos, neg, B, gscale, loss, dpos, dneg);
+    bpr_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos, neg, B, gscale, loss, dpos, dneg, nullptr, 0, 0);
     return check_launch("bpr_loss");
+}
+
+extern "C" int ngacf_bpr_loss_owned(const float* pos, const float* neg, int32_t B, float gscale, float* loss, float* dpos, float* dneg,
+                                    const int64_t* users, int64_t u_lo, int64_t u_hi, void* stream) {
+    NGACF_REQUIRE(pos && neg && users && B > 0, "bpr_loss_owned: null/empty argument");
+    bpr_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos, neg, B, gscale, loss, dpos, dneg, users, u_lo, u_hi);
+    return check_launch("bpr_loss_owned");
 }
 
 extern "C" int ngacf_adam_step(const uint64_t* tab, int32_t n_tensors, int64_t total_numel, float lr, float beta1, float beta2, float eps,

@@ -50,9 +50,22 @@ def transform_fwd(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s):
     _lib.call("ngacf_transform_fwd", _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab), H, U, I, _p(h), _p(s), _s())
 
 
-def aggregate_fwd(g: BipartiteGraph, scratch, counter, h, s, H, edgemask, scale, Z, norm):
+def aggregate_fwd(g: BipartiteGraph, scratch, counter, h, s, H, edgemask, scale, Z, norm, partial_from=-1):
     _lib.call("ngacf_aggregate_fwd", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid), _p(g.long_first_slot),
-              _p(counter), _p(scratch), _p(h), _p(s), H, _p(edgemask), float(scale), _p(Z), _p(norm), _s())
+              _p(counter), _p(scratch), _p(h), _p(s), H, _p(edgemask), float(scale), _p(Z), _p(norm), int(partial_from), _s())
+
+
+def aggregate_finalize(Z, h, norm, H):
+    _lib.call("ngacf_aggregate_finalize", _p(Z), _p(h), _p(norm), H, Z.shape[0], _s())
+
+
+def stage_bwd_finalize(dh, dS, G, wtab, H, item_side):
+    _lib.call("ngacf_stage_bwd_finalize", _p(dh), _p(dS), _p(G), _p(wtab), H, int(item_side), dh.shape[0], _s())
+
+
+def bpr_loss_owned(pos, neg, gscale, loss, dpos, dneg, users, u_lo, u_hi):
+    _lib.call("ngacf_bpr_loss_owned", _p(pos), _p(neg), pos.numel(), float(gscale), _p(loss), _p(dpos), _p(dneg), _p(users), int(u_lo),
+              int(u_hi), _s())
 
 
 def score_pairs(Z, U, users, items, out):
@@ -75,11 +88,11 @@ def stage_bwd_prep(G, Z, h, norm, H, Ghat, dN):
     _lib.call("ngacf_stage_bwd_prep", _p(G), _p(Z), _p(h), _p(norm), H, G.shape[0], _p(Ghat), _p(dN), _s())
 
 
-def stage_bwd_edges(mode, g: BipartiteGraph, scratch, counter, G, Ghat, dN, h, s, H, edgemask, scale, wtab, ds_store, dh, dS):
+def stage_bwd_edges(mode, g: BipartiteGraph, scratch, counter, G, Ghat, dN, h, s, H, edgemask, scale, wtab, ds_store, dh, dS, partial=0):
     t0, t1 = (0, g.T_users) if mode == 0 else (g.T_users, g.T)
     _lib.call("ngacf_stage_bwd_edges", mode, _p(g.tasks), t0, t1, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid),
               _p(g.long_first_slot), _p(counter), _p(scratch), _p(G), _p(Ghat), _p(dN), _p(h), _p(s), H, _p(edgemask),
-              float(scale), _p(wtab), g.U, _p(ds_store), _p(dh), _p(dS), _s())
+              float(scale), _p(wtab), g.U, _p(ds_store), _p(dh), _p(dS), int(partial), _s())
 
 
 def transform_bwd_workspace_bytes(U, I):
