@@ -77,7 +77,7 @@ __device__ __forceinline__ bool long_row_combine_b(int lid, int chunk, const int
     return true;
 }
 
-template <int H, int MODE, bool DROP>
+template <int H, int MODE, bool DROP, bool PARTIAL>
 __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
                                                               const int* __restrict__ adj_ptr, const int* __restrict__ adj_idx,
                                                               const int* __restrict__ adj_eid, const int* __restrict__ long_first_slot,
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
                                                               const float* __restrict__ h, const float* __restrict__ s,
                                                               const uint8_t* __restrict__ edgemask, float scale,
                                                               const float* const* __restrict__ wtab, int U,
-                                                              float* ds_store, float* __restrict__ dh, float* __restrict__ dS, int partial) {
+                                                              float* ds_store, float* __restrict__ dh, float* __restrict__ dS) {
     constexpr int DH = D / H;
     const int t = T_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     if (t >= T_end) return;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
             if (DROP) mk_l = edgemask[eid_l];
         }
         const int cnt = min(16, end - base);
-#pragma unroll 2
+#pragma unroll (MODE == 0 ? 4 : 8)
         for (int j = 0; j < cnt; ++j) {
             const int m = __shfl_sync(gm, m_l, j, 16);
             const int eid = __shfl_sync(gm, eid_l, j, 16);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
         if (!long_row_combine_b<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         dSacc = sums[0];
     }
-    if (partial) {     // multi-GPU: raw partial sums over this rank's slice of the row; reduced across ranks, then stage_bwd_finalize
+    if (PARTIAL) {     // multi-GPU: raw partial sums over this rank's slice of the row; reduced across ranks, then stage_bwd_finalize
         st_stream4(dh + (int64_t)node * D + lane16 * 4, acc);
         if (head_writer<H>(lane16)) dS[(int64_t)node * H + head] = dSacc;
         return;
@@ -390,16 +390,27 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
     const int blocks = ceil_div((int64_t)(T_end - T_begin) * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
-#define LAUNCH(HH, MM, DR)                                                                                                              \
-    stage_bwd_edges_kernel<HH, MM, DR><<<blocks, 256, 0, st>>>(tk, T_begin, T_end, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, \
-                                                               scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS, partial)
+#define CARVE(HH, MM, DR) cudaFuncSetAttribute(stage_bwd_edges_kernel<HH, MM, DR, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0)
+    static bool carve_done = false;
+    if (!carve_done) {
+        CARVE(8, 0, true); CARVE(8, 0, false); CARVE(8, 1, true); CARVE(8, 1, false);
+        CARVE(1, 0, true); CARVE(1, 0, false); CARVE(1, 1, true); CARVE(1, 1, false);
+        carve_done = true;
+    }
+#undef CARVE
+#define LAUNCH(HH, MM, DR, PA)                                                                                                              \
+    stage_bwd_edges_kernel<HH, MM, DR, PA><<<blocks, 256, 0, st>>>(tk, T_begin, T_end, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, \
+                                                                   scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS)
     const bool dr = edgemask != nullptr;
+    NGACF_REQUIRE(!(partial && mode == 0), "stage_bwd_edges: partial sums are produced by the item pass (mode 1) only");
     if (H == 8) {
-        if (mode == 0) { if (dr) LAUNCH(8, 0, true); else LAUNCH(8, 0, false); }
-        else           { if (dr) LAUNCH(8, 1, true); else LAUNCH(8, 1, false); }
+        if (mode == 0) { if (dr) LAUNCH(8, 0, true, false); else LAUNCH(8, 0, false, false); }
+        else if (partial) { if (dr) LAUNCH(8, 1, true, true); else LAUNCH(8, 1, false, true); }
+        else           { if (dr) LAUNCH(8, 1, true, false); else LAUNCH(8, 1, false, false); }
     } else {
-        if (mode == 0) { if (dr) LAUNCH(1, 0, true); else LAUNCH(1, 0, false); }
-        else           { if (dr) LAUNCH(1, 1, true); else LAUNCH(1, 1, false); }
+        if (mode == 0) { if (dr) LAUNCH(1, 0, true, false); else LAUNCH(1, 0, false, false); }
+        else if (partial) { if (dr) LAUNCH(1, 1, true, true); else LAUNCH(1, 1, false, true); }
+        else           { if (dr) LAUNCH(1, 1, true, false); else LAUNCH(1, 1, false, false); }
     }
 #undef LAUNCH
     return check_launch("stage_bwd_edges");

@@ -205,7 +205,7 @@ __device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* 
     return true;
 }
 
-template <int H, bool DROP>
+template <int H, bool DROP, bool PARTIAL>
 __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ adj_ptr,
                                                             const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
                                                             const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
         if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         rs = sums[0];
     }
-    if (t >= partial_from) {
+    if (PARTIAL && t >= partial_from) {
         // multi-GPU: this rank only holds a slice of the row's edges -> emit the raw partial sums; they are summed
         // across ranks (NCCL) and normalised by aggregate_finalize_kernel
         st_stream4(Z + (int64_t)node * D + lane16 * 4, acc);
@@ -347,9 +347,22 @@ extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_
     const int blocks = ceil_div((int64_t)T * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
-#define LAUNCH(HH, DR) aggregate_fwd_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm, partial_from)
-    if (H == 8) { if (edgemask) LAUNCH(8, true); else LAUNCH(8, false); }
-    else        { if (edgemask) LAUNCH(1, true); else LAUNCH(1, false); }
+    static bool carve_done = false;
+    if (!carve_done) {     // gather kernels use no shared memory: ask for the whole unified array as L1 (popular rows hit)
+        cudaFuncSetAttribute(aggregate_fwd_kernel<8, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(aggregate_fwd_kernel<8, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(aggregate_fwd_kernel<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(aggregate_fwd_kernel<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        carve_done = true;
+    }
+#define LAUNCH(HH, DR, PA) aggregate_fwd_kernel<HH, DR, PA><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm, partial_from)
+    if (partial_from < T) {
+        if (H == 8) { if (edgemask) LAUNCH(8, true, true); else LAUNCH(8, false, true); }
+        else        { if (edgemask) LAUNCH(1, true, true); else LAUNCH(1, false, true); }
+    } else {
+        if (H == 8) { if (edgemask) LAUNCH(8, true, false); else LAUNCH(8, false, false); }
+        else        { if (edgemask) LAUNCH(1, true, false); else LAUNCH(1, false, false); }
+    }
 #undef LAUNCH
     return check_launch("aggregate_fwd");
 }

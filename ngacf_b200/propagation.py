@@ -66,11 +66,15 @@ class Propagation:
         self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor]) -> torch.Tensor:
+    def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor], after_first_kernel=None) -> torch.Tensor:
+        """after_first_kernel: optional callback run right after the first (dense) kernel was enqueued -- the trainer uses it to
+        start the OTHER propagation one kernel later, so that its dense kernels overlap this one's gather kernels."""
         g = self.g
         Xu, Xi, act = uEmbd, iEmbd, 0
         for k, (H, _) in enumerate(self.stages):
             ops.transform_fwd(Xu, Xi, act, self.featmask[k], self.scale, wtabs[k], H, g.U, g.I, self.h[k], self.s[k])
+            if k == 0 and after_first_kernel is not None:
+                after_first_kernel()
             ops.aggregate_fwd(g, self.scratch, self.counter, self.h[k], self.s[k], H, self.edgemask[k], self.scale,
                               self.Z[k], self.norm[k])
             Xu, Xi, act = self.Z[k], self.Z[k][g.U:], 1
@@ -91,18 +95,25 @@ class Propagation:
         """(N,64) buffer the caller fills with dL/dZ_last (zero-filled by the caller as needed)."""
         return self._bwd_buffers()["G"][0]
 
-    def backward(self, G_last: torch.Tensor, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate: bool):
+    def backward(self, G_last: torch.Tensor, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate: bool, after_first_kernel=None,
+                 before_grads=None, after_grads=None):
         """G_last = dL/dZ_last (N,64).  Writes (accumulate=False) or adds (True) every parameter gradient:
-        embedding grads into dU/dI, attention grads through the pointer tables gtabs[k]."""
+        embedding grads into dU/dI, attention grads through the pointer tables gtabs[k].
+        before_grads(k)/after_grads(k) bracket the only kernels that touch the shared gradient buffers (stage k's
+        transform_bwd), so two propagations can run their backward passes on two streams."""
         g = self.g
         b = self._bwd_buffers()
         G = G_last
         for k in range(len(self.stages) - 1, -1, -1):
             H, _ = self.stages[k]
             ops.stage_bwd_prep(G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"])
+            if k == len(self.stages) - 1 and after_first_kernel is not None:
+                after_first_kernel()
             for mode in (0, 1):
                 ops.stage_bwd_edges(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
                                     self.edgemask[k], self.scale, wtabs[k], b["ds"], b["dh"], b["dS"])
+            if before_grads is not None:
+                before_grads(k)
             if k > 0:
                 Gprev = b["G"][1] if G is not b["G"][1] else b["G"][0]
                 ops.transform_bwd(b["dh"], b["dS"], self.h[k], self.Z[k - 1], self.Z[k - 1][g.U:], 1, self.featmask[k], self.scale,
@@ -111,6 +122,8 @@ class Propagation:
             else:
                 ops.transform_bwd(b["dh"], b["dS"], self.h[k], uEmbd, iEmbd, 0, self.featmask[k], self.scale, wtabs[k], gtabs[k],
                                   H, g.U, g.I, dU, dI, int(accumulate), int(accumulate), b["ws"])
+            if after_grads is not None:
+                after_grads(k)
 
 
 # ------------------------------------------------------------------------------------------------

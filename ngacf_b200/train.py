@@ -131,16 +131,31 @@ class FusedTrainer:
         items = (self.pos, self.neg)
         scores = (self.sc_pos, self.sc_neg)
 
-        def fwd(k):
+        side = self.side
+
+        def fwd(k, hook=None):
             self.props[k].set_dropout(droprate, seed, call0 + k, None, cd)
-            Z = self.props[k].forward(uE, iE, self.wtabs)
+            Z = self.props[k].forward(uE, iE, self.wtabs, hook)
             ops.score_pairs(Z, g.U, self.users[:b], items[k][:b], scores[k][:b])
-        if self.side is not None:
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                fwd(1)
-            fwd(0)
-            cur.wait_stream(self.side)
+        if side is not None:
+            # the neg propagation starts one kernel after the pos one: its dense transform then overlaps the pos gather
+            # kernel (FFMA-bound vs L2-fabric-bound), and so on down the two pipelines
+            ev = torch.cuda.Event()
+            side.wait_stream(cur)
+
+            def start_side():
+                ev.record(cur)
+            # masks of the side propagation do not depend on anything: issue them first
+            with torch.cuda.stream(side):
+                self.props[1].set_dropout(droprate, seed, call0 + 1, None, cd)
+            self.props[0].set_dropout(droprate, seed, call0, None, cd)
+            Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side)
+            ops.score_pairs(Z0, g.U, self.users[:b], items[0][:b], scores[0][:b])
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                Z1 = self.props[1].forward(uE, iE, self.wtabs)
+                ops.score_pairs(Z1, g.U, self.users[:b], items[1][:b], scores[1][:b])
+            cur.wait_stream(side)
         else:
             fwd(0)
             fwd(1)
@@ -151,20 +166,29 @@ class FusedTrainer:
             G = self.props[k].grad_in()
             G.zero_()
             ops.score_pairs_bwd(self.props[k].Z[-1], g.U, self.users[:b], items[k][:b], dsc[k][:b], G)
-        # the two backward passes accumulate into the same gradient buffers -> they run in order; the
-        # neg propagation's gradient scatter overlaps the pos backward on the side stream
-        if self.side is not None:
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
+        dU, dI = m.uEmbd.weight.grad, m.iEmbd.weight.grad
+        if side is not None:
+            # both backward passes run concurrently, one kernel apart; the only shared state is the gradient buffers, written by
+            # stage k's transform_bwd: pos writes, neg accumulates after it (event per stage)
+            S = len(self.props[0].stages)
+            evs = [torch.cuda.Event() for _ in range(S)]
+            ev_go = torch.cuda.Event()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
                 scatter(1)
             scatter(0)
+            self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False,
+                                   after_first_kernel=lambda: ev_go.record(cur), after_grads=lambda k: evs[k].record(cur))
+            with torch.cuda.stream(side):
+                side.wait_event(ev_go)
+                self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, True,
+                                       before_grads=lambda k: side.wait_event(evs[k]))
+            cur.wait_stream(side)
         else:
             scatter(0)
             scatter(1)
-        self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, False)
-        if self.side is not None:
-            cur.wait_stream(self.side)
-        self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, True)
+            self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False)
+            self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, True)
         if part == "compute":
             return
         self._reduce_grads()
