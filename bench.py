@@ -306,7 +306,11 @@ def main():
     top_avg_ms = top_ms_step / top_n
     achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
     step_bytes = roofline.step_bytes_compulsory(U, I, E, 2, B)
-    roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if args.workload == "gowalla" and os.path.exists(tpath):      # DRAM bytes per launch from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get(top_key, {}).get("dram_bytes_per_launch")
+    roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                 peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
                 share_of_step=top_ms_step / total_prof,
                 step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
