@@ -390,3 +390,98 @@ def test_config1_ml100k_two_epochs_vs_reference(golden):
         assert np.allclose(res[k], gz["eval/" + k], rtol=3e-2, atol=3e-3), (k, res[k], gz["eval/" + k])
     sd = model.state_dict()
     assert rel_err(sd["uEmbd.weight"].cpu().numpy(), gz["sd1/uEmbd.weight"]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes (configs 2-4): one real training step vs the oracle, and tc == exact evaluation
+# ------------------------------------------------------------------------------------------------
+FULL = {"gowalla": (29858, 40981, 1027370), "yelp2018": (31668, 38048, 1561406), "amazon-book": (52643, 91599, 2984108)}
+
+
+@pytest.mark.parametrize("shape", ["gowalla", "yelp2018", "amazon-book"])
+def test_full_size_training_step_and_eval(shape):
+    """At the BASELINE shapes: (1) one PairSampling step with dropout 0.2 -- loss and every gradient vs the fp32 oracle port
+    on the same sampled batch and the same Philox masks; (2) graph invariants; (3) AllNeg: the tensor-core path returns exactly
+    the ids/scores of the exact path for EVERY evaluated user, and metric sums agree."""
+    from ngacf_b200 import hostdata
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.evaluate import AllNegEvaluator
+    from ngacf_b200.loss import BPRLoss
+    from ngacf_b200.model import SPUIGACF
+    U, I, E = FULL[shape]
+    u, i = hostdata.synth_bipartite(U, I, E, 0)
+    (tu, ti), (su, si) = hostdata.split_per_user(u, i, U, 1)
+    torch.manual_seed(2019)
+    model = SPUIGACF(U, I, 64, [64, 64], 0.2)
+    with torch.no_grad():
+        model.uEmbd.weight.mul_(10.0)
+        model.iEmbd.weight.mul_(10.0)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).train()
+    model.drop_seed, model._call = 31, 0
+    adj = torch.from_numpy(np.stack([u, i])).to(DEV)
+    g = model.graph_for(adj)
+    # (2) graph invariants at full size
+    assert g.E == E
+    rp, cp = g.rowptr.cpu().numpy(), g.colptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == E and (np.diff(rp) >= 1).all() and cp[-1] == E and (np.diff(cp) >= 0).all()
+    ci = g.colidx.cpu().numpy()
+    assert np.array_equal(np.bincount(ci, minlength=I), np.diff(cp))
+    assert np.array_equal(np.sort(g.perm.cpu().numpy()), np.arange(E))
+    t = g.tasks.cpu().numpy()
+    assert int((t[:, 2] - t[:, 1]).sum()) == 2 * E and int((t[:, 2] - t[:, 1]).max()) <= 128
+    # (1) one step vs the oracle
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    B = 2048
+    lo = 4096
+    users, pos, neg = port.sample_pairs(it, lo, lo + B, 7, 0)
+    ut, pt, nt = (torch.from_numpy(x).to(DEV) for x in (users, pos, neg))
+    loss = BPRLoss()(model(ut, pt, g), model(ut, nt, g))
+    loss.backward()
+    pg = port.build_graph(np.stack([u, i]), U, I)
+    p = port.params_from_state_dict(sd, torch.float32)
+    mp, mn = port.dropout_masks(pg, 31, 0, 0.2), port.dropout_masks(pg, 31, 1, 0.2)
+    ref_loss, ref_grads, _, _ = port.train_step_grads(p, pg, users, pos, neg, mp, mn, 0.2)
+    assert abs(loss.item() - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    ref_sd = port.state_dict_from_params(ref_grads)
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), ref_sd[k].numpy()) < 2e-4, k
+    # (3) evaluation: tensor-core path == exact path, every user
+    dit = Interactions.from_arrays(U, I, tu, ti, su, si, device=DEV)
+    model.eval()
+    with torch.no_grad():
+        Z = model.propagate(g)
+        ev_tc, ev_ex = AllNegEvaluator(dit, "tc"), AllNegEvaluator(dit, "exact")
+        r_tc, r_ex = ev_tc(Z), ev_ex(Z)
+    assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
+    assert ev_tc.n_fallback <= dit.eval_users.numel() // 100
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        assert np.array_equal(r_tc[k], r_ex[k])
+
+
+def test_edge_cases_small_batches_and_single_edge_users():
+    """B=1, a batch made of one repeated user, users with exactly one edge, an item adjacent to every user."""
+    from ngacf_b200.loss import BPRLoss
+    from ngacf_b200.model import SPUIGACF
+    U, I = 40, 30
+    u = np.concatenate([np.arange(U), np.arange(U), np.arange(10)])
+    i = np.concatenate([np.zeros(U, np.int64), (np.arange(U) % 7) + 1, np.full(10, 20)])      # item 0 touches every user; users >= 10 have 2 edges
+    u, i = np.concatenate([u, [39]]), np.concatenate([i, [29]])
+    g = port.build_graph(np.stack([u, i]), U, I)
+    p64 = port.init_params(U, I, 11, torch.float64)
+    p64["uEmbd"] *= 30
+    p64["iEmbd"] *= 30
+    model = SPUIGACF(U, I, 64, [64, 64], 0.0)
+    model.load_state_dict({k: v.float() for k, v in port.state_dict_from_params(p64).items()})
+    model = model.to(DEV).train()
+    adj = torch.from_numpy(np.stack([u, i])).to(DEV)
+    for users, pos, neg in (([3], [0], [5]), ([7] * 9, [0, 1, 0, 1, 0, 1, 0, 1, 0], [9, 9, 9, 11, 11, 12, 13, 14, 15])):
+        model.zero_grad()
+        ut, pt, nt = (torch.tensor(x, device=DEV) for x in (users, pos, neg))
+        loss = BPRLoss()(model(ut, pt, adj), model(ut, nt, adj))
+        loss.backward()
+        ref_loss, ref_grads, _, _ = port.train_step_grads(p64, g, np.array(users), np.array(pos), np.array(neg))
+        assert abs(loss.item() - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+        ref_sd = port.state_dict_from_params(ref_grads)
+        for k, v in model.named_parameters():
+            assert rel_err(v.grad.cpu().numpy(), ref_sd[k].numpy()) < 1e-4, k
