@@ -263,7 +263,7 @@ class ShardedTrainer:
         self.dev = dev
         self.shard = UserShard(edge_u, edge_i, model.userNum, model.itemNum, self.rank, self.world, dev)
         self.g = self.shard.graph
-        self.props = [ShardedPropagation(self.shard), ShardedPropagation(self.shard)]
+        self.props = [ShardedPropagation(self.shard, model.stages), ShardedPropagation(self.shard, model.stages)]
         self.use_cuda_graph = use_cuda_graph
         i64, f32 = dict(dtype=torch.int64, device=dev), dict(dtype=torch.float32, device=dev)
         self.users, self.pos, self.neg = torch.zeros(self.B, **i64), torch.zeros(self.B, **i64), torch.zeros(self.B, **i64)

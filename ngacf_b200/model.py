@@ -61,17 +61,46 @@ class SpUIGAT(nn.Module):
                 [self.out_att.W_u, self.out_att.W_i, self.out_att.a]]
 
 
+class SPUIMultiGAT(nn.Module):
+    """attention1_0..7, attention2_0..7 (64->8, concat) + out_att (64->64): the 3-stage variant (SPUIGACF.py:217-256)."""
+
+    def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads):
+        super().__init__()
+        self.dropout = dropout
+        self.nheads = nheads
+        # the reference constructs all attentions1 layers, then all attentions2 layers, then registers them (same RNG order)
+        a1 = [SpUIGraphAttentionLayer(nfeat, nhid, dropout, alpha, True) for _ in range(nheads)]
+        a2 = [SpUIGraphAttentionLayer(nfeat, nhid, dropout, alpha, True) for _ in range(nheads)]
+        for k, l in enumerate(a1):
+            self.add_module("attention1_{}".format(k), l)
+        for k, l in enumerate(a2):
+            self.add_module("attention2_{}".format(k), l)
+        self.out_att = SpUIGraphAttentionLayer(nhid * nheads, nclass, dropout, alpha, False)
+
+    def stage_parameters(self):
+        out = []
+        for tag in ("attention1_", "attention2_"):
+            att = [getattr(self, tag + str(k)) for k in range(self.nheads)]
+            out.append([l.W_u for l in att] + [l.W_i for l in att] + [l.a for l in att])
+        out.append([self.out_att.W_u, self.out_att.W_i, self.out_att.a])
+        return out
+
+
 class SPUIGACF(nn.Module):
+    GAT = SpUIGAT
+    STAGES = ((8, 8), (1, 64))
+
     def __init__(self, userNum, itemNum, embedSize, layers, droprate, useCuda=True):
         super().__init__()
         if embedSize != 64:
             raise ValueError("the sm_100a kernels are specialised for embedSize 64 (every BASELINE config)")
         self.useCuda = useCuda
         self.userNum, self.itemNum, self.droprate = int(userNum), int(itemNum), float(droprate)
+        self.stages = tuple(self.STAGES)
         self.uEmbd = nn.Embedding(userNum, embedSize)
         self.iEmbd = nn.Embedding(itemNum, embedSize)
         # `layers` is accepted and ignored exactly as in the reference (SPUIGACF.py:7 is its only use)
-        self.gat = SpUIGAT(nfeat=embedSize, nhid=8, nclass=embedSize, dropout=droprate, nheads=8, alpha=ALPHA)
+        self.gat = self.GAT(nfeat=embedSize, nhid=8, nclass=embedSize, dropout=droprate, nheads=8, alpha=ALPHA)
         nn.init.normal_(self.uEmbd.weight, std=0.01)
         nn.init.normal_(self.iEmbd.weight, std=0.01)
         self.drop_seed = None       # Philox key of the dropout streams; defaults to torch.initial_seed()
@@ -112,7 +141,7 @@ class SPUIGACF(nn.Module):
             # eval mode: no autograd graph (the reference detaches every eval score, train_eval_Gowalla.py:334)
             key = tuple(p._version for p in [self.uEmbd.weight, self.iEmbd.weight] + params) + (id(graph), self.training)
             if key != self._eval_key:
-                prop = Propagation(graph)
+                prop = Propagation(graph, self.stages)
                 prop.set_dropout(0.0)
                 wtabs = [ops.pointer_table([p.detach() for p in st]) for st in self.gat.stage_parameters()]
                 self._eval_Z = prop.forward(self.uEmbd.weight.detach(), self.iEmbd.weight.detach(), wtabs)
@@ -122,9 +151,15 @@ class SPUIGACF(nn.Module):
         call = self._call
         self._call += 1
         injected, self.injected_masks = self.injected_masks, None
-        return PropagateFn.apply(graph, self.droprate if training else 0.0, self._seed(), call, injected,
+        return PropagateFn.apply(graph, self.droprate if training else 0.0, self._seed(), call, injected, self.stages,
                                  self.uEmbd.weight, self.iEmbd.weight, *params)
 
     def forward(self, userIdx, itemIdx, mask):
         Z = self.propagate(mask)
         return ScoreFn.apply(Z, self.userNum, userIdx.to(Z.device), itemIdx.to(Z.device))
+
+
+class SPUIMultiGACF(SPUIGACF):
+    """3-stage variant (SPUIGACF.py:54-101): two 8-head stages, then out_att.  Same kernels, one more entry in the stage list."""
+    GAT = SPUIMultiGAT
+    STAGES = ((8, 8), (8, 8), (1, 64))

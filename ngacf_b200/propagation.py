@@ -145,10 +145,11 @@ class PropagateFn(torch.autograd.Function):
     PairSampling step are alive together until loss.backward)."""
 
     @staticmethod
-    def forward(ctx, graph, droprate, seed, call, injected, uEmbd, iEmbd, *stage_params):
-        prop = Propagation(graph)
+    def forward(ctx, graph, droprate, seed, call, injected, stages, uEmbd, iEmbd, *stage_params):
+        prop = Propagation(graph, stages)
         prop.set_dropout(droprate, seed, call, injected)
-        per_stage = stage_param_lists([p.detach() for p in stage_params])
+        per_stage = stage_param_lists([p.detach() for p in stage_params], stages)
+        ctx.stages = stages
         wtabs = [ops.pointer_table(ps) for ps in per_stage]
         Z = prop.forward(uEmbd.detach(), iEmbd.detach(), wtabs)
         ctx.prop, ctx.wtabs = prop, wtabs
@@ -163,10 +164,10 @@ class PropagateFn(torch.autograd.Function):
         dU = torch.empty_like(ctx.uEmbd)
         dI = torch.empty_like(ctx.iEmbd)
         grads = [torch.empty(s, dtype=torch.float32, device=G.device) for s in ctx.shapes]
-        gtabs = [ops.pointer_table(gs) for gs in stage_param_lists(grads)]
+        gtabs = [ops.pointer_table(gs) for gs in stage_param_lists(grads, ctx.stages)]
         prop.backward(G, ctx.uEmbd, ctx.iEmbd, ctx.wtabs, gtabs, dU, dI, accumulate=False)
         ctx.prop = None
-        return (None, None, None, None, None, dU, dI, *grads)
+        return (None, None, None, None, None, None, dU, dI, *grads)
 
 
 class ScoreFn(torch.autograd.Function):

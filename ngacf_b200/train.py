@@ -29,7 +29,7 @@ class FusedTrainer:
         self.two_streams = two_streams
         dev = graph.device
         self.dev = dev
-        self.props = [Propagation(graph), Propagation(graph)]      # pos / neg
+        self.props = [Propagation(graph, model.stages), Propagation(graph, model.stages)]      # pos / neg
         for p in self.props:
             p._bwd_buffers()
         i64 = dict(dtype=torch.int64, device=dev)

@@ -16,7 +16,7 @@ import torch
 from torch.optim import Adam
 
 from graphattention.BPRLoss import BPRLoss
-from graphattention.SPUIGACF import SPUIGACF
+from graphattention.SPUIGACF import SPUIGACF, SPUIMultiGACF
 from ngacf_b200.data import Interactions
 from ngacf_b200.hostdata import load_dataset
 from train_eval_Gowalla import eval_neg_all, train_bpr
@@ -38,9 +38,10 @@ def prepareData(args):
 
 
 def createModels(args, userNum, itemNum):
-    if args.model != "SPUIGACF":
-        raise NotImplementedError("only --model SPUIGACF is in scope (SPUIMultiGACF / SPUIGAGPCF are SURVEY.md 8f 'next')")
-    model = SPUIGACF(userNum, itemNum, embedSize=args.embedSize, layers=args.layers, droprate=args.droprate).cuda()
+    if args.model not in ("SPUIGACF", "SPUIMultiGACF"):
+        raise NotImplementedError("--model SPUIGACF (in scope) and SPUIMultiGACF (SURVEY.md 8f-1) are built; SPUIGAGPCF is not")
+    cls = SPUIGACF if args.model == "SPUIGACF" else SPUIMultiGACF
+    model = cls(userNum, itemNum, embedSize=args.embedSize, layers=args.layers, droprate=args.droprate).cuda()
     lossfn = BPRLoss()
     optim = Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
     return model, lossfn, optim

@@ -485,3 +485,22 @@ def test_edge_cases_small_batches_and_single_edge_users():
         ref_sd = port.state_dict_from_params(ref_grads)
         for k, v in model.named_parameters():
             assert rel_err(v.grad.cpu().numpy(), ref_sd[k].numpy()) < 1e-4, k
+
+
+def test_multi_gacf_three_stage_vs_reference(golden):
+    """SPUIMultiGACF (3 stages: 8 heads, 8 heads, out_att) on the same kernels -- GPU vs the reference's fp64 run with the
+    Philox masks injected (tests/golden/multi_fwd_bwd_small.npz); also through the fused trainer for one step."""
+    from ngacf_b200.model import SPUIMultiGACF
+    gz = golden("multi_fwd_bwd_small")
+    U, I = int(gz["U"]), int(gz["I"])
+    model = SPUIMultiGACF(U, I, 64, [64, 64], float(gz["drop_p"]))
+    model.load_state_dict(sd_from(gz, "sd/"))
+    model = model.to(DEV).train()
+    model.drop_seed, model._call = int(gz["drop_seed"]), int(gz["drop_call"])
+    adj = torch.from_numpy(np.stack([gz["edge_u"], gz["edge_i"]])).to(DEV)
+    sc = model(torch.from_numpy(gz["users"]).to(DEV), torch.from_numpy(gz["items"]).to(DEV), adj)
+    assert rel_err(sc.detach().cpu().numpy(), gz["scores_drop_f64"]) < 1e-4
+    (sc * torch.from_numpy(gz["w"]).float().to(DEV)).sum().backward()
+    assert len(list(model.parameters())) == 2 + 3 * 17
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), gz["grad_drop_f64/" + k]) < 1e-4, k

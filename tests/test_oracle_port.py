@@ -257,3 +257,24 @@ def test_config1_ml100k_first_epoch_matches_reference(golden):
     loss, _ = port.train_bpr(p, g, it, int(gz["batch"]), st, float(gz["lr"]), float(gz["wd"]), 0, int(gz["sample_seed"]),
                              float(gz["droprate"]), int(gz["drop_seed"]), 0)
     assert abs(loss - gz["epoch_losses"][0]) < 1e-4 * gz["epoch_losses"][0]
+
+
+def test_multi_gacf_three_stage_matches_reference(golden):
+    """SPUIMultiGACF: the port's generic stage list vs the reference's 3-stage model, fp64, injected dropout."""
+    gz = golden("multi_fwd_bwd_small")
+    U, I = int(gz["U"]), int(gz["I"])
+    g = port.build_graph(np.stack([gz["edge_u"], gz["edge_i"]]), U, I)
+    p = port.params_from_state_dict(sd_from(gz, "sd/"), torch.float64)
+    assert len(p["stages"]) == 3
+    stages = [(8, 8), (8, 8), (1, 64)]
+    masks = port.dropout_masks(g, int(gz["drop_seed"]), int(gz["drop_call"]), float(gz["drop_p"]), stages)
+    F, caches = port.propagate(p, g, masks, float(gz["drop_p"]))
+    users, items, w = gz["users"], gz["items"], torch.from_numpy(gz["w"])
+    assert rel_err(port.scores(F, U, users, items).numpy(), gz["scores_drop_f64"]) < 1e-12
+    ut, itt = torch.from_numpy(users), torch.from_numpy(items) + U
+    dF = torch.zeros_like(F)
+    dF.index_add_(0, ut, w[:, None] * F[itt])
+    dF.index_add_(0, itt, w[:, None] * F[ut])
+    grads = port.state_dict_from_params(port.propagate_backward(dF, p, g, caches))
+    for k, v in grads.items():
+        assert rel_err(v.numpy(), gz["grad_drop_f64/" + k]) < 1e-11, k
