@@ -35,6 +35,11 @@ SHAPES = {   # U, I, E
     "amazon-book": (52643, 91599, 2984108),
     "ml100k-shape": (943, 1682, 100000),
     "tiny": (2000, 3000, 60000),
+    # BASELINE config 5: power-law scale sweep with Gowalla ratios (U = E/34.4, I = 1.37 U), SURVEY.md 8d
+    "sweep-3m": (87209, 119476, 3000000),
+    "sweep-10m": (290698, 398256, 10000000),
+    "sweep-30m": (872093, 1194767, 30000000),
+    "sweep-100m": (2906977, 3982558, 100000000),
 }
 HYPER = dict(lr=0.01, weight_decay=1e-6, droprate=0.2, batch=2048)   # README.md:27 of the reference
 
