@@ -307,7 +307,9 @@ def main():
     top_name, top_H = top_key.split("/H")[0], int(top_key.split("/H")[1]) if "/H" in top_key else 0
     n_params = sum(p.numel() for p in model.parameters())
     pk = peaks()
-    top_bytes = roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params)
+    gather = roofline.gather_regime(U, I) and top_name in ("ngacf_aggregate_fwd", "ngacf_stage_bwd_edges_users", "ngacf_stage_bwd_edges_items")
+    top_bytes = (roofline.kernel_bytes_gather(top_name, U, I, E, top_H or 1, True) if gather
+                 else roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params))
     top_avg_ms = top_ms_step / top_n
     achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
     step_bytes = roofline.step_bytes_compulsory(U, I, E, 2, B)
@@ -317,6 +319,7 @@ def main():
         traffic = json.load(open(tpath)).get(top_key, {}).get("dram_bytes_per_launch")
     roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                 peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
+                byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
                 share_of_step=top_ms_step / total_prof,
                 step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
                                 frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),

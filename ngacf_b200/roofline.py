@@ -30,6 +30,26 @@ def kernel_bytes(name: str, U: int, I: int, E: int, H: int, dropout: bool, B: in
     raise KeyError(name)
 
 
+GATHER_TABLE_L2_LIMIT = 63 * 2 ** 20     # above this the gathered table no longer stays L2-resident
+
+
+def gather_regime(U: int, I: int) -> bool:
+    return (U + I) * R > GATHER_TABLE_L2_LIMIT
+
+
+def kernel_bytes_gather(name: str, U: int, I: int, E: int, H: int, dropout: bool) -> int:
+    """Gather model (tables >> L2): every gathered 256-byte row and per-head scalar crosses HBM once per EDGE."""
+    N = U + I
+    sc = 4 * H
+    if name == "ngacf_aggregate_fwd":                     # 2E directed edges: row + scalar + index (+eid, mask)
+        return 2 * E * (R + sc + 4 + (5 if dropout else 0)) + 2 * N * R + 2 * N * sc
+    if name == "ngacf_stage_bwd_edges_users":             # E edges: Ghat row + h row + s + dN + idx + eid + ds write
+        return E * (2 * R + 2 * sc + 8 + sc + (1 if dropout else 0)) + 4 * U * R + 3 * U * sc
+    if name == "ngacf_stage_bwd_edges_items":             # E edges: Ghat row + s + idx + eid + ds read
+        return E * (R + sc + 8 + sc + (1 if dropout else 0)) + 2 * I * R + 2 * I * sc
+    raise KeyError(name)
+
+
 def step_bytes_compulsory(U: int, I: int, E: int, S: int = 2, B: int = 2048) -> int:
     """fwd_stage = 5 N r + 12 E, bwd_stage = 9 N r + 12 E,
     step = 2 S (fwd + bwd) + 7 N r (Adam) + 6 B r (BPR gather + scatter)."""
