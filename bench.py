@@ -289,7 +289,8 @@ def main():
     prof = trainer.profile_kernels(3)
     if not prof:      # sharded trainer: per-kernel timing is taken from the single-GPU run
         prof = [("ngacf_aggregate_fwd", tuple([None] * 10 + [8]), ms_step)]
-    hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10}
+    hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10,
+           "ngacf_transform_bwd_dx": 7, "ngacf_transform_bwd_dw": 9}
     agg = {}
     for name, args_, ms in prof:
         key = name

@@ -146,6 +146,18 @@ int ngacf_transform_bwd(const float* dh, const float* dS, const float* h, const 
                         int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate_dx, int32_t accumulate_dw,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same dense backward split in two, so that only dX sits on the backward dependency chain:
+ *   ngacf_transform_bwd_dx: dX = dh W^T (+ dropout mask, ELU' of the producer) -> G of the previous stage / embedding grads;
+ *   ngacf_transform_bwd_dw: dW = Xd^T dh and da (through V = Xd^T dS, so h is not re-read), accumulated into gtab; it is only
+ *   needed by the optimizer and is launched on a separate stream, overlapping the next stage's gather kernels. */
+int ngacf_transform_bwd_dx(const float* dh, const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
+                           const float* const* wtab, int32_t H, int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate,
+                           void* stream);
+size_t ngacf_transform_bwd_dw_workspace_bytes(int32_t U, int32_t I);
+int ngacf_transform_bwd_dw(const float* dh, const float* dS, const float* Xu, const float* Xi, int32_t apply_elu,
+                           const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H, int32_t U,
+                           int32_t I, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* (a13) Adam with L2 weight decay over a table of tensors (torch.optim.Adam semantics, run_Gowalla.py:114).
  * tab: device array of n entries {param, grad, exp_avg, exp_avg_sq, numel} (5 x 64-bit words each).
  * step_host is the 1-based step count (bias corrections computed on the host in double). */

@@ -35,6 +35,9 @@ SIGNATURES = {
     "ngacf_transform_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "ngacf_transform_bwd": (c_int32, [P, P, P, P, P, c_int32, P, c_float, P, P, c_int32, c_int32, c_int32, P, P, c_int32, c_int32,
                                       P, c_size_t, P]),
+    "ngacf_transform_bwd_dx": (c_int32, [P, P, P, c_int32, P, c_float, P, c_int32, c_int32, c_int32, P, P, c_int32, P]),
+    "ngacf_transform_bwd_dw_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "ngacf_transform_bwd_dw": (c_int32, [P, P, P, P, c_int32, P, c_float, P, P, c_int32, c_int32, c_int32, c_int32, P, c_size_t, P]),
     "ngacf_adam_step": (c_int32, [P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, P]),
     "ngacf_adam_step_dev": (c_int32, [P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
     "ngacf_sample_pairs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, P, P, P, P]),

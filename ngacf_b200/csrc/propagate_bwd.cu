@@ -329,18 +329,23 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
     if (threadIdx.x < 64) part[64 * 64 + threadIdx.x] = (red[threadIdx.x] + red[64 + threadIdx.x]) + (red[128 + threadIdx.x] + red[192 + threadIdx.x]);
 }
 
-// sums the block partials of each side in block order and writes the per-head gradient tensors
+// sums the block partials of each side and writes the per-head gradient tensors.  One CTA = 32 consecutive outputs x 8
+// groups of partials (coalesced 128-byte loads, fixed summation order -> deterministic)
 template <int H>
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nb_u, int nb_total, float* const* __restrict__ gtab,
-                                       int accumulate) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nb_u, int nb_total,
+                                                              float* const* __restrict__ gtab, int accumulate) {
     constexpr int DH = D / H;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 2 * TB_PART) return;
+    __shared__ float red[8][33];
+    const int og = threadIdx.x & 31, pg = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + og;                 // TB_PART is a multiple of 32
     const int side = idx / TB_PART, o = idx % TB_PART;
     const int b0 = side ? nb_u : 0, b1 = side ? nb_total : nb_u;
-    if (b1 <= b0) return;          // this call covered one side only (multi-GPU row sharding): leave the other side's gradients alone
     float sum = 0.f;
-    for (int b = b0; b < b1; ++b) sum += partials[(size_t)b * TB_PART + o];
+    for (int b = b0 + pg; b < b1; b += 8) sum += partials[(size_t)b * TB_PART + o];
+    red[pg][og] = sum;
+    __syncthreads();
+    if (pg != 0 || b1 <= b0) return;      // b1 <= b0: this call covered one side only (multi-GPU row sharding)
+    sum = ((red[0][og] + red[1][og]) + (red[2][og] + red[3][og])) + ((red[4][og] + red[5][og]) + (red[6][og] + red[7][og]));
     float* dst;
     if (o < 64 * 64) {
         const int k = o >> 6, c = o & 63;
@@ -459,10 +464,10 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
     float* partials = (float*)workspace;
     if (H == 8) {
         transform_bwd_kernel<8><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
-        reduce_partials_kernel<8><<<ceil_div(2 * TB_PART, 256), 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
+        reduce_partials_kernel<8><<<2 * TB_PART / 32, 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
     } else {
         transform_bwd_kernel<1><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
-        reduce_partials_kernel<1><<<ceil_div(2 * TB_PART, 256), 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
+        reduce_partials_kernel<1><<<2 * TB_PART / 32, 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
     }
     return check_launch("transform_bwd");
 }

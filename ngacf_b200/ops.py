@@ -104,6 +104,20 @@ def transform_bwd(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, gtab, H, 
               _p(gtab), H, U, I, _p(dXu), _p(dXi), int(accumulate_dx), int(accumulate_dw), _p(ws), ws.numel() * ws.element_size(), _s())
 
 
+def transform_bwd_dx(dh, Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, dXu, dXi, accumulate):
+    _lib.call("ngacf_transform_bwd_dx", _p(dh), _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab), H, U, I, _p(dXu), _p(dXi),
+              int(accumulate), _s())
+
+
+def transform_bwd_dw_workspace_bytes(U, I):
+    return int(_lib.load().ngacf_transform_bwd_dw_workspace_bytes(U, I))
+
+
+def transform_bwd_dw(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, gtab, H, U, I, accumulate, ws):
+    _lib.call("ngacf_transform_bwd_dw", _p(dh), _p(dS), _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab), _p(gtab), H, U, I,
+              int(accumulate), _p(ws), ws.numel() * ws.element_size(), _s())
+
+
 def adam_step(tab, n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, step):
     _lib.call("ngacf_adam_step", _p(tab), n_tensors, total_numel, lr, beta1, beta2, eps, weight_decay, int(step), _s())
 

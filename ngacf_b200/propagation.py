@@ -85,10 +85,14 @@ class Propagation:
         if self._bwd is None:
             dev, N, E = self.g.device, self.g.N, self.g.E
             f32 = dict(dtype=torch.float32, device=dev)
+            S = len(self.stages)
             self._bwd = dict(G=[torch.empty((N, D), **f32), torch.empty((N, D), **f32)], Ghat=torch.empty((N, D), **f32),
                              dh=torch.empty((N, D), **f32), dN=torch.empty((N, 8), **f32), dS=torch.empty((N, 8), **f32),
                              ds=torch.empty(max(E, 1) * 8, **f32),
-                             ws=torch.empty(ops.transform_bwd_workspace_bytes(self.g.U, self.g.I) // 4, **f32))
+                             ws=torch.empty(ops.transform_bwd_workspace_bytes(self.g.U, self.g.I) // 4, **f32),
+                             # split mode: per-stage dh/dS (the deferred dW kernel of stage k reads them while stage k-1 is running)
+                             dh_k=[torch.empty((N, D), **f32) for _ in range(S)], dS_k=[torch.empty((N, 8), **f32) for _ in range(S)],
+                             ws_k=[torch.empty(ops.transform_bwd_dw_workspace_bytes(self.g.U, self.g.I) // 4 + 16, **f32) for _ in range(S)])
         return self._bwd
 
     def grad_in(self) -> torch.Tensor:
@@ -96,11 +100,13 @@ class Propagation:
         return self._bwd_buffers()["G"][0]
 
     def backward(self, G_last: torch.Tensor, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate: bool, after_first_kernel=None,
-                 before_grads=None, after_grads=None):
+                 before_grads=None, after_grads=None, dw_launcher=None):
         """G_last = dL/dZ_last (N,64).  Writes (accumulate=False) or adds (True) every parameter gradient:
         embedding grads into dU/dI, attention grads through the pointer tables gtabs[k].
         before_grads(k)/after_grads(k) bracket the only kernels that touch the shared gradient buffers (stage k's
-        transform_bwd), so two propagations can run their backward passes on two streams."""
+        transform_bwd), so two propagations can run their backward passes on two streams.
+        dw_launcher(k, fn): split mode -- only dX stays on this chain; fn (the dW/da kernel of stage k, needed by the optimizer
+        only) is handed to the caller, which runs it on another stream once this stream reached the current point."""
         g = self.g
         b = self._bwd_buffers()
         G = G_last
@@ -109,9 +115,25 @@ class Propagation:
             ops.stage_bwd_prep(G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"])
             if k == len(self.stages) - 1 and after_first_kernel is not None:
                 after_first_kernel()
+            dh, dS = (b["dh_k"][k], b["dS_k"][k]) if dw_launcher is not None else (b["dh"], b["dS"])
             for mode in (0, 1):
                 ops.stage_bwd_edges(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
-                                    self.edgemask[k], self.scale, wtabs[k], b["ds"], b["dh"], b["dS"])
+                                    self.edgemask[k], self.scale, wtabs[k], b["ds"], dh, dS)
+            if dw_launcher is not None:
+                Xu, Xi, act = (self.Z[k - 1], self.Z[k - 1][g.U:], 1) if k > 0 else (uEmbd, iEmbd, 0)
+                dw_launcher(k, lambda k=k, H=H, dh=dh, dS=dS, Xu=Xu, Xi=Xi, act=act: ops.transform_bwd_dw(
+                    dh, dS, Xu, Xi, act, self.featmask[k], self.scale, wtabs[k], gtabs[k], H, g.U, g.I, int(accumulate), b["ws_k"][k]))
+                if before_grads is not None:
+                    before_grads(k)
+                if k > 0:
+                    Gprev = b["G"][1] if G is not b["G"][1] else b["G"][0]
+                    ops.transform_bwd_dx(dh, Xu, Xi, 1, self.featmask[k], self.scale, wtabs[k], H, g.U, g.I, Gprev, Gprev[g.U:], 0)
+                    G = Gprev
+                else:
+                    ops.transform_bwd_dx(dh, None, None, 0, self.featmask[k], self.scale, wtabs[k], H, g.U, g.I, dU, dI, int(accumulate))
+                if after_grads is not None:
+                    after_grads(k)
+                continue
             if before_grads is not None:
                 before_grads(k)
             if k > 0:

@@ -21,6 +21,10 @@ def kernel_bytes(name: str, U: int, I: int, E: int, H: int, dropout: bool, B: in
         return (U + 2 * I) * R + 2 * sc + 2 * E * 4 + E * H * 4 + (E if dropout else 0)
     if name == "ngacf_transform_bwd":
         return 4 * N * R + sc + (N * 8 if dropout else 0)                       # dh, X, h -> dX ; dS
+    if name == "ngacf_transform_bwd_dx":
+        return 3 * N * R + (N * 8 if dropout else 0)                            # dh, Zprev (ELU') -> dX
+    if name == "ngacf_transform_bwd_dw":
+        return 2 * N * R + sc + (N * 8 if dropout else 0)                       # dh, X (recomputed input), dS
     if name == "ngacf_adam_step_dev":
         return 7 * n_params * 4
     if name == "ngacf_score_pairs_bwd":

@@ -257,8 +257,8 @@ def test_adam_matches_torch():
     b.load_state_dict(sd)          # state layout is torch.optim.Adam's (checkpoint compatibility)
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_train_epochs_vs_reference(golden, fused):
+@pytest.mark.parametrize("fused", [False, True, "split"])
+def test_train_epochs_vs_reference(golden, fused, monkeypatch):
     """Two PairSampling epochs (dropout 0.2, Adam, GPU sampler + GPU Philox masks) vs the reference run that
     had the same samples and masks injected (tests/golden/train_eval_small.npz)."""
     import train_eval_Gowalla as T
@@ -266,6 +266,9 @@ def test_train_epochs_vs_reference(golden, fused):
     from ngacf_b200.loss import BPRLoss
     from ngacf_b200.optim import FusedAdam
     gz = golden("train_eval_small")
+    if fused == "split":       # dX / dW split kernels with the weight gradients deferred to a third stream
+        monkeypatch.setenv("NGACF_SPLIT_DENSE_BWD", "1")
+        fused = True
     model = make_model(gz, "sd0/", float(gz["droprate"]))
     U, I = int(gz["U"]), int(gz["I"])
     dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)

@@ -87,7 +87,8 @@ def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is
         tr = getattr(m, "_trainer", None)
         key = (id(inter), id(graph), int(batch_size), id(optim), int(sample_seed))
         if tr is None or tr.key != key:
-            tr = FusedTrainer(m, inter, graph, batch_size, optim, sample_seed)
+            tr = FusedTrainer(m, inter, graph, batch_size, optim, sample_seed,
+                              split_dense_backward=os.environ.get("NGACF_SPLIT_DENSE_BWD", "0") == "1")
             tr.key = key
             m._trainer = tr
         return tr.train_epoch(epoch, max_steps)
