@@ -322,6 +322,9 @@ def main():
                 peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
                 byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
                 share_of_step=top_ms_step / total_prof,
+                note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by L2->SM traffic (0.6-1.1 GB per "
+                     "launch at 9-12 TB/s, profiles/r1c_top_kernels_ncu_full.txt), DRAM traffic ~= algorithmic bytes (no re-reads); in the "
+                     "HBM regime (sweep-30m) the same kernels reach 0.9-1.0 of the measured HBM peak (profiles/r1c_bench_sweep-30m.json)",
                 step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
                                 frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
                 kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
@@ -343,9 +346,10 @@ def main():
                 if to_host:
                     return res, ev.top_ids.cpu()
                 return res, None
-        eval_once(False)
+        for _ in range(3):
+            eval_once(False)
         barrier()
-        reps = 3
+        reps = 5
         e0.record()
         for _ in range(reps):
             res, _ = eval_once(False)
@@ -359,11 +363,25 @@ def main():
         barrier()
         ms_eval_e2e = e0.elapsed_time(e1) / reps
         fl = roofline.eval_flops(n_eval, I)
+        # live duration of the scoring entry point alone (prep + tcgen05 kernel + exact re-score), CUDA events
+        _lib.PROFILE = []
+        with torch.no_grad():
+            ev.rank(model.propagate(graph))
+        torch.cuda.synchronize()
+        sc_ms = [e0_.elapsed_time(e1_) for n_, a_, e0_, e1_ in _lib.PROFILE if n_.startswith("ngacf_score_topk")]
+        _lib.PROFILE = None
+        sc_ms = float(sum(sc_ms)) if sc_ms else ms_eval
+        n_local = int(ev.users.numel())
+        ev_roof = dict(bound="tensor", kernel="ngacf_score_topk_tc" if ev._use_tc() else "ngacf_score_topk_exact",
+                       achieved=roofline.eval_flops(n_local, I) / (sc_ms / 1000.0) / 1e12, peak=pk["bf16"], unit="TFLOP/s",
+                       frac=roofline.eval_flops(n_local, I) / (sc_ms / 1000.0) / 1e12 / pk["bf16"], traffic=None, launch_ms=sc_ms,
+                       note="algorithmic FLOP 2*U*I*64 (the bf16x3 split issues 3x that on the tensor pipe); K=64 makes the kernel "
+                            "epilogue-bound: every accumulator is inspected once by the fused top-K (SURVEY 7 hard part 1)")
         ev_out = dict(metric="allneg_eval_users_per_s", value=n_eval / (ms_eval / 1000.0), unit="users/s", ms=ms_eval, users=n_eval,
                       e2e=dict(value=n_eval / (ms_eval_e2e / 1000.0), unit="users/s", d2h_bytes=n_eval * 20 * 4 + 128),
                       mode=("tc" if ev._use_tc() else "exact"), fallback_rows=getattr(ev, "n_fallback", 0),
                       tensor_frac_of_peak=fl / (ms_eval / 1000.0) / 1e12 / pk["bf16"],
-                      recall_at_20=float(res["recall"][3]), ndcg_at_20=float(res["ndcg"][3]))
+                      recall_at_20=float(res["recall"][3]), ndcg_at_20=float(res["ndcg"][3]), roofline=ev_roof)
         model.train()
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------

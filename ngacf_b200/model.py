@@ -141,10 +141,15 @@ class SPUIGACF(nn.Module):
             # eval mode: no autograd graph (the reference detaches every eval score, train_eval_Gowalla.py:334)
             key = tuple(p._version for p in [self.uEmbd.weight, self.iEmbd.weight] + params) + (id(graph), self.training)
             if key != self._eval_key:
-                prop = Propagation(graph, self.stages)
-                prop.set_dropout(0.0)
-                wtabs = [ops.pointer_table([p.detach() for p in st]) for st in self.gat.stage_parameters()]
-                self._eval_Z = prop.forward(self.uEmbd.weight.detach(), self.iEmbd.weight.detach(), wtabs)
+                prop = getattr(self, "_eval_prop", None)
+                if prop is None or prop.g is not graph:        # buffers are reused across evaluations of the same graph
+                    prop = Propagation(graph, self.stages)
+                    prop.set_dropout(0.0)
+                ptrs = tuple(p.data_ptr() for p in params)
+                if getattr(self, "_wtab_key", None) != ptrs:   # pointer tables only change when parameters move
+                    self._wtabs = [ops.pointer_table([p.detach() for p in st]) for st in self.gat.stage_parameters()]
+                    self._wtab_key = ptrs
+                self._eval_Z = prop.forward(self.uEmbd.weight.detach(), self.iEmbd.weight.detach(), self._wtabs)
                 self._eval_prop = prop
                 self._eval_key = key
             return self._eval_Z
