@@ -68,6 +68,10 @@ int ngacf_graph_build(const int64_t* coo_u, const int64_t* coo_i, int64_t E_in, 
  * ------------------------------------------------------------------------------------------- */
 int ngacf_feature_mask(uint64_t* feat, int64_t N, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage, float droprate, void* stream);
 int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t call, const int64_t* call_dev, uint32_t stage, float droprate, void* stream);
+/* all S stages of one propagation in ONE launch: feat/edge/heads are HOST arrays of S entries (device pointers / head counts);
+ * stage k uses Philox sites 2k / 2k+1 -- identical bits to S pairs of the two calls above. */
+int ngacf_dropout_masks(uint64_t* const* feat, uint8_t* const* edge, const int32_t* heads, int32_t S, int64_t N, int64_t E,
+                        uint64_t seed, uint32_t call, const int64_t* call_dev, float droprate, void* stream);
 /* call_dev (may be NULL): device-resident int64 added to `call` at run time; likewise ngacf_sample_pairs'
  * row_dev = int64[2] {added to row_begin, added to epoch}.  A CUDA graph captured once then replays with
  * advancing dropout streams, train rows and epochs. */

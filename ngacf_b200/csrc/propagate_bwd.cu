@@ -78,7 +78,7 @@ __device__ __forceinline__ bool long_row_combine_b(int lid, int chunk, const int
 }
 
 template <int H, int MODE, bool DROP, bool PARTIAL>
-__global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
+__global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
                                                               const int* __restrict__ adj_ptr, const int* __restrict__ adj_idx,
                                                               const int* __restrict__ adj_eid, const int* __restrict__ long_first_slot,
                                                               int* long_counter, float* scratch, const float* __restrict__ G,
@@ -106,14 +106,22 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float dSacc = 0.f;
+    // software-pipelined adjacency: batch b+1's neighbour/edge ids are requested before batch b's gathers, its mask bytes
+    // right after them (same scheme as aggregate_fwd_kernel)
+    int m_l = 0, eid_l = 0;
+    unsigned mk_l = 0xFFu;
+    if (beg + lane16 < end) {
+        m_l = ld_stream_i32(adj_idx + beg + lane16);
+        eid_l = ld_stream_i32(adj_eid + beg + lane16);
+        if (DROP) mk_l = edgemask[eid_l];
+    }
     for (int base = beg; base < end; base += 16) {
-        const int idx = base + lane16;
-        int m_l = 0, eid_l = 0;
-        unsigned mk_l = 0xFFu;
-        if (idx < end) {
-            m_l = ld_stream_i32(adj_idx + idx);
-            eid_l = ld_stream_i32(adj_eid + idx);
-            if (DROP) mk_l = edgemask[eid_l];
+        const int nidx = base + 16 + lane16;
+        int m_n = 0, eid_n = 0;
+        unsigned mk_n = 0xFFu;
+        if (nidx < end) {
+            m_n = ld_stream_i32(adj_idx + nidx);
+            eid_n = ld_stream_i32(adj_eid + nidx);
         }
         const int cnt = min(16, end - base);
 #pragma unroll (MODE == 0 ? 4 : 8)
@@ -146,6 +154,8 @@ __global__ void __launch_bounds__(256) stage_bwd_edges_kernel(const int4* __rest
             }
             dSacc += ds;
         }
+        if (DROP && nidx < end) mk_n = edgemask[eid_n];
+        m_l = m_n; eid_l = eid_n; mk_l = mk_n;
     }
     if (lid >= 0) {
         float sums[1] = {dSacc};

@@ -53,6 +53,48 @@ __global__ void edge_mask_kernel(uint8_t* __restrict__ out, int64_t E, int H, ui
     out[e] = (uint8_t)(bits & ((1u << H) - 1u));
 }
 
+// every mask of one propagation in a single launch: the grid is the concatenation of the per-stage
+// feature blocks and edge blocks (same per-element streams as the two kernels above)
+constexpr int MASK_MAX_STAGES = 8;
+struct MaskPlan {
+    uint64_t* feat[MASK_MAX_STAGES];
+    uint8_t* edge[MASK_MAX_STAGES];
+    int heads[MASK_MAX_STAGES];
+    int S;
+    int feat_blocks, edge_blocks;   // per stage
+};
+
+__global__ void __launch_bounds__(256) dropout_masks_kernel(MaskPlan plan, int64_t N, int64_t E, uint32_t k0, uint32_t k1, uint32_t call,
+                                                            const int64_t* __restrict__ call_dev, uint32_t thr) {
+    if (call_dev) call += (uint32_t)*call_dev;
+    int b = blockIdx.x;
+    const int per_stage = plan.feat_blocks + plan.edge_blocks;
+    const int site = b / per_stage;     // = stage; Philox sites are 2*stage (features) and 2*stage+1 (edges)
+    b -= site * per_stage;
+    uint32_t w[4];
+    if (b < plan.feat_blocks) {
+        const int64_t t = (int64_t)b * 256 + threadIdx.x;
+        const int64_t n = t >> 3;
+        const int c = (int)(t & 7);
+        uint32_t bits = 0;
+        if (n < N) {
+            const uint64_t idx = (uint64_t)n * 8u + (uint64_t)c;
+            philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)site * 2u, call, k0, k1, w);
+            bits = decisions8(w, thr);
+        }
+        uint64_t word = (uint64_t)bits << (8 * c);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if (n < N && c == 0) plan.feat[site][n] = word;
+    } else {
+        const int64_t e = (int64_t)(b - plan.feat_blocks) * 256 + threadIdx.x;
+        if (e >= E) return;
+        philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)site * 2u + 1u, call, k0, k1, w);
+        plan.edge[site][e] = (uint8_t)(decisions8(w, thr) & ((1u << plan.heads[site]) - 1u));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense transform: h = Xd @ Wcat, s = per-head a . h
 // block = 256 threads, tile = 128 rows of one side; thread = 8 rows x 4 columns
@@ -222,13 +264,33 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
     const float sn = __ldg(s + (int64_t)node * H + head);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 0.f;
+    // H=1: the adjacency slice of batch b+1 (and its edge ids) is requested before batch b's gathers and the mask bytes right
+    // after them, so the only dependent round trips on a row's chain are the gathers.  Measured per instantiation (in-box A/B,
+    // profiles/r1e_ab_prefetch.txt): helps <1,*>, hurts <8,*> (registers), hence the compile-time switch.
+    constexpr bool PF = (H == 1);
+    int m_l = 0, eid_n = 0;
+    unsigned mk_l = 0xFFu;
+    if (PF && beg + lane16 < end) {
+        m_l = ld_stream_i32(adj_idx + beg + lane16);
+        if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + beg + lane16)];
+    }
     for (int base = beg; base < end; base += 16) {
-        const int idx = base + lane16;
-        int m_l = 0;
-        unsigned mk_l = 0xFFu;
-        if (idx < end) {
-            m_l = ld_stream_i32(adj_idx + idx);
-            if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + idx)];
+        const int nidx = base + 16 + lane16;
+        int m_n = 0;
+        unsigned mk_n = 0xFFu;
+        if (PF) {
+            if (nidx < end) {
+                m_n = ld_stream_i32(adj_idx + nidx);
+                if (DROP) eid_n = ld_stream_i32(adj_eid + nidx);
+            }
+        } else {
+            const int idx = base + lane16;
+            m_l = 0;
+            mk_l = 0xFFu;
+            if (idx < end) {
+                m_l = ld_stream_i32(adj_idx + idx);
+                if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + idx)];
+            }
         }
         const int cnt = min(16, end - base);
 #pragma unroll 4
@@ -245,6 +307,10 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
             }
             acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
             acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
+        }
+        if (PF) {
+            if (DROP && nidx < end) mk_n = edgemask[eid_n];
+            m_l = m_n; mk_l = mk_n;
         }
     }
     if (lid >= 0) {
@@ -315,6 +381,24 @@ extern "C" int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t see
     edge_mask_kernel<<<ceil_div(E, 256), 256, 0, (cudaStream_t)stream>>>(edge, E, H, (uint32_t)seed, (uint32_t)(seed >> 32), call,
                                                                           call_dev, stage * 2 + 1, thr);
     return check_launch("edge_mask");
+}
+
+extern "C" int ngacf_dropout_masks(uint64_t* const* feat, uint8_t* const* edge, const int32_t* heads, int32_t S, int64_t N, int64_t E,
+                                   uint64_t seed, uint32_t call, const int64_t* call_dev, float droprate, void* stream) {
+    NGACF_REQUIRE(feat && edge && heads && S >= 1 && S <= MASK_MAX_STAGES && N >= 0 && E >= 0, "dropout_masks: bad args");
+    MaskPlan plan;
+    for (int k = 0; k < S; ++k) {
+        NGACF_REQUIRE(feat[k] && (edge[k] || E == 0) && (heads[k] == 1 || heads[k] == 8), "dropout_masks: bad stage %d", k);
+        plan.feat[k] = feat[k]; plan.edge[k] = edge[k]; plan.heads[k] = heads[k];
+    }
+    plan.S = S;
+    plan.feat_blocks = ceil_div(N * 8, 256);
+    plan.edge_blocks = ceil_div(E, 256);
+    const int64_t blocks = (int64_t)S * (plan.feat_blocks + plan.edge_blocks);
+    if (blocks == 0) return NGACF_OK;
+    dropout_masks_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plan, N, E, (uint32_t)seed, (uint32_t)(seed >> 32), call,
+                                                                             call_dev, keep_threshold(droprate));
+    return check_launch("dropout_masks");
 }
 
 extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,

@@ -174,9 +174,7 @@ class ShardedPropagation:
             self.featmask, self.edgemask, self.scale = [None] * S, [None] * S, 1.0
             return
         self.scale = 1.0 / (1.0 - droprate)
-        for k, (H, _) in enumerate(self.p.stages):
-            ops.feature_mask(self._fm[k], seed, call, k, droprate, call_dev)
-            ops.edge_mask(self._em[k][:self.sh.E], H, seed, call, k, droprate, call_dev)
+        ops.dropout_masks(self._fm, self._em, [H for H, _ in self.p.stages], self.sh.graph.N, self.sh.E, seed, call, droprate, call_dev)
         self.featmask = list(self._fm)
         self.edgemask = [m[self.sh.edge_offset:] for m in self._em]       # local edge id + offset = global edge id
 

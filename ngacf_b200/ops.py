@@ -3,6 +3,8 @@ devices/dtypes, passes raw pointers + the current CUDA stream, and never allocat
 (so everything here can be captured in a CUDA graph).  No CPU path exists."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -44,6 +46,15 @@ def edge_mask(out, H, seed, call, stage, droprate, call_dev=None):
 
 def counter_add(counter, delta):
     _lib.call("ngacf_counter_add", _p(counter), int(delta), _s())
+
+
+def dropout_masks(feats, edges, heads, N, E, seed, call, droprate, call_dev=None):
+    """every stage's feature + edge mask of one propagation in a single launch (same bits as feature_mask/edge_mask per stage)"""
+    S = len(heads)
+    fa = (ctypes.c_void_p * S)(*[f.data_ptr() for f in feats])
+    ea = (ctypes.c_void_p * S)(*[e.data_ptr() for e in edges])
+    ha = (ctypes.c_int32 * S)(*[int(h) for h in heads])
+    _lib.call("ngacf_dropout_masks", fa, ea, ha, S, int(N), int(E), int(seed), int(call) & 0xFFFFFFFF, _p(call_dev), float(droprate), _s())
 
 
 def transform_fwd(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s):

@@ -60,9 +60,7 @@ class Propagation:
             self.edgemask = [m.contiguous() for m in injected["edge"]]
             return
         fm, em = self._mask_buffers()
-        for k, (H, _) in enumerate(self.stages):
-            ops.feature_mask(fm[k], seed, call, k, droprate, call_dev)
-            ops.edge_mask(em[k][:self.g.E], H, seed, call, k, droprate, call_dev)
+        ops.dropout_masks(fm, em, [H for H, _ in self.stages], self.g.N, self.g.E, seed, call, droprate, call_dev)
         self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
 
     # ------------------------------------------------------------------------------------------

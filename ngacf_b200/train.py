@@ -227,7 +227,7 @@ class FusedTrainer:
     def launches_per_step(self, droprate: float) -> int:
         """Number of OUR kernels launched per step (bench.py's gpu_launches claim)."""
         S = len(self.props[0].stages)
-        per_prop_fwd = (2 * S if droprate > 0 else 0) + 2 * S + 1          # masks, transform+aggregate, score
+        per_prop_fwd = (1 if droprate > 0 else 0) + 2 * S + 1              # masks (one launch), transform+aggregate, score
         per_prop_bwd = 1 + S * (1 + 2 + (4 if self.split_dense_backward else 2))   # scatter, prep + 2 edge passes + dense backward
         return 1 + 2 * (per_prop_fwd + per_prop_bwd) + 1 + 2 + 2             # sampler, ..., loss, adam(2), counters(2)
 

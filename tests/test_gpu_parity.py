@@ -95,6 +95,14 @@ def test_dropout_masks_bit_exact(p):
         ops.edge_mask(em, H, 0x1234567890ABCDEF, 7, stage, p)
         assert np.array_equal(fm.cpu().numpy().view(np.uint64), port.feature_mask_bits(N, 0x1234567890ABCDEF, 7, stage, p))
         assert np.array_equal(em.cpu().numpy(), port.edge_mask_bits(E, H, 0x1234567890ABCDEF, 7, stage, p))
+    # the single-launch form the propagation uses: all stages at once, same bits (three stages = SPUIMultiGACF)
+    heads = (8, 8, 1)
+    fms = [torch.empty(N, dtype=torch.int64, device=DEV) for _ in heads]
+    ems = [torch.empty(E, dtype=torch.uint8, device=DEV) for _ in heads]
+    ops.dropout_masks(fms, ems, heads, N, E, 0x1234567890ABCDEF, 7, p)
+    for stage, H in enumerate(heads):
+        assert np.array_equal(fms[stage].cpu().numpy().view(np.uint64), port.feature_mask_bits(N, 0x1234567890ABCDEF, 7, stage, p))
+        assert np.array_equal(ems[stage].cpu().numpy(), port.edge_mask_bits(E, H, 0x1234567890ABCDEF, 7, stage, p))
 
 
 def make_interactions(U, I, E, seed):
