@@ -194,17 +194,23 @@ __global__ void __launch_bounds__(256) stage_bwd_finalize_kernel(float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense backward: dX = dh W^T (+ mask/ELU'), partial dW = Xd^T dh, partial da = sum dS (x) h
-// persistent blocks per side; deterministic two-pass reduction of the partials
+// dense backward: dX = dh W^T (+ mask/ELU'), partial dW = Xd^T dh, partial da = W^T-contracted Q = Xd^T dS
+// persistent blocks per side, 64-row tiles, three CTAs per SM; deterministic two-pass reduction of the partials.
+//   * h = Xd W, hence da[c] = sum_r dS[r,head(c)] h[r,c] = sum_k W[k,c] Q[k,head(c)]: the h tile is never read
+//   * ELU'(z) is recovered from the recomputed stage input e = ELU(z) already in shared memory (1 for e > 0, e + 1 otherwise)
+//   * lane = (8 row/k groups) x (4 column groups): both GEMMs read 8 + 4 distinct 16-byte words per warp and step,
+//     conflict-free with the 68-float row stride
 // ------------------------------------------------------------------------------------------------
-constexpr int TB_TM = 128;
+constexpr int TB_TM = 64;
 constexpr int TB_XS = 68;
-constexpr size_t TB_SMEM = (size_t)(64 * 64 + 2 * TB_TM * TB_XS + 256) * sizeof(float);
+constexpr int TB_SMEM_FLOATS = 64 * 64 + 2 * TB_TM * TB_XS + TB_TM * 8 + 2 * TB_TM;   // W^T, dh tile, Xd tile, dS tile, mask words
+constexpr size_t TB_SMEM = (size_t)TB_SMEM_FLOATS * sizeof(float);
 constexpr int TB_PART = 64 * 64 + 64;   // floats per block partial
+constexpr int TB_CTAS_PER_SM = 3;     // in-box A/B: 3 CTAs (85 registers, no spills) beat 4 (64 registers, spills)
 
 template <int H>
-__global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dS,
-                                                            const float* __restrict__ h, const float* __restrict__ Xu,
+__global__ void __launch_bounds__(256, TB_CTAS_PER_SM) transform_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dS,
+                                                            const float* __restrict__ Xu,
                                                             const float* __restrict__ Xi, int apply_elu,
                                                             const uint64_t* __restrict__ featmask, float scale,
                                                             const float* const* __restrict__ wtab, int U, int I, int nb_u,
@@ -212,9 +218,10 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
                                                             float* __restrict__ partials) {
     extern __shared__ __align__(16) float smem[];
     float* WTs = smem;                       // [c][k] = W[k][c]
-    float* dhs = smem + 64 * 64;             // [128][68]
-    float* Xds = dhs + TB_TM * TB_XS;        // [128][68]
-    float* red = Xds + TB_TM * TB_XS;        // [256]
+    float* dhs = smem + 64 * 64;             // [64][68]
+    float* Xds = dhs + TB_TM * TB_XS;        // [64][68]
+    float* dSs = Xds + TB_TM * TB_XS;        // [64][H]
+    uint64_t* msk = reinterpret_cast<uint64_t*>(dSs + TB_TM * 8);   // [64]
     constexpr int DH = D / H;
     const bool item_side = (int)blockIdx.x >= nb_u;
     const int bs = item_side ? blockIdx.x - nb_u : blockIdx.x;
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
     float* dX = item_side ? dXi : dXu;
     const int64_t node_off = item_side ? U : 0;
     const int tiles = (rows_side + TB_TM - 1) / TB_TM;
+    const float inv_scale = featmask ? 1.f / scale : 1.f;
 
     // WTs[c*64+k] = W[k][c]
     {
@@ -234,50 +242,57 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
             WTs[(c + 0) * 64 + k] = v.x; WTs[(c + 1) * 64 + k] = v.y; WTs[(c + 2) * 64 + k] = v.z; WTs[(c + 3) * 64 + k] = v.w;
         }
     }
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g8 = (warp & 1) * 8 + (lane >> 2);      // 0..15: row group of GEMM (a), k group of GEMM (b)
+    const int c4 = (warp >> 1) * 4 + (lane & 3);      // 0..15: output column group (4 columns) of both GEMMs
     float accW[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) accW[i][0] = accW[i][1] = accW[i][2] = accW[i][3] = 0.f;
-    float acc_a = 0.f;
-    const int ac = threadIdx.x & 63, arp = threadIdx.x >> 6;
+    const int qh = c4 & 7;
+    const bool qhi = (c4 >> 3) != 0;
+    float q[4] = {0.f, 0.f, 0.f, 0.f};   // H=1: Q[4*g8 + j]; H=8: q[0..1] = Q[4*g8 + 2*(c4>>3) + j][c4 & 7]
 
     for (int tile = bs; tile < tiles; tile += nbs) {
         const int row0 = tile * TB_TM;
         const int nrows = min(TB_TM, rows_side - row0);
         __syncthreads();
         for (int idx = threadIdx.x; idx < TB_TM * 16; idx += 256) {
-            int r = idx >> 4, q = idx & 15;
+            const int r = idx >> 4, qd = idx & 15;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f), x = v;
             if (r < nrows) {
-                v = ld_stream4(dh + (node_off + row0 + r) * D + q * 4);
+                v = ld_stream4(dh + (node_off + row0 + r) * D + qd * 4);
                 // same expression as transform_fwd: recomputes the dropped, activated stage input
-                x = ld_stream4(X + (int64_t)(row0 + r) * D + q * 4);
+                x = ld_stream4(X + (int64_t)(row0 + r) * D + qd * 4);
                 if (apply_elu) { x.x = elu(x.x); x.y = elu(x.y); x.z = elu(x.z); x.w = elu(x.w); }
                 if (featmask) {
-                    uint32_t m = (uint32_t)(featmask[node_off + row0 + r] >> (q * 4)) & 0xFu;
+                    uint32_t m = (uint32_t)(featmask[node_off + row0 + r] >> (qd * 4)) & 0xFu;
                     x.x = (m & 1u) ? x.x * scale : 0.f; x.y = (m & 2u) ? x.y * scale : 0.f;
                     x.z = (m & 4u) ? x.z * scale : 0.f; x.w = (m & 8u) ? x.w * scale : 0.f;
                 }
             }
-            *reinterpret_cast<float4*>(dhs + r * TB_XS + q * 4) = v;
-            *reinterpret_cast<float4*>(Xds + r * TB_XS + q * 4) = x;
+            *reinterpret_cast<float4*>(dhs + r * TB_XS + qd * 4) = v;
+            *reinterpret_cast<float4*>(Xds + r * TB_XS + qd * 4) = x;
         }
+        for (int idx = threadIdx.x; idx < TB_TM * H; idx += 256)
+            dSs[idx] = idx < nrows * H ? __ldg(dS + (node_off + row0) * H + idx) : 0.f;
+        if (threadIdx.x < TB_TM)
+            msk[threadIdx.x] = (featmask && (int)threadIdx.x < nrows) ? featmask[node_off + row0 + threadIdx.x] : ~0ull;
         __syncthreads();
 
-        // (a) dXd[r][k] = sum_c dh[r][c] * W[k][c]; thread = rows ty+16i, k = 4tx..4tx+3
+        // (a) dXd[r][k] = sum_c dh[r][c] * W[k][c]; thread = rows g8 + 16i, k = 4*c4 .. 4*c4+3
         {
-            float acc[8][4];
+            float acc[4][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-#pragma unroll 2
-            for (int c4 = 0; c4 < 16; ++c4) {
-                float4 w0 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 0) * 64 + tx * 4);
-                float4 w1 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 1) * 64 + tx * 4);
-                float4 w2 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 2) * 64 + tx * 4);
-                float4 w3 = *reinterpret_cast<const float4*>(WTs + (c4 * 4 + 3) * 64 + tx * 4);
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll 4
+            for (int cc = 0; cc < 16; ++cc) {
+                const float4 w0 = *reinterpret_cast<const float4*>(WTs + (cc * 4 + 0) * 64 + c4 * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(WTs + (cc * 4 + 1) * 64 + c4 * 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(WTs + (cc * 4 + 2) * 64 + c4 * 4);
+                const float4 w3 = *reinterpret_cast<const float4*>(WTs + (cc * 4 + 3) * 64 + c4 * 4);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 x = *reinterpret_cast<const float4*>(dhs + (ty + 16 * i) * TB_XS + c4 * 4);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 x = *reinterpret_cast<const float4*>(dhs + (g8 + 16 * i) * TB_XS + cc * 4);
                     acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
                     acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
                     acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
@@ -289,32 +304,35 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = ty + 16 * i;
+            for (int i = 0; i < 4; ++i) {
+                const int r = g8 + 16 * i;
                 if (r >= nrows) continue;
                 float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
                 if (featmask) {
-                    uint32_t m = (uint32_t)(featmask[node_off + row0 + r] >> (tx * 4)) & 0xFu;
+                    const uint32_t m = (uint32_t)(msk[r] >> (c4 * 4)) & 0xFu;
                     v.x = (m & 1u) ? v.x * scale : 0.f; v.y = (m & 2u) ? v.y * scale : 0.f;
                     v.z = (m & 4u) ? v.z * scale : 0.f; v.w = (m & 8u) ? v.w * scale : 0.f;
                 }
-                float* dst = dX + (int64_t)(row0 + r) * D + tx * 4;
-                if (apply_elu) {   // the stage input was ELU(Zprev): chain through ELU'
-                    float4 z = ld_stream4(X + (int64_t)(row0 + r) * D + tx * 4);
-                    v.x *= elu_grad(z.x); v.y *= elu_grad(z.y); v.z *= elu_grad(z.z); v.w *= elu_grad(z.w);
+                if (apply_elu) {   // the stage input was ELU(Zprev): chain through ELU' = 1 (e > 0) or e + 1 = exp(z)
+                    const float4 e = *reinterpret_cast<const float4*>(Xds + r * TB_XS + c4 * 4);
+                    const float ex = e.x * inv_scale, ey = e.y * inv_scale, ez = e.z * inv_scale, ew = e.w * inv_scale;
+                    v.x *= ex > 0.f ? 1.f : ex + 1.f; v.y *= ey > 0.f ? 1.f : ey + 1.f;
+                    v.z *= ez > 0.f ? 1.f : ez + 1.f; v.w *= ew > 0.f ? 1.f : ew + 1.f;
                 }
+                float* dst = dX + (int64_t)(row0 + r) * D + c4 * 4;
                 if (accumulate_dx) {
-                    float4 o = *reinterpret_cast<const float4*>(dst);
+                    const float4 o = *reinterpret_cast<const float4*>(dst);
                     v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
                 }
                 *reinterpret_cast<float4*>(dst) = v;
             }
         }
-        // (b) dW[k][c] += sum_r Xd[r][k] * dh[r][c]; thread = k 4ty..4ty+3, c 4tx..4tx+3 (rows >= nrows are zero)
+        // (b) dW[k][c] += sum_r Xd[r][k] * dh[r][c], Q[k][hd] += sum_r Xd[r][k] * dS[r][hd]; thread = k 4*g8.., c 4*c4..
+        //     (rows >= nrows are zero in all three tiles)
 #pragma unroll 4
         for (int r = 0; r < TB_TM; ++r) {
-            float4 xs = *reinterpret_cast<const float4*>(Xds + r * TB_XS + ty * 4);
-            float4 ds = *reinterpret_cast<const float4*>(dhs + r * TB_XS + tx * 4);
+            const float4 xs = *reinterpret_cast<const float4*>(Xds + r * TB_XS + g8 * 4);
+            const float4 ds = *reinterpret_cast<const float4*>(dhs + r * TB_XS + c4 * 4);
             accW[0][0] = fmaf(xs.x, ds.x, accW[0][0]); accW[0][1] = fmaf(xs.x, ds.y, accW[0][1]);
             accW[0][2] = fmaf(xs.x, ds.z, accW[0][2]); accW[0][3] = fmaf(xs.x, ds.w, accW[0][3]);
             accW[1][0] = fmaf(xs.y, ds.x, accW[1][0]); accW[1][1] = fmaf(xs.y, ds.y, accW[1][1]);
@@ -323,20 +341,38 @@ __global__ void __launch_bounds__(256) transform_bwd_kernel(const float* __restr
             accW[2][2] = fmaf(xs.z, ds.z, accW[2][2]); accW[2][3] = fmaf(xs.z, ds.w, accW[2][3]);
             accW[3][0] = fmaf(xs.w, ds.x, accW[3][0]); accW[3][1] = fmaf(xs.w, ds.y, accW[3][1]);
             accW[3][2] = fmaf(xs.w, ds.z, accW[3][2]); accW[3][3] = fmaf(xs.w, ds.w, accW[3][3]);
-        }
-        // (c) da[c] += sum_r dS[r][head(c)] * h[r][c]
-        for (int r = arp; r < nrows; r += 4) {
-            const int64_t node = node_off + row0 + r;
-            acc_a = fmaf(__ldg(dS + node * H + ac / DH), __ldg(h + node * D + ac), acc_a);
+            if (H == 1) {
+                const float d = dSs[r];
+                q[0] = fmaf(xs.x, d, q[0]); q[1] = fmaf(xs.y, d, q[1]); q[2] = fmaf(xs.z, d, q[2]); q[3] = fmaf(xs.w, d, q[3]);
+            } else {
+                const float d = dSs[r * 8 + qh];
+                q[0] = fmaf(qhi ? xs.z : xs.x, d, q[0]);
+                q[1] = fmaf(qhi ? xs.w : xs.y, d, q[1]);
+            }
         }
     }
     float* part = partials + (size_t)blockIdx.x * TB_PART;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(part + (ty * 4 + i) * 64 + tx * 4) = make_float4(accW[i][0], accW[i][1], accW[i][2], accW[i][3]);
-    red[threadIdx.x] = acc_a;
+        *reinterpret_cast<float4*>(part + (g8 * 4 + i) * 64 + c4 * 4) = make_float4(accW[i][0], accW[i][1], accW[i][2], accW[i][3]);
+    // da partial of this block: da[c] = sum_k W[k][c] * Q[k][head(c)]
     __syncthreads();
-    if (threadIdx.x < 64) part[64 * 64 + threadIdx.x] = (red[threadIdx.x] + red[64 + threadIdx.x]) + (red[128 + threadIdx.x] + red[192 + threadIdx.x]);
+    float* Qs = dhs;     // [64][H]
+    if (H == 1) {
+        if (c4 == 0) { Qs[g8 * 4 + 0] = q[0]; Qs[g8 * 4 + 1] = q[1]; Qs[g8 * 4 + 2] = q[2]; Qs[g8 * 4 + 3] = q[3]; }
+    } else {
+        const int k0 = g8 * 4 + (qhi ? 2 : 0);
+        Qs[(k0 + 0) * 8 + qh] = q[0];
+        Qs[(k0 + 1) * 8 + qh] = q[1];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x, hd = c / DH;
+        float a = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) a = fmaf(WTs[c * 64 + k], Qs[k * H + hd], a);
+        part[64 * 64 + c] = a;
+    }
 }
 
 // sums the block partials of each side and writes the per-head gradient tensors.  One CTA = 32 consecutive outputs x 8
@@ -433,7 +469,7 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
 
 static void transform_bwd_grid(int U, int I, int* nb_u, int* nb_i) {
     const int tiles_u = ceil_div(U, TB_TM), tiles_i = ceil_div(I, TB_TM);
-    const int budget = 2 * 148;   // two resident CTAs per SM (86 KB of shared memory each)
+    const int budget = TB_CTAS_PER_SM * 148;   // resident CTAs (54 KB of shared memory each; register-limited)
     int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i > 0 ? tiles_u + tiles_i : 1));
     if (bu < 1) bu = 1;
     if (bu > tiles_u) bu = tiles_u;      // 0 when this call has no user rows
@@ -473,10 +509,10 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
     cudaStream_t st = (cudaStream_t)stream;
     float* partials = (float*)workspace;
     if (H == 8) {
-        transform_bwd_kernel<8><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
+        transform_bwd_kernel<8><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
         reduce_partials_kernel<8><<<2 * TB_PART / 32, 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
     } else {
-        transform_bwd_kernel<1><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, h, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
+        transform_bwd_kernel<1><<<bu + bi, 256, TB_SMEM, st>>>(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, bu, dXu, dXi, accumulate_dx, partials);
         reduce_partials_kernel<1><<<2 * TB_PART / 32, 256, 0, st>>>(partials, bu, bu + bi, gtab, accumulate_dw);
     }
     return check_launch("transform_bwd");
