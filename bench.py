@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--workload", default="gowalla", choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--split-bwd", action="store_true", help="dense backward as dX (on the chain) + dW/da (gradient stream)")
     ap.add_argument("--eval-mode", default="auto")
     ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
     ap.add_argument("--dist", default="replica", choices=["replica", "shard"],
@@ -231,7 +232,7 @@ def main():
             trainer = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=0)
     else:
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
-        trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0)
+        trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0, split_dense_backward=args.split_bwd)
     launches_per_step = trainer.launches_per_step(HYPER["droprate"])
 
     def barrier():

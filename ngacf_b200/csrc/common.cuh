@@ -27,6 +27,14 @@ int check_launch(const char* what);
         }                                              \
     } while (0)
 
+// dense stage transforms: tcgen05 3xTF32 kernels (transform_tc.cu) unless NGACF_DENSE=ffma selects the CUDA-core kernels
+// (kept for parity triage); read once per process
+bool dense_on_tensor_cores();
+void transform_fwd_tc(const float* Xu, const float* Xi, int apply_elu, const uint64_t* featmask, float scale, const float* const* wtab, int H,
+                      int U, int I, float* h, float* s, cudaStream_t st);
+void transform_bwd_dx_tc(const float* dh, const float* Zu, const float* Zi, int apply_elu, const uint64_t* featmask, float scale,
+                         const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate, cudaStream_t st);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
@@ -54,7 +62,20 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) {   // L2-coherent (oth
     return __ldcg(reinterpret_cast<const float4*>(p));
 }
 
-__device__ __forceinline__ float elu(float z) { return z > 0.f ? z : expm1f(z); }
+// ELU.  expm1 for z <= 0 without libdevice's ~50-instruction expm1f (it was 75% of the dense kernels' instruction stream,
+// profiles/r1e_dense_tc_ncu.txt): Taylor to z^6 on (-0.25, 0] (relative error < 6e-8), exp(z) - 1 below (|expm1| >= 0.22 there,
+// so __expf's ~2^-22 absolute error stays < 1.2e-6 relative).  Forward and backward use this one definition.
+__device__ __forceinline__ float elu(float z) {
+    float p = fmaf(z, 1.f / 720.f, 1.f / 120.f);
+    p = fmaf(p, z, 1.f / 24.f);
+    p = fmaf(p, z, 1.f / 6.f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.f);
+    p *= z;
+    const float e = __expf(z) - 1.f;
+    const float r = z > -0.25f ? p : e;
+    return z > 0.f ? z : r;
+}
 __device__ __forceinline__ float elu_grad(float z) { return z > 0.f ? 1.f : __expf(z); }
 
 // e = exp(-LeakyReLU(x)); the same expression is used by forward and backward so the recomputed

@@ -406,6 +406,10 @@ extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t app
     NGACF_REQUIRE(wtab && h && s && U >= 0 && I >= 0 && (U == 0 || Xu) && (I == 0 || Xi), "transform_fwd: null argument");
     if (U + I == 0) return NGACF_OK;
     NGACF_REQUIRE(H == 1 || H == 8, "transform_fwd: H must be 1 or 8 (got %d)", H);
+    if (dense_on_tensor_cores()) {
+        transform_fwd_tc(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s, (cudaStream_t)stream);
+        return check_launch("transform_fwd(tc)");
+    }
     const int tiles_u = ceil_div(U, TF_TM), tiles_i = ceil_div(I, TF_TM);
     static bool attr_done = false;
     if (!attr_done) {

@@ -257,6 +257,10 @@ extern "C" int ngacf_transform_bwd_dx(const float* dh, const float* Xu, const fl
                   "transform_bwd_dx: null argument");
     NGACF_REQUIRE(H == 1 || H == 8, "transform_bwd_dx: H must be 1 or 8");
     if (U + I == 0) return NGACF_OK;
+    if (dense_on_tensor_cores()) {
+        transform_bwd_dx_tc(dh, Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, dXu, dXi, accumulate, (cudaStream_t)stream);
+        return check_launch("transform_bwd_dx(tc)");
+    }
     const int tiles_u = ceil_div(U, DX_TM), tiles_i = ceil_div(I, DX_TM);
     static bool attr_done = false;
     if (!attr_done) {

@@ -1,0 +1,369 @@
+// Dense stage transforms on the 5th-generation tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM).
+//   forward   h = drop(act(X)) Wcat, s = per-head a . h          (SPUIGACF.py:30-39,356-361)
+//   backward  dX = (dh Wcat^T) * mask/(1-p) * ELU'(Zprev)          (autograd of the above w.r.t. the stage input)
+// Both are (rows x 64) x (64 x 64) products with K = 64: far too thin for the FFMA pipe to keep up with HBM
+// (profiles/r1e_ab_prefetch.txt), so the product runs as "3xTF32": every fp32 operand is split into a TF32 head and a
+// TF32 tail (x = hi + lo, |lo| <= 2^-11 |x|) and D = Ahi Bhi + Alo Bhi + Ahi Blo is accumulated in fp32.  The dropped
+// lo*lo term and the tail rounding are ~2^-22 relative per product -- fp32-class accuracy (parity bar: 1e-4).
+//
+// One CTA = 256 threads = one 128-row tile at a time (persistent over its side's tiles), two CTAs per SM:
+//   16-byte loads (next tile prefetched into registers) -> activation / dropout / split -> K-major SWIZZLE_NONE operand
+//   image in shared memory -> one elected thread issues 24 tcgen05.mma (8 k-steps x 3 terms) -> tcgen05.commit -> mbarrier
+//   -> thread (row = TMEM lane, column half) reads 32 accumulators with tcgen05.ld -> epilogue -> staged through the (now
+//   free) operand buffer for 128-byte row-segment stores.
+#include "common.cuh"
+
+namespace ngacf {
+namespace tcx {
+
+constexpr int TM = 128;
+constexpr int PANEL_A = TM * 16;          // one 16-byte k-chunk of all 128 rows
+constexpr int A_HALF = 16 * PANEL_A;      // 32 KB: hi (or lo) image of the row tile, 16 k-chunks
+constexpr int PANEL_B = 64 * 16;
+constexpr int B_HALF = 16 * PANEL_B;      // 16 KB
+constexpr int THREADS = 256;
+constexpr size_t SMEM_BYTES = 2 * A_HALF + 2 * B_HALF + 64 * 4 /*a vector*/ + 2 * TM * 4 /*logit partials*/ + 64 /*barrier + tmem slot*/ + 128 /*alignment*/;
+constexpr uint32_t TMEM_COLS = 64;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N = 64, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE matrix descriptor: core matrix = 8 rows x 16 B; LBO = distance between the two k-chunks of one
+// MMA (one panel), SBO = distance between 8-row groups (128 B).  Same encoding as eval_topk_tc.cu.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t panel_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((128 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+    uint32_t u[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+          "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+          "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+// x = hi + lo with hi, lo representable in TF32 (round-to-nearest both times)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+    split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+
+// coalesced-enough tile load: warp w (of 8) owns rows 16w..16w+15; one instruction = 8 rows x 4 chunks (64-byte row segments in
+// global memory, 4 x 128 contiguous bytes in the operand image: no bank conflicts)
+__device__ __forceinline__ void tile_rows(int warp, int lane, int it, int& r, int& q) {
+    r = 16 * warp + 8 * (it >> 2) + (lane & 7);
+    q = 4 * (it & 3) + (lane >> 3);
+}
+
+// MODE 0: forward (A = drop(act(X)), B[n][k] = Wcat[k][n], epilogue h, s)
+// MODE 1: backward dX (A = dh, B[n][k] = Wcat[n][k], epilogue mask/ELU'/accumulate)
+template <int H, int MODE>
+__global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* __restrict__ Au, const float* __restrict__ Ai,   // fwd: X; bwd: dh rows
+                                                                  const float* __restrict__ Zu, const float* __restrict__ Zi,   // bwd: stage input (ELU'), else null
+                                                                  int apply_elu, const uint64_t* __restrict__ featmask, float scale,
+                                                                  const float* const* __restrict__ wtab, int U, int I, int nb_u,
+                                                                  float* __restrict__ Ou, float* __restrict__ Oi,               // fwd: h rows; bwd: dX
+                                                                  float* __restrict__ s, int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* sAhi = base;
+    uint8_t* sAlo = base + A_HALF;
+    uint8_t* sBhi = base + 2 * A_HALF;
+    uint8_t* sBlo = sBhi + B_HALF;
+    float* av = reinterpret_cast<float*>(sBlo + B_HALF);      // [64] logit vector of this side
+    float* sp = av + 64;                                      // [2][128] H=1: per-row partial logits of the two column halves
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 2 * TM);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    constexpr int DH = D / H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool item_side = (int)blockIdx.x >= nb_u;
+    const int bs = item_side ? blockIdx.x - nb_u : blockIdx.x;
+    const int nbs = item_side ? gridDim.x - nb_u : nb_u;
+    const int rows_side = item_side ? I : U;
+    const float* A = item_side ? Ai : Au;
+    const float* Zin = item_side ? Zi : Zu;
+    float* O = item_side ? Oi : Ou;
+    const int64_t node_off = item_side ? U : 0;
+    const int tiles = (rows_side + TM - 1) / TM;
+
+    // ---- first tile's rows are requested before anything else ----
+    float4 v[8];
+    uint64_t mw[2] = {0ull, 0ull};
+    auto request = [&](int tile) {
+        const int row0 = tile * TM;
+        const int nrows = min(TM, rows_side - row0);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int r, q;
+            tile_rows(warp, lane, it, r, q);
+            v[it] = r < nrows ? ld_stream4(A + (int64_t)(row0 + r) * D + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (MODE == 0 && featmask) {
+#pragma unroll
+            for (int rg = 0; rg < 2; ++rg) {
+                const int r = 16 * warp + 8 * rg + (lane & 7);
+                mw[rg] = r < nrows ? featmask[node_off + row0 + r] : 0ull;
+            }
+        }
+    };
+    if (bs < tiles) request(bs);
+
+    // ---- one-time: barrier, TMEM, operand B (the side's 64x64 weight block, split) ----
+    if (tid == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float* const* wptr = wtab + (item_side ? H : 0);
+        float4 w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
+            w[j] = __ldg(reinterpret_cast<const float4*>(wptr[c / DH] + k * DH + (c % DH)));     // Wcat[k][c..c+3]
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
+            float4 hi, lo;
+            split4(w[j], hi, lo);
+            if (MODE == 0) {   // B[n = c+i][kk = k]
+                const uint32_t o = (uint32_t)(k >> 2) * PANEL_B + (uint32_t)(k & 3) * 4;
+                *reinterpret_cast<float*>(sBhi + o + (c + 0) * 16) = hi.x; *reinterpret_cast<float*>(sBlo + o + (c + 0) * 16) = lo.x;
+                *reinterpret_cast<float*>(sBhi + o + (c + 1) * 16) = hi.y; *reinterpret_cast<float*>(sBlo + o + (c + 1) * 16) = lo.y;
+                *reinterpret_cast<float*>(sBhi + o + (c + 2) * 16) = hi.z; *reinterpret_cast<float*>(sBlo + o + (c + 2) * 16) = lo.z;
+                *reinterpret_cast<float*>(sBhi + o + (c + 3) * 16) = hi.w; *reinterpret_cast<float*>(sBlo + o + (c + 3) * 16) = lo.w;
+            } else {           // B[n = k][kk = c..c+3]
+                const uint32_t o = (uint32_t)(c >> 2) * PANEL_B + (uint32_t)k * 16;
+                *reinterpret_cast<float4*>(sBhi + o) = hi;
+                *reinterpret_cast<float4*>(sBlo + o) = lo;
+            }
+        }
+        if (MODE == 0 && tid < 64) av[tid] = __ldg(wtab[2 * H + tid / DH] + (item_side ? DH : 0) + tid % DH);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    uint32_t phase = 0;
+    const uint64_t dAhi = smem_desc(smem_u32(sAhi), PANEL_A), dAlo = smem_desc(smem_u32(sAlo), PANEL_A);
+    const uint64_t dBhi = smem_desc(smem_u32(sBhi), PANEL_B), dBlo = smem_desc(smem_u32(sBlo), PANEL_B);
+    const int quarter = warp & 3, half = warp >> 2;      // TMEM lanes 32*quarter.., accumulator columns 32*half..
+
+    for (int tile = bs; tile < tiles; tile += nbs) {
+        const int row0 = tile * TM;
+        const int nrows = min(TM, rows_side - row0);
+        // ---- A image of this tile from the prefetched registers ----
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int r, q;
+            tile_rows(warp, lane, it, r, q);
+            float4 x = v[it];
+            if (MODE == 0) {
+                if (apply_elu) { x.x = elu(x.x); x.y = elu(x.y); x.z = elu(x.z); x.w = elu(x.w); }
+                if (featmask) {
+                    const uint32_t m = (uint32_t)(mw[it >> 2] >> (q * 4)) & 0xFu;
+                    x.x = (m & 1u) ? x.x * scale : 0.f; x.y = (m & 2u) ? x.y * scale : 0.f;
+                    x.z = (m & 4u) ? x.z * scale : 0.f; x.w = (m & 8u) ? x.w * scale : 0.f;
+                }
+            }
+            float4 hi, lo;
+            split4(x, hi, lo);
+            const uint32_t o = (uint32_t)q * PANEL_A + (uint32_t)r * 16;
+            *reinterpret_cast<float4*>(sAhi + o) = hi;
+            *reinterpret_cast<float4*>(sAlo + o) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+                const uint64_t a0 = term == 1 ? dAlo : dAhi;
+                const uint64_t b0 = term == 2 ? dBlo : dBhi;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)          // K = 8 TF32 per MMA = two 16-byte k-chunk panels (start address field += bytes/16)
+                    umma_tf32(tmem_base, a0 + (uint64_t)(ks * 2 * PANEL_A / 16), b0 + (uint64_t)(ks * 2 * PANEL_B / 16), (term | ks) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(bar));
+        }
+        // the next tile's rows -- and what this tile's epilogue needs from global memory -- travel while the tensor core works
+        if (tile + nbs < tiles) request(tile + nbs);
+        float4 zz[8];
+        uint32_t em[8];
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = 32 * quarter + 4 * j + (lane >> 3), q = 8 * half + (lane & 7);
+                const bool ok = r < nrows;
+                em[j] = (featmask && ok) ? (uint32_t)(featmask[node_off + row0 + r] >> (q * 4)) & 0xFu : 0xFu;
+                zz[j] = (apply_elu && ok) ? ld_stream4(Zin + (int64_t)(row0 + r) * D + q * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+        }
+        mbar_wait(smem_u32(bar), phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- epilogue: thread = (row = TMEM lane 32*quarter + lane, 32 accumulator columns 32*half..) ----
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(32 * half), acc);
+        const int rl = 32 * quarter + lane;
+        if (MODE == 0) {
+            if (H == 8) {
+                float sv[4];
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    const float* ap = av + 32 * half + hh * 8;
+                    const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+                    float p = acc[hh * 8] * a0.x;
+                    p = fmaf(acc[hh * 8 + 1], a0.y, p); p = fmaf(acc[hh * 8 + 2], a0.z, p); p = fmaf(acc[hh * 8 + 3], a0.w, p);
+                    p = fmaf(acc[hh * 8 + 4], a1.x, p); p = fmaf(acc[hh * 8 + 5], a1.y, p); p = fmaf(acc[hh * 8 + 6], a1.z, p);
+                    p = fmaf(acc[hh * 8 + 7], a1.w, p);
+                    sv[hh] = p;
+                }
+                if (rl < nrows) *reinterpret_cast<float4*>(s + (node_off + row0 + rl) * 8 + 4 * half) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            } else {
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(av + 32 * half + c);
+                    p0 = fmaf(acc[c], a.x, p0); p1 = fmaf(acc[c + 1], a.y, p1); p2 = fmaf(acc[c + 2], a.z, p2); p3 = fmaf(acc[c + 3], a.w, p3);
+                }
+                sp[half * TM + rl] = (p0 + p1) + (p2 + p3);
+            }
+        }
+        // stage this warp's 32 rows x 128 bytes through its slice of the (retired) A-hi image: row r at r*128, 16-byte chunk c at
+        // slot c ^ (r & 7) -> conflict-free for the row-per-thread writes and the 4-rows-per-instruction reads
+        uint8_t* stg = sAhi + warp * 4096;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + (lane >> 3), qq = lane & 7;
+            const int r = 32 * quarter + rr, q = 8 * half + qq;
+            if (r >= nrows) continue;
+            float4 o4 = *reinterpret_cast<const float4*>(stg + rr * 128 + ((qq ^ (rr & 7)) * 16));
+            float* dst = O + (int64_t)(row0 + r) * D + q * 4;
+            if (MODE == 1) {
+                if (featmask) {
+                    const uint32_t m = em[j];
+                    o4.x = (m & 1u) ? o4.x * scale : 0.f; o4.y = (m & 2u) ? o4.y * scale : 0.f;
+                    o4.z = (m & 4u) ? o4.z * scale : 0.f; o4.w = (m & 8u) ? o4.w * scale : 0.f;
+                }
+                if (apply_elu) {
+                    const float4 z = zz[j];
+                    o4.x *= elu_grad(z.x); o4.y *= elu_grad(z.y); o4.z *= elu_grad(z.z); o4.w *= elu_grad(z.w);
+                }
+                if (accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(dst);
+                    o4.x += o.x; o4.y += o.y; o4.z += o.z; o4.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dst) = o4;
+            } else {
+                st_stream4(dst, o4);
+            }
+        }
+        // the staging reads and the TMEM reads of this tile must retire before the next tile's image / MMAs overwrite them
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (MODE == 0 && H == 1 && tid < nrows) s[node_off + row0 + tid] = sp[tid] + sp[TM + tid];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+static void side_grid(int U, int I, int* nb_u, int* nb_i) {
+    const int tiles_u = ceil_div(U, TM), tiles_i = ceil_div(I, TM);
+    const int budget = 2 * 148;
+    int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i > 0 ? tiles_u + tiles_i : 1));
+    if (bu < 1) bu = 1;
+    if (bu > tiles_u) bu = tiles_u;
+    int bi = budget - bu;
+    if (bi < 1) bi = 1;
+    if (bi > tiles_i) bi = tiles_i;
+    *nb_u = bu;
+    *nb_i = bi;
+}
+
+template <int H, int MODE>
+static void launch(const float* Au, const float* Ai, const float* Zu, const float* Zi, int apply_elu, const uint64_t* featmask, float scale,
+                   const float* const* wtab, int U, int I, float* Ou, float* Oi, float* s, int accumulate, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(transform_tc_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        attr_done = true;
+    }
+    int bu, bi;
+    side_grid(U, I, &bu, &bi);
+    transform_tc_kernel<H, MODE><<<bu + bi, THREADS, SMEM_BYTES, st>>>(Au, Ai, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, bu, Ou, Oi, s, accumulate);
+}
+
+}  // namespace tcx
+
+// called by ngacf_transform_fwd / ngacf_transform_bwd_dx (propagate_fwd.cu, transform_bwd_split.cu)
+void transform_fwd_tc(const float* Xu, const float* Xi, int apply_elu, const uint64_t* featmask, float scale, const float* const* wtab, int H,
+                      int U, int I, float* h, float* s, cudaStream_t st) {
+    float* hi = h + (int64_t)U * D;
+    if (H == 8) tcx::launch<8, 0>(Xu, Xi, nullptr, nullptr, apply_elu, featmask, scale, wtab, U, I, h, hi, s, 0, st);
+    else        tcx::launch<1, 0>(Xu, Xi, nullptr, nullptr, apply_elu, featmask, scale, wtab, U, I, h, hi, s, 0, st);
+}
+void transform_bwd_dx_tc(const float* dh, const float* Zu, const float* Zi, int apply_elu, const uint64_t* featmask, float scale,
+                         const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate, cudaStream_t st) {
+    const float* dhi = dh + (int64_t)U * D;
+    if (H == 8) tcx::launch<8, 1>(dh, dhi, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, dXu, dXi, nullptr, accumulate, st);
+    else        tcx::launch<1, 1>(dh, dhi, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, dXu, dXi, nullptr, accumulate, st);
+}
+
+}  // namespace ngacf

@@ -1,5 +1,6 @@
 // Error reporting shared by every entry point of the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -20,6 +21,15 @@ int check_launch(const char* what) {
         return NGACF_ERR_CUDA;
     }
     return NGACF_OK;
+}
+
+bool dense_on_tensor_cores() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("NGACF_DENSE");
+        mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    }
+    return mode == 1;
 }
 }  // namespace ngacf
 
