@@ -35,6 +35,10 @@ void transform_fwd_tc(const float* Xu, const float* Xi, int apply_elu, const uin
 void transform_bwd_dx_tc(const float* dh, const float* Zu, const float* Zi, int apply_elu, const uint64_t* featmask, float scale,
                          const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate, cudaStream_t st);
 
+void transform_bwd_tc(const float* dh, const float* dS, const float* Xu, const float* Xi, int apply_elu, const uint64_t* featmask, float scale,
+                      const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate_dx, float* partials,
+                      int* nb_u, int* nb_i, cudaStream_t st);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

@@ -499,6 +499,13 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
         return NGACF_ERR_WORKSPACE;
     }
     int bu, bi;
+    if (dense_on_tensor_cores()) {
+        cudaStream_t st = (cudaStream_t)stream;
+        transform_bwd_tc(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, dXu, dXi, accumulate_dx, (float*)workspace, &bu, &bi, st);
+        if (H == 8) reduce_partials_kernel<8><<<2 * TB_PART / 32, 256, 0, st>>>((float*)workspace, bu, bu + bi, gtab, accumulate_dw);
+        else        reduce_partials_kernel<1><<<2 * TB_PART / 32, 256, 0, st>>>((float*)workspace, bu, bu + bi, gtab, accumulate_dw);
+        return check_launch("transform_bwd(tc)");
+    }
     transform_bwd_grid(U, I, &bu, &bi);
     static bool attr_done = false;
     if (!attr_done) {

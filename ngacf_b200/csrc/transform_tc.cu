@@ -11,6 +11,7 @@
 //   image in shared memory -> one elected thread issues 24 tcgen05.mma (8 k-steps x 3 terms) -> tcgen05.commit -> mbarrier
 //   -> thread (row = TMEM lane, column half) reads 32 accumulators with tcgen05.ld -> epilogue -> staged through the (now
 //   free) operand buffer for 128-byte row-segment stores.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace ngacf {
@@ -350,6 +351,354 @@ static void launch(const float* Au, const float* Ai, const float* Zu, const floa
     transform_tc_kernel<H, MODE><<<bu + bi, THREADS, SMEM_BYTES, st>>>(Au, Ai, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, bu, Ou, Oi, s, accumulate);
 }
 
+
+// =================================================================================================
+// Fused dense backward of one stage on the tensor cores (replaces the CUDA-core transform_bwd_kernel):
+//   dX  = (dh W^T) * F,  F = mask/(1-p) * ELU'(Zprev)                       D1[128 rows x 64]   per tile
+//   dW += Xd^T dh,  Q += Xd^T dS  (da[c] = sum_k W[k][c] Q[k][head(c)])     D2[64(+64) x 80]    accumulated over the CTA's tiles
+// One 512-thread CTA per SM, persistent over its side's 128-row tiles.
+//
+// Operand format.  The dW product contracts over ROWS, i.e. both of its operands are MN-major in their natural row-major
+// tiles.  kind::tf32 returns zeros for MN-major operands on sm_100a (scripts/probe/run_probe.py, profiles/r1e_umma_probe.txt),
+// kind::f16 supports them, so this kernel splits every fp32 value into THREE bf16 terms x = h + m + l (8+8+8 mantissa bits,
+// exact) and accumulates the six products with weight >= 2^-16 (hh, hm, mh, mm, hl, lh): dropped terms are <= 2^-23 relative,
+// fp32-class accuracy at the bf16 rate (6 bf16 MMAs cost what 3 tf32 MMAs do).
+//
+// The two row-major tiles are written ONCE, as SWIZZLE_NONE images [16-byte chunk = 8 features][row][16 B]: read K-major they
+// are the A operand of the dX product (K = feature), read MN-major (LBO/SBO roles swapped) they are the A and B operands of
+// the dW product (K = row) -- no transposed copy.  The dS tile is appended to the dh image as chunk 8, so Q comes out as
+// accumulator columns 64..71 of the same MMAs.  M = 128 for both products (the M = 64 accumulator layout is not row = lane):
+// for dW only lanes 0..63 (k) are meaningful, lanes 64..127 come from reading past the Xd image (ignored).
+// =================================================================================================
+namespace bwd {
+constexpr int THREADS = 512;
+constexpr int PANEL = TM * 16;                       // 2048: one 16-byte chunk column of 128 rows
+constexpr int DH_TERM = 10 * PANEL;                  // dh (8 chunks) + dS (chunk 8) + pad (chunk 9): one bf16 term
+constexpr int XD_TERM = 8 * PANEL;
+constexpr int WPANEL = 64 * 16;                      // W image of the dX product: [chunk = 8 c][row = k][16 B]
+constexpr int W_TERM = 8 * WPANEL;
+constexpr int OFF_DH = 0;                            // [h | m | l]
+constexpr int OFF_XD = 3 * DH_TERM;                  // [h | m | l]
+constexpr int OFF_W = OFF_XD + 3 * XD_TERM;          // [h | m | l]; also the slack the M = 128 reads of the last Xd term run into
+constexpr int OFF_F = OFF_W + 3 * W_TERM;            // fp32 factor tile in the epilogue's staging layout (M = 128 slack too)
+constexpr int OFF_MISC = OFF_F + TM * 64 * 4;
+constexpr size_t SMEM_BYTES = OFF_MISC + 64 * 8 * 4 /*Q*/ + 64 /*barrier, tmem slot*/ + 128 /*alignment*/;
+constexpr uint32_t TMEM_COLS = 256;                  // D1: columns 0..63, D2: columns 64..143
+constexpr uint32_t IDESC_DX = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);     // bf16, K-major, N = 64
+constexpr uint32_t IDESC_DW = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(80 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr int PART = 64 * 64 + 64;                   // floats per CTA partial (same layout as propagate_bwd.cu: dW then da)
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MN-major SWIZZLE_NONE descriptor over the same image: SBO = distance between 16-byte chunks along M/N (one panel),
+// LBO = distance between the two 8-row groups of one MMA along K (128 B)
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((128 >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((PANEL >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+// x = h + m + l, three bf16 terms (round-to-nearest, residuals exact in fp32); returns the terms of two values packed lo|hi
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
+    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(r0 - __bfloat162float(m0)), l1 = __float2bfloat16_rn(r1 - __bfloat162float(m1));
+    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    m = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+__device__ __forceinline__ void split3x8(const float4 a, const float4 b, uint4& h, uint4& m, uint4& l) {
+    split3_pair(a.x, a.y, h.x, m.x, l.x); split3_pair(a.z, a.w, h.y, m.y, l.y);
+    split3_pair(b.x, b.y, h.z, m.z, l.z); split3_pair(b.z, b.w, h.w, m.w, l.w);
+}
+// staging / factor-tile layout: slice of epilogue warp (quarter, cq) = 32 rows x 64 B; 16-byte chunk qq of row rr at slot qq ^ ((rr>>1)&3)
+__device__ __forceinline__ uint32_t stage_off(int r, int q) {
+    const int rr = r & 31, quarter = r >> 5, cq = q >> 2, qq = q & 3;
+    return (uint32_t)((quarter + 4 * cq) * 2048 + rr * 64 + ((qq ^ ((rr >> 1) & 3)) * 16));
+}
+
+template <int H>
+__global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const float* __restrict__ dh, const float* __restrict__ dS,
+                                                                      const float* __restrict__ Xu, const float* __restrict__ Xi, int apply_elu,
+                                                                      const uint64_t* __restrict__ featmask, float scale,
+                                                                      const float* const* __restrict__ wtab, int U, int I, int nb_u,
+                                                                      float* __restrict__ dXu, float* __restrict__ dXi, int accumulate_dx,
+                                                                      float* __restrict__ partials) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* sDH = base + OFF_DH;
+    uint8_t* sXD = base + OFF_XD;
+    uint8_t* sW = base + OFF_W;
+    uint8_t* sF = base + OFF_F;
+    float* Qs = reinterpret_cast<float*>(base + OFF_MISC);        // [64][8]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Qs + 64 * 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    constexpr int DH_ = D / H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool item_side = (int)blockIdx.x >= nb_u;
+    const int bs = item_side ? blockIdx.x - nb_u : blockIdx.x;
+    const int nbs = item_side ? gridDim.x - nb_u : nb_u;
+    const int rows_side = item_side ? I : U;
+    const float* X = item_side ? Xi : Xu;
+    float* dX = item_side ? dXi : dXu;
+    const int64_t node_off = item_side ? U : 0;
+    const int tiles = (rows_side + TM - 1) / TM;
+
+    // tile loads: warp w (of 16) owns rows 8w..8w+7; item `it` = those 8 rows x feature chunks (8 floats) 4it..4it+3
+    const int lr = 8 * warp + (lane & 7);            // this thread's row within the tile (fixed)
+    float4 vd[4], vx[4], vs0 = make_float4(0.f, 0.f, 0.f, 0.f), vs1 = vs0;
+    uint64_t mw = 0ull;
+    auto request = [&](int tile) {
+        const int row0 = tile * TM;
+        const bool ok = row0 + lr < rows_side;
+        const int64_t node = node_off + row0 + lr;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int q8 = 4 * it + (lane >> 3);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            vd[2 * it] = ok ? ld_stream4(dh + node * D + q8 * 8) : z4;
+            vd[2 * it + 1] = ok ? ld_stream4(dh + node * D + q8 * 8 + 4) : z4;
+            vx[2 * it] = ok ? ld_stream4(X + (int64_t)(row0 + lr) * D + q8 * 8) : z4;
+            vx[2 * it + 1] = ok ? ld_stream4(X + (int64_t)(row0 + lr) * D + q8 * 8 + 4) : z4;
+        }
+        mw = (featmask && ok) ? featmask[node] : (ok ? ~0ull : 0ull);
+        // dS: one 16-byte bf16 chunk per row, built by threads 0..127 (row = tid)
+        vs0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        vs1 = vs0;
+        if (tid < TM && row0 + tid < rows_side) {
+            if (H == 8) {
+                vs0 = ld_stream4(dS + (node_off + row0 + tid) * 8);
+                vs1 = ld_stream4(dS + (node_off + row0 + tid) * 8 + 4);
+            } else {
+                vs0.x = __ldg(dS + node_off + row0 + tid);
+            }
+        }
+    };
+    if (bs < tiles) request(bs);
+
+    if (tid == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // W image of the dX product: B[n = k][kk = c] = Wcat[k][c], one (row k, 8-feature chunk) item per thread
+        const float* const* wptr = wtab + (item_side ? H : 0);
+        const int k = tid >> 3, c = (tid & 7) * 8;
+        const float* src = wptr[c / DH_] + k * DH_ + (c % DH_);       // DH is 8 or 64: the 8 values are contiguous
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(src)), w1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+        uint4 h, m, l;
+        split3x8(w0, w1, h, m, l);
+        const uint32_t o = (uint32_t)(c >> 3) * WPANEL + (uint32_t)k * 16;
+        *reinterpret_cast<uint4*>(sW + o) = h;
+        *reinterpret_cast<uint4*>(sW + W_TERM + o) = m;
+        *reinterpret_cast<uint4*>(sW + 2 * W_TERM + o) = l;
+    }
+    // chunk 9 of the dh image (accumulator columns 72..79) is never written by the tile loop: clear it once
+    for (int i = tid; i < 3 * (PANEL / 16); i += THREADS)
+        *reinterpret_cast<uint4*>(sDH + (i / (PANEL / 16)) * DH_TERM + 9 * PANEL + (i % (PANEL / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tD1 = tmem_base, tD2 = tmem_base + 64;
+    uint32_t phase = 0;
+    const uint32_t aDH = smem_u32(sDH), aXD = smem_u32(sXD), aW = smem_u32(sW);
+    const int quarter = warp & 3, cq = warp >> 2;     // epilogue: TMEM lanes 32*quarter.., D1 columns 16*cq..
+    const float sc = featmask ? scale : 1.f;
+    bool first = true;
+
+    for (int tile = bs; tile < tiles; tile += nbs) {
+        const int row0 = tile * TM;
+        const int nrows = min(TM, rows_side - row0);
+        // ---- operand images + factor tile from the prefetched registers ----
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int q8 = 4 * it + (lane >> 3);
+            const uint32_t o = (uint32_t)q8 * PANEL + (uint32_t)lr * 16;
+            uint4 h, m, l;
+            split3x8(vd[2 * it], vd[2 * it + 1], h, m, l);
+            *reinterpret_cast<uint4*>(sDH + o) = h;
+            *reinterpret_cast<uint4*>(sDH + DH_TERM + o) = m;
+            *reinterpret_cast<uint4*>(sDH + 2 * DH_TERM + o) = l;
+            // recomputed stage input (same expressions as the forward) and the dX factor mask/(1-p) * ELU'(z)
+            float4 xs[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float4 z = vx[2 * it + j];
+                float4 x = z, f = make_float4(sc, sc, sc, sc);
+                if (apply_elu) {
+                    x.x = elu(z.x); x.y = elu(z.y); x.z = elu(z.z); x.w = elu(z.w);
+                    f.x *= z.x > 0.f ? 1.f : x.x + 1.f; f.y *= z.y > 0.f ? 1.f : x.y + 1.f;
+                    f.z *= z.z > 0.f ? 1.f : x.z + 1.f; f.w *= z.w > 0.f ? 1.f : x.w + 1.f;
+                }
+                const int q = 2 * q8 + j;
+                const uint32_t mk = (uint32_t)(mw >> (q * 4)) & 0xFu;
+                x.x = (mk & 1u) ? x.x * sc : 0.f; x.y = (mk & 2u) ? x.y * sc : 0.f; x.z = (mk & 4u) ? x.z * sc : 0.f; x.w = (mk & 8u) ? x.w * sc : 0.f;
+                f.x = (mk & 1u) ? f.x : 0.f; f.y = (mk & 2u) ? f.y : 0.f; f.z = (mk & 4u) ? f.z : 0.f; f.w = (mk & 8u) ? f.w : 0.f;
+                xs[j] = x;
+                *reinterpret_cast<float4*>(sF + stage_off(lr, q)) = f;
+            }
+            split3x8(xs[0], xs[1], h, m, l);
+            *reinterpret_cast<uint4*>(sXD + o) = h;
+            *reinterpret_cast<uint4*>(sXD + XD_TERM + o) = m;
+            *reinterpret_cast<uint4*>(sXD + 2 * XD_TERM + o) = l;
+        }
+        if (tid < TM) {
+            uint4 h, m, l;
+            split3x8(vs0, vs1, h, m, l);
+            const uint32_t o = (uint32_t)8 * PANEL + (uint32_t)tid * 16;
+            *reinterpret_cast<uint4*>(sDH + o) = h;
+            *reinterpret_cast<uint4*>(sDH + DH_TERM + o) = m;
+            *reinterpret_cast<uint4*>(sDH + 2 * DH_TERM + o) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l)
+            // dX: D1 = sum DH_a W_b   (K-major: K = feature, 16 per MMA = two chunk panels)
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr) {
+                const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
+                const uint32_t a0 = aDH + ta * DH_TERM, b0 = aW + tb * W_TERM;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma(tD1, smem_desc(a0 + ks * 2 * PANEL, PANEL), smem_desc(b0 + ks * 2 * WPANEL, WPANEL), IDESC_DX, (pr | ks) ? 1u : 0u);
+            }
+            // dW | Q: D2 += sum XD_a^T [DH|DS]_b   (both MN-major: K = rows, 16 per MMA = two 8-row groups)
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr) {
+                const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
+                const uint32_t a0 = aXD + ta * XD_TERM, b0 = aDH + tb * DH_TERM;
+#pragma unroll 4
+                for (int ks = 0; ks < 8; ++ks)
+                    umma(tD2, smem_desc_mn(a0 + ks * 256), smem_desc_mn(b0 + ks * 256), IDESC_DW, (!first || (pr | ks)) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(bar));
+        }
+        first = false;
+        if (tile + nbs < tiles) request(tile + nbs);
+        mbar_wait(smem_u32(bar), phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- dX epilogue: thread = (row = TMEM lane 32*quarter + lane, 16 columns 16*cq..) ----
+        float acc[16];
+        tmem_ld16(tD1 + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * cq), acc);
+        uint8_t* stg = sDH + warp * 2048;            // the dh images are retired: 16 slices x 2 KB = the first 32 KB of that region
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) * 16)) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + (lane >> 2), qq = lane & 3;
+            const int r = 32 * quarter + rr, q = 4 * cq + qq;
+            if (r >= nrows) continue;
+            const uint32_t so = (uint32_t)(rr * 64 + ((qq ^ ((rr >> 1) & 3)) * 16));
+            float4 o4 = *reinterpret_cast<const float4*>(stg + so);
+            const float4 f = *reinterpret_cast<const float4*>(sF + warp * 2048 + so);
+            o4.x *= f.x; o4.y *= f.y; o4.z *= f.z; o4.w *= f.w;
+            float* dst = dX + (int64_t)(row0 + r) * D + q * 4;
+            if (accumulate_dx) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                o4.x += o.x; o4.y += o.y; o4.z += o.z; o4.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst) = o4;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+
+    // ---- CTA partial: dW[k][c] (lanes 0..63 of D2, columns 0..63) and da through Q (columns 64..71) ----
+    float* part = partials + (size_t)blockIdx.x * PART;
+    if (first) {          // no tile (cannot happen with the grid below; keeps the reduction well defined)
+        for (int i = tid; i < PART; i += THREADS) part[i] = 0.f;
+    } else {
+        if (quarter < 2) {
+            float acc[16];
+            const int k = 32 * quarter + lane;
+            tmem_ld16(tD2 + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * cq), acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(part + k * 64 + 16 * cq + 4 * c) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            if (cq == 0) {
+                float qv[8];
+                tmem_ld8(tD2 + ((uint32_t)(32 * quarter) << 16) + 64u, qv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Qs[k * 8 + j] = qv[j];
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 64) {
+            const int c = tid, hd = c / DH_;
+            float a = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) {
+                const uint32_t o = (uint32_t)(c >> 3) * WPANEL + (uint32_t)k * 16 + (uint32_t)(c & 7) * 2;
+                const float w = (__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sW + o)) +
+                                 __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sW + W_TERM + o))) +
+                                __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sW + 2 * W_TERM + o));     // h + m + l = W[k][c]
+                a = fmaf(w, Qs[k * 8 + hd], a);
+            }
+            part[64 * 64 + c] = a;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+static void side_grid1(int U, int I, int* nb_u, int* nb_i) {
+    const int tiles_u = ceil_div(U, TM), tiles_i = ceil_div(I, TM);
+    const int budget = 148;
+    int bu = (int)((int64_t)budget * tiles_u / (tiles_u + tiles_i > 0 ? tiles_u + tiles_i : 1));
+    if (bu < 1) bu = 1;
+    if (bu > tiles_u) bu = tiles_u;
+    int bi = budget - bu;
+    if (bi < 1) bi = 1;
+    if (bi > tiles_i) bi = tiles_i;
+    *nb_u = bu;
+    *nb_i = bi;
+}
+}  // namespace bwd
+
 }  // namespace tcx
 
 // called by ngacf_transform_fwd / ngacf_transform_bwd_dx (propagate_fwd.cu, transform_bwd_split.cu)
@@ -364,6 +713,26 @@ void transform_bwd_dx_tc(const float* dh, const float* Zu, const float* Zi, int 
     const float* dhi = dh + (int64_t)U * D;
     if (H == 8) tcx::launch<8, 1>(dh, dhi, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, dXu, dXi, nullptr, accumulate, st);
     else        tcx::launch<1, 1>(dh, dhi, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, dXu, dXi, nullptr, accumulate, st);
+}
+
+// fused dense backward on the tensor cores; writes (*nb_u + *nb_i) CTA partials of 64*64+64 floats into `partials`
+void transform_bwd_tc(const float* dh, const float* dS, const float* Xu, const float* Xi, int apply_elu, const uint64_t* featmask, float scale,
+                      const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate_dx, float* partials,
+                      int* nb_u, int* nb_i, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tcx::bwd::transform_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx::bwd::SMEM_BYTES);
+        cudaFuncSetAttribute(tcx::bwd::transform_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx::bwd::SMEM_BYTES);
+        attr_done = true;
+    }
+    tcx::bwd::side_grid1(U, I, nb_u, nb_i);
+    const int grid = *nb_u + *nb_i;
+    if (H == 8)
+        tcx::bwd::transform_bwd_tc_kernel<8><<<grid, tcx::bwd::THREADS, tcx::bwd::SMEM_BYTES, st>>>(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, *nb_u,
+                                                                                                   dXu, dXi, accumulate_dx, partials);
+    else
+        tcx::bwd::transform_bwd_tc_kernel<1><<<grid, tcx::bwd::THREADS, tcx::bwd::SMEM_BYTES, st>>>(dh, dS, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, *nb_u,
+                                                                                                   dXu, dXi, accumulate_dx, partials);
 }
 
 }  // namespace ngacf

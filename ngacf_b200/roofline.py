@@ -20,7 +20,7 @@ def kernel_bytes(name: str, U: int, I: int, E: int, H: int, dropout: bool, B: in
     if name == "ngacf_stage_bwd_edges_items":
         return (U + 2 * I) * R + 2 * sc + 2 * E * 4 + E * H * 4 + (E if dropout else 0)
     if name == "ngacf_transform_bwd":
-        return 4 * N * R + sc + (N * 8 if dropout else 0)                       # dh, X, h -> dX ; dS
+        return 3 * N * R + sc + (N * 8 if dropout else 0)                       # dh, X -> dX ; dS (da goes through Xd^T dS: h is not read)
     if name == "ngacf_transform_bwd_dx":
         return 3 * N * R + (N * 8 if dropout else 0)                            # dh, Zprev (ELU') -> dX
     if name == "ngacf_transform_bwd_dw":

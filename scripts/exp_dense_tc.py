@@ -59,6 +59,28 @@ def run(U, I, H, act, p, seed=0):
     dref = 2 * dref
     ed = ((torch.cat([dXu, dXi]).double() - dref).abs().max() / dref.abs().max()).item()
 
+    # fused backward: dX, dW, da
+    dS = torch.randn(N, H, device=dev, generator=g)
+    gWu = [torch.zeros(D, DH, device=dev) for _ in range(H)]
+    gWi = [torch.zeros(D, DH, device=dev) for _ in range(H)]
+    ga = [torch.zeros(2 * DH, device=dev) for _ in range(H)]
+    gtab = torch.tensor([t.data_ptr() for t in gWu + gWi + ga], dtype=torch.int64, device=dev)
+    ws = torch.empty(ops.transform_bwd_workspace_bytes(U, I) // 4 + 16, device=dev)
+    fXu, fXi = torch.zeros(U, D, device=dev), torch.zeros(I, D, device=dev)
+    ops.transform_bwd(dh, dS, h, Xu, Xi, act, fm, scale, wtab, gtab, H, U, I, fXu, fXi, 0, 0, ws)
+    ops.transform_bwd(dh, dS, h, Xu, Xi, act, fm, scale, wtab, gtab, H, U, I, fXu, fXi, 1, 1, ws)    # accumulate: 2x
+    torch.cuda.synchronize()
+    efx = ((torch.cat([fXu, fXi]).double() - dref).abs().max() / dref.abs().max()).item()
+    dWu_ref = 2 * X[:U].T @ dh[:U].double()
+    dWi_ref = 2 * X[U:].T @ dh[U:].double()
+    ew = max(((torch.cat(gWu, 1).double() - dWu_ref).abs().max() / dWu_ref.abs().max()).item(),
+             ((torch.cat(gWi, 1).double() - dWi_ref).abs().max() / dWi_ref.abs().max()).item())
+    dau = 2 * (dS[:U].double().repeat_interleave(DH, 1) * href[:U]).sum(0)
+    dai = 2 * (dS[U:].double().repeat_interleave(DH, 1) * href[U:]).sum(0)
+    ga_u = torch.cat([t[:DH] for t in ga]).double()
+    ga_i = torch.cat([t[DH:] for t in ga]).double()
+    ea = max(((ga_u - dau).abs().max() / dau.abs().max()).item(), ((ga_i - dai).abs().max() / dai.abs().max()).item())
+
     def timeit(fn, n=20):
         for _ in range(3):
             fn()
@@ -72,7 +94,9 @@ def run(U, I, H, act, p, seed=0):
         return e0.elapsed_time(e1) / n * 1e3
     tf = timeit(lambda: ops.transform_fwd(Xu, Xi, act, fm, scale, wtab, H, U, I, h, s))
     td = timeit(lambda: ops.transform_bwd_dx(dh, Zu if act else None, Zi if act else None, act, fm, scale, wtab, H, U, I, dXu, dXi, 0))
-    print("U=%d I=%d H=%d act=%d p=%.1f  err h %.2e s %.2e dX %.2e   fwd %.1f us  dx %.1f us" % (U, I, H, act, p, eh, es, ed, tf, td), flush=True)
+    tb = timeit(lambda: ops.transform_bwd(dh, dS, h, Xu, Xi, act, fm, scale, wtab, gtab, H, U, I, fXu, fXi, 0, 0, ws))
+    print("U=%d I=%d H=%d act=%d p=%.1f  err h %.2e s %.2e dX %.2e | fused dX %.2e dW %.2e da %.2e | fwd %.1f us  dx %.1f us  bwd %.1f us"
+          % (U, I, H, act, p, eh, es, ed, efx, ew, ea, tf, td, tb), flush=True)
 
 
 if __name__ == "__main__":
