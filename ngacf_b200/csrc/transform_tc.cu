@@ -426,13 +426,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
 }
 // x = h + m + l, three bf16 terms (round-to-nearest, residuals exact in fp32); returns the terms of two values packed lo|hi
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
-    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(r0 - __bfloat162float(m0)), l1 = __float2bfloat16_rn(r1 - __bfloat162float(m1));
-    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    m = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
-    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // packed conversions (cvt.rn.bf16x2.f32): low half = first value; a bf16 widens to fp32 by a 16-bit shift
+    __nv_bfloat162 t = __floats2bfloat162_rn(x0, x1);
+    h = *reinterpret_cast<uint32_t*>(&t);
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
+    t = __floats2bfloat162_rn(r0, r1);
+    m = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(r0 - __uint_as_float(m << 16), r1 - __uint_as_float(m & 0xFFFF0000u));
+    l = *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ void split3x8(const float4 a, const float4 b, uint4& h, uint4& m, uint4& l) {
     split3_pair(a.x, a.y, h.x, m.x, l.x); split3_pair(a.z, a.w, h.y, m.y, l.y);
@@ -533,7 +534,8 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tD1 = tmem_base, tD2 = tmem_base + 64;
     uint32_t phase = 0;
-    const uint32_t aDH = smem_u32(sDH), aXD = smem_u32(sXD), aW = smem_u32(sW);
+    const uint64_t dDHk = smem_desc(smem_u32(sDH), PANEL), dWk = smem_desc(smem_u32(sW), WPANEL);      // K-major views (dX product)
+    const uint64_t dXDm = smem_desc_mn(smem_u32(sXD)), dDHm = smem_desc_mn(smem_u32(sDH));                // MN-major views (dW product)
     const int quarter = warp & 3, cq = warp >> 2;     // epilogue: TMEM lanes 32*quarter.., D1 columns 16*cq..
     const float sc = featmask ? scale : 1.f;
     bool first = true;
@@ -587,24 +589,25 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l)
+            // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l); descriptors = base + constant (start address field
+            // is in 16-byte units)
             // dX: D1 = sum DH_a W_b   (K-major: K = feature, 16 per MMA = two chunk panels)
 #pragma unroll
             for (int pr = 0; pr < 6; ++pr) {
                 const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
-                const uint32_t a0 = aDH + ta * DH_TERM, b0 = aW + tb * W_TERM;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma(tD1, smem_desc(a0 + ks * 2 * PANEL, PANEL), smem_desc(b0 + ks * 2 * WPANEL, WPANEL), IDESC_DX, (pr | ks) ? 1u : 0u);
+                    umma(tD1, dDHk + (uint64_t)((ta * DH_TERM + ks * 2 * PANEL) >> 4), dWk + (uint64_t)((tb * W_TERM + ks * 2 * WPANEL) >> 4), IDESC_DX,
+                         (pr | ks) ? 1u : 0u);
             }
             // dW | Q: D2 += sum XD_a^T [DH|DS]_b   (both MN-major: K = rows, 16 per MMA = two 8-row groups)
 #pragma unroll
             for (int pr = 0; pr < 6; ++pr) {
                 const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
-                const uint32_t a0 = aXD + ta * XD_TERM, b0 = aDH + tb * DH_TERM;
-#pragma unroll 4
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma(tD2, smem_desc_mn(a0 + ks * 256), smem_desc_mn(b0 + ks * 256), IDESC_DW, (!first || (pr | ks)) ? 1u : 0u);
+                    umma(tD2, dXDm + (uint64_t)((ta * XD_TERM + ks * 256) >> 4), dDHm + (uint64_t)((tb * DH_TERM + ks * 256) >> 4), IDESC_DW,
+                         (!first || (pr | ks)) ? 1u : 0u);
             }
             umma_commit(smem_u32(bar));
         }
