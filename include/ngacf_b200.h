@@ -126,7 +126,7 @@ int ngacf_bpr_loss_owned(const float* pos, const float* neg, int32_t B, float gs
 /* ---------------------------------------------------------------------------------------------
  * (a12) backward of one stage (closed form of SURVEY.md 3.4; the reference uses autograd).
  * prep:   Ghat = G/norm, dN = -(G . (Z-h))/norm per head.
- * edges:  mode 0 = user rows (CSR walk): computes d s_e per edge, stores it in ds_store[E*H];
+ * edges:  mode 0 = user rows (CSR walk): computes d s_e per edge, stores it in ds_store (float[E*8]; H = 1 stores (d s_e, e*keep) pairs);
  *         mode 1 = item rows (CSC walk): reads d s_e through adj_eid -- no atomics on either side.
  *         dh[n] = G[n] + sum_m drop(e) Ghat[m] + dS[n] (x) a_side,  dS[n] = sum_m ds.
  * transform_bwd: dW/da (accumulated into gtab, same layout as wtab), dX -> Gprev = dX*mask*scale*ELU'(Zprev)

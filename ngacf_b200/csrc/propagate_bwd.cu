@@ -95,7 +95,11 @@ __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_
     const int head = lane_head_b<H>(lane16);
     const int4 tk = __ldg(tasks + t);
     const int node = tk.x, beg = tk.y, end = tk.z, lid = tk.w;
-    const float sn = __ldg(s + (int64_t)node * H + head);
+    // H = 1: the user pass stores (d s_e, e*keep) per edge and the item pass reads the pair -- no logit gather, exp or mask byte
+    // there (in-box A/B: 60 -> 47 us per launch; for H = 8 the 64-byte pairs cost more than they save, profiles/r1e_ab_prefetch.txt)
+    constexpr bool PAIR = (H == 1);
+    constexpr bool NEED_MASK = DROP && !(PAIR && MODE == 1);
+    const float sn = (PAIR && MODE == 1) ? 0.f : __ldg(s + (int64_t)node * H + head);
     const float sc = DROP ? scale : 1.f;
     float4 ghn = make_float4(0.f, 0.f, 0.f, 0.f), hn = ghn;
     float dNn = 0.f;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_
     if (beg + lane16 < end) {
         m_l = ld_stream_i32(adj_idx + beg + lane16);
         eid_l = ld_stream_i32(adj_eid + beg + lane16);
-        if (DROP) mk_l = edgemask[eid_l];
+        if (NEED_MASK) mk_l = edgemask[eid_l];
     }
     for (int base = beg; base < end; base += 16) {
         const int nidx = base + 16 + lane16;
@@ -128,6 +132,14 @@ __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_
         for (int j = 0; j < cnt; ++j) {
             const int m = __shfl_sync(gm, m_l, j, 16);
             const int eid = __shfl_sync(gm, eid_l, j, 16);
+            if (PAIR && MODE == 1) {
+                const float4 g4 = ld_gather4(Ghat + (int64_t)m * D + lane16 * 4);
+                const float2 pr = __ldg(reinterpret_cast<const float2*>(ds_store) + eid);
+                acc.x = fmaf(pr.y, g4.x, acc.x); acc.y = fmaf(pr.y, g4.y, acc.y);
+                acc.z = fmaf(pr.y, g4.z, acc.z); acc.w = fmaf(pr.y, g4.w, acc.w);
+                dSacc += pr.x;
+                continue;
+            }
             const float sm = __ldg(s + (int64_t)m * H + head);
             const float4 gm4 = ld_gather4(Ghat + (int64_t)m * D + lane16 * 4);
             const float x = sn + sm;
@@ -148,13 +160,16 @@ __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_
                 const float det = head_reduce<H>(part, gm);
                 const float de = fmaf(det, keepsc, dNn + __ldg(dN + (int64_t)m * H + head));
                 ds = de * (-e) * (x > 0.f ? 1.f : LRELU_ALPHA);
-                if (head_writer<H>(lane16)) ds_store[(int64_t)eid * H + head] = ds;
+                if (head_writer<H>(lane16)) {
+                    if (PAIR) reinterpret_cast<float2*>(ds_store)[eid] = make_float2(ds, et);
+                    else ds_store[(int64_t)eid * H + head] = ds;
+                }
             } else {
                 ds = __ldg(ds_store + (int64_t)eid * H + head);
             }
             dSacc += ds;
         }
-        if (DROP && nidx < end) mk_n = edgemask[eid_n];
+        if (NEED_MASK && nidx < end) mk_n = edgemask[eid_n];
         m_l = m_n; eid_l = eid_n; mk_l = mk_n;
     }
     if (lid >= 0) {
