@@ -324,7 +324,7 @@ def main():
                 byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
                 share_of_step=top_ms_step / total_prof,
                 note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by L2->SM traffic (0.6-1.1 GB per "
-                     "launch at 9-12 TB/s, profiles/r1c_top_kernels_ncu_full.txt), DRAM traffic ~= algorithmic bytes (no re-reads); in the "
+                     "launch at 9-12 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic ~= algorithmic bytes (no re-reads); in the "
                      "HBM regime (sweep-30m) the same kernels reach 0.9-1.0 of the measured HBM peak (profiles/r1c_bench_sweep-30m.json)",
                 step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
                                 frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),

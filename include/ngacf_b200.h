@@ -86,6 +86,9 @@ int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream);
  * wtab: device array of 3*H pointers [W_u heads | W_i heads | a heads], the reference's own
  * parameter tensors (64,DH) and (1,2*DH).  U or I may be 0 (row-sharded multi-GPU calls process one side,
  * with every pointer pre-offset to the first row; ngacf_transform_bwd then leaves the absent side's gradients untouched).
+ * Implementation: tcgen05 tensor cores with fp32-class operand splits (3xTF32 forward and dX; three-term bf16 for the fused
+ * backward, whose dW product needs MN-major operands) -- csrc/transform_tc.cu; the environment variable NGACF_DENSE=ffma,
+ * read once per process, selects the CUDA-core kernels instead (parity triage).  Errors vs an fp64 product: 1e-6 / 4e-7.
  * ------------------------------------------------------------------------------------------- */
 int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
                         const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream);
@@ -130,7 +133,8 @@ int ngacf_bpr_loss_owned(const float* pos, const float* neg, int32_t B, float gs
  *         mode 1 = item rows (CSC walk): reads d s_e through adj_eid -- no atomics on either side.
  *         dh[n] = G[n] + sum_m drop(e) Ghat[m] + dS[n] (x) a_side,  dS[n] = sum_m ds.
  * transform_bwd: dW/da (accumulated into gtab, same layout as wtab), dX -> Gprev = dX*mask*scale*ELU'(Zprev)
- *         (stage > 0) or accumulated into the embedding gradients (stage 0).
+ *         (stage > 0) or accumulated into the embedding gradients (stage 0).  da is formed as W^T-contracted
+ *         Xd^T dS, so the `h` argument is not read any more (kept in the signature; may be NULL).
  * ------------------------------------------------------------------------------------------- */
 int ngacf_stage_bwd_prep(const float* G, const float* Z, const float* h, const float* norm, int32_t H, int64_t N,
                          float* Ghat, float* dN, void* stream);

@@ -505,7 +505,7 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
                                    const uint64_t* featmask, float scale, const float* const* wtab, float* const* gtab, int32_t H,
                                    int32_t U, int32_t I, float* dXu, float* dXi, int32_t accumulate_dx, int32_t accumulate_dw,
                                    void* workspace, size_t workspace_bytes, void* stream) {
-    NGACF_REQUIRE(dh && dS && h && wtab && gtab && workspace && U >= 0 && I >= 0 && (U == 0 || (Xu && dXu)) && (I == 0 || (Xi && dXi)),
+    NGACF_REQUIRE(dh && dS && wtab && gtab && workspace && U >= 0 && I >= 0 && (U == 0 || (Xu && dXu)) && (I == 0 || (Xi && dXi)),
                   "transform_bwd: null argument");
     if (U + I == 0) return NGACF_OK;
     NGACF_REQUIRE(H == 1 || H == 8, "transform_bwd: H must be 1 or 8");

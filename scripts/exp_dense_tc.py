@@ -97,10 +97,19 @@ def run(U, I, H, act, p, seed=0):
     tb = timeit(lambda: ops.transform_bwd(dh, dS, h, Xu, Xi, act, fm, scale, wtab, gtab, H, U, I, fXu, fXi, 0, 0, ws))
     print("U=%d I=%d H=%d act=%d p=%.1f  err h %.2e s %.2e dX %.2e | fused dX %.2e dW %.2e da %.2e | fwd %.1f us  dx %.1f us  bwd %.1f us"
           % (U, I, H, act, p, eh, es, ed, efx, ew, ea, tf, td, tb), flush=True)
+    return max(eh, es, ed, efx, ew, ea)
 
 
 if __name__ == "__main__":
     print("NGACF_DENSE =", os.environ.get("NGACF_DENSE", "(tc)"))
+    if "--check" in sys.argv:       # tests/test_gpu_parity.py::test_dense_transforms_vs_fp64: ragged, tiny and multi-tile shapes
+        worst = 0.0
+        for (U, I) in ((1, 1), (127, 129), (300, 517), (2048, 1000)):
+            for H in (8, 1):
+                for act, p in ((0, 0.0), (1, 0.2), (1, 0.0), (0, 0.5)):
+                    worst = max(worst, run(U, I, H, act, p, seed=U + H))
+        print("worst relative error", worst)
+        sys.exit(0 if worst < 2e-5 else 1)
     for (U, I) in ((300, 517), (29858, 40981)):
         for H in (8, 1):
             for act, p in ((0, 0.0), (1, 0.2)):

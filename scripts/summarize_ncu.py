@@ -62,5 +62,52 @@ def full(src, dst):
     print(open(dst).read()[:3000])
 
 
+def entry_key(kernel_name):
+    """C-ABI entry point / head count key used by bench.py's roofline table for an ncu kernel name, or None."""
+    import re
+    n = kernel_name
+    m = re.search(r"aggregate_fwd_kernel<(?:\(int\))?(\d+)", n)
+    if m:
+        return "ngacf_aggregate_fwd/H" + m.group(1)
+    m = re.search(r"stage_bwd_edges_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+)", n)
+    if m:
+        return "ngacf_stage_bwd_edges_%s/H%s" % ("users" if m.group(2) == "0" else "items", m.group(1))
+    m = re.search(r"transform_tc_kernel<(?:\(int\))?(\d+), (?:\(int\))?0", n)
+    if m:
+        return "ngacf_transform_fwd/H" + m.group(1)
+    m = re.search(r"transform_bwd_tc_kernel<(?:\(int\))?(\d+)", n)
+    if m:
+        return "ngacf_transform_bwd/H" + m.group(1)
+    m = re.search(r"stage_bwd_prep_kernel<(?:\(int\))?(\d+)", n)
+    if m:
+        return "ngacf_stage_bwd_prep/H" + m.group(1)
+    for k in ("score_pairs_bwd", "dropout_masks", "adam"):
+        if k + "_kernel" in n:
+            return {"adam": "ngacf_adam_step_dev"}.get(k, "ngacf_" + k)
+    return None
+
+
+def traffic(src, dst):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) per entry point -> json for bench.py's roofline.traffic"""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.OrderedDict()
+    for r in data:
+        key = entry_key(r[idx["Kernel Name"]])
+        if key is None:
+            continue
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    res = {k: dict(dram_bytes_per_launch=v[1] / v[0], launches=v[0]) for k, v in agg.items()}
+    json.dump(res, open(dst, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

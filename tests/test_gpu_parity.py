@@ -1,6 +1,8 @@
 """GPU parity tests: every CUDA entry point, called through the C-ABI (ctypes), against the oracle
 (oracle/port.py) and the committed reference fixtures (tests/golden).  Bit-exact for integer work
 (graph, masks, sampler), 1e-4 relative for fp32 (north_star)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -515,3 +517,19 @@ def test_multi_gacf_three_stage_vs_reference(golden):
     assert len(list(model.parameters())) == 2 + 3 * 17
     for k, v in model.named_parameters():
         assert rel_err(v.grad.cpu().numpy(), gz["grad_drop_f64/" + k]) < 1e-4, k
+
+
+# ------------------------------------------------------------------------------------------------
+# dense stage transforms: tensor-core (tcgen05 3xTF32 / bf16 three-term) and CUDA-core kernels against an fp64 product
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dense", ["tc", "ffma"])
+def test_dense_transforms_vs_fp64(dense):
+    """h, s, dX, dW, da of ngacf_transform_fwd / _bwd / _bwd_dx for ragged, single-row and multi-tile shapes, both heads layouts,
+    with and without ELU / feature dropout; the kernel family is chosen once per process (NGACF_DENSE), hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NGACF_DENSE=dense)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "exp_dense_tc.py"), "--check"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

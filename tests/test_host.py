@@ -44,6 +44,28 @@ def test_only_sm100a_code_in_the_library():
     assert archs == {"sm_100a"}, archs
 
 
+def test_dense_and_eval_kernels_use_the_tensor_cores():
+    """tcgen05 in the SASS: UTCHMMA (MMA), LDTM (TMEM loads) for the dense transforms and the AllNeg scorer."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from ngacf_b200 import _lib
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    per_kernel = {}
+    name = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+        elif name and "UTCHMMA" in line:
+            per_kernel[name] = per_kernel.get(name, 0) + 1
+    assert any("transform_tc_kernel" in k for k in per_kernel), sorted(per_kernel)
+    assert any("transform_bwd_tc_kernel" in k for k in per_kernel), sorted(per_kernel)
+    assert any("score_topk_tc_kernel" in k for k in per_kernel), sorted(per_kernel)
+    assert "LDTM" in sass
+
+
 def test_model_mirrors_reference_names_and_shapes():
     from graphattention.BPRLoss import BPRLoss  # noqa: F401  (re-export import path of the reference)
     from graphattention.SPUIGACF import SPUIGACF
