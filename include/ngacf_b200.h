@@ -88,7 +88,7 @@ int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream);
  * with every pointer pre-offset to the first row; ngacf_transform_bwd then leaves the absent side's gradients untouched).
  * Implementation: tcgen05 tensor cores with fp32-class operand splits (3xTF32 forward and dX; three-term bf16 for the fused
  * backward, whose dW product needs MN-major operands) -- csrc/transform_tc.cu; the environment variable NGACF_DENSE=ffma,
- * read once per process, selects the CUDA-core kernels instead (parity triage).  Errors vs an fp64 product: 1e-6 / 4e-7.
+ * read once per process, selects the CUDA-core kernels instead (parity triage).  Errors vs an fp64 product: 2-7e-7 either way.
  * ------------------------------------------------------------------------------------------- */
 int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,
                         const float* const* wtab, int32_t H, int32_t U, int32_t I, float* h, float* s, void* stream);

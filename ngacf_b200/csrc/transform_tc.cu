@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
+            // the two 2^-11 terms first, hi.hi last: every accumulation rounds at the accumulator's current magnitude
             for (int term = 0; term < 3; ++term) {
-                const uint64_t a0 = term == 1 ? dAlo : dAhi;
-                const uint64_t b0 = term == 2 ? dBlo : dBhi;
+                const uint64_t a0 = term == 0 ? dAlo : dAhi;
+                const uint64_t b0 = term == 1 ? dBlo : dBhi;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)          // K = 8 TF32 per MMA = two 16-byte k-chunk panels (start address field += bytes/16)
                     umma_tf32(tmem_base, a0 + (uint64_t)(ks * 2 * PANEL_A / 16), b0 + (uint64_t)(ks * 2 * PANEL_B / 16), (term | ks) ? 1u : 0u);
@@ -383,10 +384,13 @@ constexpr int OFF_W = OFF_XD + 3 * XD_TERM;          // [h | m | l]; also the sl
 constexpr int OFF_F = OFF_W + 3 * W_TERM;            // fp32 factor tile in the epilogue's staging layout (M = 128 slack too)
 constexpr int OFF_MISC = OFF_F + TM * 64 * 4;
 constexpr size_t SMEM_BYTES = OFF_MISC + 64 * 8 * 4 /*Q*/ + 64 /*barrier, tmem slot*/ + 128 /*alignment*/;
-constexpr uint32_t TMEM_COLS = 256;                  // D1: columns 0..63, D2: columns 64..143
+constexpr uint32_t TMEM_COLS = 256;                  // D1: columns 0..63, D2 (h.h): 64..143, D2s (corrections): 144..223
 constexpr uint32_t IDESC_DX = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);     // bf16, K-major, N = 64
 constexpr uint32_t IDESC_DW = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(80 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr int PART = 64 * 64 + 64;                   // floats per CTA partial (same layout as propagate_bwd.cu: dW then da)
+// term pairs ordered by weight: l.h, h.l, m.m (2^-16), m.h, h.m (2^-8), h.h
+__device__ constexpr int TERM_A[6] = {2, 0, 1, 1, 0, 0};
+__device__ constexpr int TERM_B[6] = {0, 2, 1, 0, 1, 0};
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tD1 = tmem_base, tD2 = tmem_base + 64;
+    const uint32_t tD1 = tmem_base, tD2 = tmem_base + 64, tD2s = tmem_base + 144;
     uint32_t phase = 0;
     const uint64_t dDHk = smem_desc(smem_u32(sDH), PANEL), dWk = smem_desc(smem_u32(sW), WPANEL);      // K-major views (dX product)
     const uint64_t dXDm = smem_desc_mn(smem_u32(sXD)), dDHm = smem_desc_mn(smem_u32(sDH));                // MN-major views (dW product)
@@ -589,12 +593,12 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l); descriptors = base + constant (start address field
-            // is in 16-byte units)
+            // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l), smallest products first: every accumulation rounds at
+            // the accumulator's current magnitude; descriptors = base + constant (start address field is in 16-byte units)
             // dX: D1 = sum DH_a W_b   (K-major: K = feature, 16 per MMA = two chunk panels)
 #pragma unroll
             for (int pr = 0; pr < 6; ++pr) {
-                const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
+                const int ta = TERM_A[pr], tb = TERM_B[pr];
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                     umma(tD1, dDHk + (uint64_t)((ta * DH_TERM + ks * 2 * PANEL) >> 4), dWk + (uint64_t)((tb * W_TERM + ks * 2 * WPANEL) >> 4), IDESC_DX,
@@ -602,12 +606,15 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
             }
             // dW | Q: D2 += sum XD_a^T [DH|DS]_b   (both MN-major: K = rows, 16 per MMA = two 8-row groups)
 #pragma unroll
+            // D2 lives across the CTA's tiles, so the five correction products (<= 2^-8 of h.h) get their own accumulator D2s
+            // and meet h.h only once, in the final fp32 add
             for (int pr = 0; pr < 6; ++pr) {
-                const int ta = pr == 2 || pr == 3 ? 1 : (pr == 5 ? 2 : 0), tb = pr == 1 || pr == 3 ? 1 : (pr == 4 ? 2 : 0);
+                const int ta = TERM_A[pr], tb = TERM_B[pr];
+                const uint32_t dst = pr == 5 ? tD2 : tD2s;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma(tD2, dXDm + (uint64_t)((ta * XD_TERM + ks * 256) >> 4), dDHm + (uint64_t)((tb * DH_TERM + ks * 256) >> 4), IDESC_DW,
-                         (!first || (pr | ks)) ? 1u : 0u);
+                    umma(dst, dXDm + (uint64_t)((ta * XD_TERM + ks * 256) >> 4), dDHm + (uint64_t)((tb * DH_TERM + ks * 256) >> 4), IDESC_DW,
+                         (!first || ((pr != 0 && pr != 5) | ks)) ? 1u : 0u);
             }
             umma_commit(smem_u32(bar));
         }
@@ -653,15 +660,19 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         if (quarter < 2) {
             float acc[16];
             const int k = 32 * quarter + lane;
+            float accs[16];
             tmem_ld16(tD2 + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * cq), acc);
+            tmem_ld16(tD2s + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * cq), accs);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<float4*>(part + k * 64 + 16 * cq + 4 * c) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                *reinterpret_cast<float4*>(part + k * 64 + 16 * cq + 4 * c) =
+                    make_float4(acc[4 * c] + accs[4 * c], acc[4 * c + 1] + accs[4 * c + 1], acc[4 * c + 2] + accs[4 * c + 2], acc[4 * c + 3] + accs[4 * c + 3]);
             if (cq == 0) {
-                float qv[8];
+                float qv[8], qs[8];
                 tmem_ld8(tD2 + ((uint32_t)(32 * quarter) << 16) + 64u, qv);
+                tmem_ld8(tD2s + ((uint32_t)(32 * quarter) << 16) + 64u, qs);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) Qs[k * 8 + j] = qv[j];
+                for (int j = 0; j < 8; ++j) Qs[k * 8 + j] = qv[j] + qs[j];
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
