@@ -63,6 +63,17 @@ class Propagation:
         ops.dropout_masks(fm, em, [H for H, _ in self.stages], self.g.N, self.g.E, seed, call, droprate, call_dev)
         self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
 
+    def use_dropout_buffers(self, droprate: float):
+        """Point the kernels at the own mask buffers WITHOUT generating masks: the trainer's captured step generates the masks of
+        step t+1 at the end of step t (overlapping Adam), so the next replay finds them ready."""
+        S = len(self.stages)
+        if droprate <= 0.0:
+            self.featmask, self.edgemask, self.scale = [None] * S, [None] * S, 1.0
+            return
+        self.scale = 1.0 / (1.0 - droprate)
+        fm, em = self._mask_buffers()
+        self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
+
     # ------------------------------------------------------------------------------------------
     def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor], after_first_kernel=None) -> torch.Tensor:
         """after_first_kernel: optional callback run right after the first (dense) kernel was enqueued -- the trainer uses it to

@@ -10,6 +10,8 @@ independent dropout per step, gradients of both summed, Adam with L2 weight deca
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -30,6 +32,8 @@ class FusedTrainer:
         # False: one fused dX+dW+da kernel per stage (shares the tile loads; measured best: 1.22 ms/step at Gowalla shape).
         # True: dX on the chain, dW/da deferred to a third stream (1.24 ms/step: ~40% more dense work for a shorter chain).
         self.split_dense_backward = split_dense_backward
+        # captured steps: masks of step t+1 are generated next to Adam of step t (NGACF_PREFETCH_MASKS=0: at the head of the step)
+        self.prefetch_masks = os.environ.get("NGACF_PREFETCH_MASKS", "1") != "0"
         dev = graph.device
         self.dev = dev
         self.props = [Propagation(graph, model.stages), Propagation(graph, model.stages)]      # pos / neg
@@ -138,9 +142,16 @@ class FusedTrainer:
         side = self.side
 
         def fwd(k, hook=None):
-            self.props[k].set_dropout(droprate, seed, call0 + k, None, cd)
+            if dev_counters and self.prefetch_masks:
+                self.props[k].use_dropout_buffers(droprate)
+            else:
+                self.props[k].set_dropout(droprate, seed, call0 + k, None, cd)
             Z = self.props[k].forward(uE, iE, self.wtabs, hook)
             ops.score_pairs(Z, g.U, self.users[:b], items[k][:b], scores[k][:b])
+        # captured steps find their dropout masks ready: they were generated at the end of the previous replay (or by
+        # _prime_masks before the first one), next to Adam instead of at the head of the critical path
+        premask = dev_counters and self.prefetch_masks
+        self._mask_args = (droprate, seed) if premask else None
         if side is not None:
             # the neg propagation starts one kernel after the pos one: its dense transform then overlaps the pos gather
             # kernel (FFMA-bound vs L2-fabric-bound), and so on down the two pipelines
@@ -149,10 +160,14 @@ class FusedTrainer:
 
             def start_side():
                 ev.record(cur)
-            # masks of the side propagation do not depend on anything: issue them first
-            with torch.cuda.stream(side):
-                self.props[1].set_dropout(droprate, seed, call0 + 1, None, cd)
-            self.props[0].set_dropout(droprate, seed, call0, None, cd)
+            if premask:
+                self.props[0].use_dropout_buffers(droprate)
+                self.props[1].use_dropout_buffers(droprate)
+            else:
+                # masks of the side propagation do not depend on anything: issue them first
+                with torch.cuda.stream(side):
+                    self.props[1].set_dropout(droprate, seed, call0 + 1, None, cd)
+                self.props[0].set_dropout(droprate, seed, call0, None, cd)
             Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side)
             ops.score_pairs(Z0, g.U, self.users[:b], items[0][:b], scores[0][:b])
             with torch.cuda.stream(side):
@@ -217,11 +232,37 @@ class FusedTrainer:
 
     def _step_update(self, dev_counters: bool):
         h = self.hyper
+        margs = getattr(self, "_mask_args", None) if dev_counters else None
+        mask_stream = self.side if self.side is not None else None
+        if margs is not None and mask_stream is not None:
+            # next step's masks (call counter + 2) on the side stream, concurrently with Adam; every reader of the current masks
+            # (the backward kernels) is already ordered before this point
+            cur = torch.cuda.current_stream()
+            mask_stream.wait_stream(cur)
+            with torch.cuda.stream(mask_stream):
+                ops.counter_add(self.call_dev, 2)
+                self._generate_masks(*margs)
         ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
         self.total.add_(self.loss.double())
         if dev_counters:
             ops.counter_add(self.row_dev, self._row_stride())
-            ops.counter_add(self.call_dev, 2)
+            if margs is None:
+                ops.counter_add(self.call_dev, 2)
+            elif mask_stream is None:
+                ops.counter_add(self.call_dev, 2)
+                self._generate_masks(*margs)
+            else:
+                torch.cuda.current_stream().wait_stream(mask_stream)
+
+    def _generate_masks(self, droprate, seed):
+        """masks of both propagations for the step whose first call index is the current value of call_dev"""
+        for k in (0, 1):
+            self.props[k].set_dropout(droprate, seed, k, None, self.call_dev)
+
+    def _prime_masks(self, droprate, seed):
+        """before the first replay of a captured step: the masks that step will read"""
+        if self.prefetch_masks:
+            self._generate_masks(droprate, seed)
 
     # ------------------------------------------------------------------------------------------
     def launches_per_step(self, droprate: float) -> int:
@@ -250,6 +291,7 @@ class FusedTrainer:
                 self._capture(droprate, seed)
             self.row_dev.copy_(torch.tensor([0, epoch], dtype=torch.int64), non_blocking=False)
             self.call_dev.fill_(m._call)
+            self._prime_masks(droprate, seed)
             for _ in range(n_full):
                 self._replay()
             m._call += 2 * n_full
@@ -339,6 +381,7 @@ class FusedTrainer:
             self._cursor = 0
         self.row_dev.copy_(torch.tensor([self._cursor, 0], dtype=torch.int64))
         self.call_dev.fill_(m._call)
+        self._prime_masks(droprate, seed)
         losses = []
         for _ in range(n_steps):
             if self._cursor + stride > n:
