@@ -40,15 +40,17 @@ __global__ void final_features_kernel(const float* __restrict__ Z, int64_t n4, f
 
 // Gradient scatter of the pair scores, deterministic and atomic-free.
 // entry e in [0,2B): e<B -> (row = users[e], other = U+items[e]); else (row = U+items[e-B], other = users[e-B]).
-// One CTA per entry; only the CTA of the FIRST entry of each distinct row survives.  It walks the batch
-// in 256-key chunks, compacts the matching entries in order, and its 16 lane-groups gather the matching
-// rows in parallel (4 loads in flight each); the 16 partial sums are combined in a fixed order.
-// A PairSampling batch is user-sorted, so a heavy user can own a whole batch: this keeps that case parallel.
+// One CTA per entry; only the CTA of the FIRST entry of each distinct row survives.  It reads 2048 keys of the batch at once
+// (eight independent loads per thread: one memory round trip), leaves if an earlier entry owns the row, compacts the matching
+// entries in batch order, and its 16 lane-groups gather the matching rows in parallel (4 loads in flight each); the 16 partial
+// sums are combined in a fixed order.  A PairSampling batch is user-sorted, so a heavy user can own a whole batch: this keeps
+// that case parallel.
+constexpr int SPB_SUPER = 2048;
 __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
                                                               const int64_t* __restrict__ items, const float* __restrict__ dscore, int B,
                                                               float* __restrict__ G) {
-    __shared__ int list[256];
-    __shared__ int warp_cnt[8];
+    __shared__ int list[SPB_SUPER];
+    __shared__ int warp_cnt[8][8];
     __shared__ float part[16][D];
     const int e = blockIdx.x;
     const bool user_row = e < B;
@@ -59,19 +61,40 @@ __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid >> 4, lane16 = tid & 15;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = 0; base < B; base += 256) {
-        const int j = base + tid;
-        const bool match = j < B && keys[j] == key;
-        const unsigned bal = __ballot_sync(0xffffffffu, match);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = 0, total = 0;
+    for (int sbase = 0; sbase < B; sbase += SPB_SUPER) {
+        int64_t kreg[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; if (w < warp) off += c; total += c; }
-        if (match) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+        for (int c = 0; c < 8; ++c) {
+            const int j = sbase + c * 256 + tid;
+            kreg[c] = j < B ? keys[j] : (int64_t)-1;
+        }
+        unsigned mbits = 0;
+        bool earlier = false;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = sbase + c * 256 + tid;
+            const bool m = kreg[c] == key;                   // ids are non-negative: the -1 padding never matches
+            mbits |= (unsigned)m << c;
+            earlier |= m && j < eb;
+        }
+        if (__syncthreads_or(earlier)) return;               // an earlier entry owns this row (block-uniform)
+        unsigned bal[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            bal[c] = __ballot_sync(0xffffffffu, (mbits >> c) & 1u);
+            if (lane == 0) warp_cnt[c][warp] = __popc(bal[c]);
+        }
         __syncthreads();
-        if (total > 0 && list[0] < eb) return;           // an earlier entry owns this row (block-uniform)
-        for (int q0 = grp; q0 < total; q0 += 64) {       // group g takes matches g, g+16, g+32, g+48 per round
+        int total = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                        // batch order: chunk, warp, lane
+            int off = total;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const int cw = warp_cnt[c][w]; if (w < warp) off += cw; total += cw; }
+            if ((mbits >> c) & 1u) list[off + __popc(bal[c] & ((1u << lane) - 1u))] = sbase + c * 256 + tid;
+        }
+        __syncthreads();
+        for (int q0 = grp; q0 < total; q0 += 64) {           // group g takes matches g, g+16, g+32, g+48 per round
             int jj[4]; float c[4]; float4 f[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -92,7 +115,7 @@ __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __res
                 acc.x = fmaf(c[q], fo.x, acc.x); acc.y = fmaf(c[q], fo.y, acc.y); acc.z = fmaf(c[q], fo.z, acc.z); acc.w = fmaf(c[q], fo.w, acc.w);
             }
         }
-        __syncthreads();                                  // list is rewritten by the next chunk
+        __syncthreads();                                      // list is rewritten by the next 2048 keys
     }
     *reinterpret_cast<float4*>(&part[grp][lane16 * 4]) = acc;
     __syncthreads();
