@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(1024) bpr_loss_kernel(const float* __restrict_
 struct AdamEntry { float* p; const float* g; float* m; float* v; int64_t numel; };
 constexpr int ADAM_MAX_TENSORS = 64;
 
-__global__ void __launch_bounds__(256) adam_kernel(const AdamEntry* __restrict__ tab, int n_tensors, float lr_over_bc1, float inv_sqrt_bc2,
+__global__ void __launch_bounds__(256, 4) adam_kernel(const AdamEntry* __restrict__ tab, int n_tensors, float lr_over_bc1, float inv_sqrt_bc2,
                                                    const double* __restrict__ state, float beta1, float beta2, float eps, float wd) {
     if (state) { lr_over_bc1 = (float)state[1]; inv_sqrt_bc2 = (float)state[2]; }
     __shared__ AdamEntry ent[ADAM_MAX_TENSORS];
@@ -181,12 +181,20 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamEntry* __restrict__
     }
     __syncthreads();
     const int64_t total = pref[n_tensors];
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
-        int lo = 0, hi = n_tensors - 1;
+    // a thread's chunk index only grows: one binary search, then a forward scan (almost always zero steps -- two tensors hold
+    // 99.8 % of the chunks); the search per chunk was a third of the kernel's instruction stream (ncu: 350 instructions per
+    // warp and chunk, issue-bound at 4 CTAs/SM)
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0;
+    {
+        int hi = n_tensors - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
             if (pref[mid] <= c) lo = mid; else hi = mid - 1;
         }
+    }
+    for (; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+        while (c >= pref[lo + 1]) ++lo;
         const AdamEntry& en = ent[lo];
         const int64_t off = (c - pref[lo]) * 4;
         const int cnt = (int)min((int64_t)4, en.numel - off);
