@@ -264,53 +264,82 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
     const float sn = __ldg(s + (int64_t)node * H + head);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 0.f;
-    // H=1: the adjacency slice of batch b+1 (and its edge ids) is requested before batch b's gathers and the mask bytes right
-    // after them, so the only dependent round trips on a row's chain are the gathers.  Measured per instantiation (in-box A/B,
-    // profiles/r1e_ab_prefetch.txt): helps <1,*>, hurts <8,*> (registers), hence the compile-time switch.
-    constexpr bool PF = (H == 1);
-    int m_l = 0, eid_n = 0;
-    unsigned mk_l = 0xFFu;
-    if (PF && beg + lane16 < end) {
-        m_l = ld_stream_i32(adj_idx + beg + lane16);
-        if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + beg + lane16)];
-    }
-    for (int base = beg; base < end; base += 16) {
-        const int nidx = base + 16 + lane16;
-        int m_n = 0;
-        unsigned mk_n = 0xFFu;
-        if (PF) {
-            if (nidx < end) {
-                m_n = ld_stream_i32(adj_idx + nidx);
-                if (DROP) eid_n = ld_stream_i32(adj_eid + nidx);
+    if constexpr (H == 1) {
+        // One logit per edge: lane l owns edge base+l of the batch and computes its weight ONCE (before, all 16 lanes recomputed
+        // every weight: ~30 instructions per visit, the kernel was issue-bound at 63 %); the visit loop is two shuffles, one
+        // 16-byte gather and four FMAs.  The adjacency slice, logit and mask byte of batch b+1 are requested during batch b.
+        // three-stage software pipeline (issue is in order: nothing the visit loop needs may still be in flight when a batch
+        // starts): at the top of batch b the adjacency slice of b+2 and the logits / mask bytes of b+1 are requested, the weights
+        // of b come from loads issued a whole batch earlier
+        float rs_l = 0.f, s_c = 0.f;
+        int m_c = 0, m_1 = 0, eid_1 = 0;
+        unsigned mk_c = 1u;
+        if (beg + lane16 < end) {
+            m_c = ld_stream_i32(adj_idx + beg + lane16);
+            if (DROP) mk_c = edgemask[ld_stream_i32(adj_eid + beg + lane16)];
+        }
+        if (beg + 16 + lane16 < end) {
+            m_1 = ld_stream_i32(adj_idx + beg + 16 + lane16);
+            if (DROP) eid_1 = ld_stream_i32(adj_eid + beg + 16 + lane16);
+        }
+        if (beg + lane16 < end) s_c = __ldg(s + m_c);
+        for (int base = beg; base < end; base += 16) {
+            const int i1x = base + 16 + lane16, i2x = base + 32 + lane16;
+            int m_2 = 0, eid_2 = 0;
+            float s_1 = 0.f;
+            unsigned mk_1 = 1u;
+            if (i2x < end) {
+                m_2 = ld_stream_i32(adj_idx + i2x);
+                if (DROP) eid_2 = ld_stream_i32(adj_eid + i2x);
             }
-        } else {
+            if (i1x < end) {
+                s_1 = __ldg(s + m_1);
+                if (DROP) mk_1 = edgemask[eid_1];
+            }
+            const float w_l = base + lane16 < end ? edge_weight(sn + s_c) : 0.f;
+            rs_l += w_l;
+            const float wd_l = DROP ? ((mk_c & 1u) ? w_l * scale : 0.f) : w_l;
+            const int cnt = min(16, end - base);
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) {
+                const int m = __shfl_sync(gm, m_c, j, 16);
+                const float wd = __shfl_sync(gm, wd_l, j, 16);
+                const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
+                acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
+            }
+            m_c = m_1; m_1 = m_2; eid_1 = eid_2; s_c = s_1; mk_c = mk_1;
+        }
+        rs_l += __shfl_xor_sync(gm, rs_l, 1, 16);
+        rs_l += __shfl_xor_sync(gm, rs_l, 2, 16);
+        rs_l += __shfl_xor_sync(gm, rs_l, 4, 16);
+        rs_l += __shfl_xor_sync(gm, rs_l, 8, 16);
+        rs = rs_l;
+    } else {
+        for (int base = beg; base < end; base += 16) {
             const int idx = base + lane16;
-            m_l = 0;
-            mk_l = 0xFFu;
+            int m_l = 0;
+            unsigned mk_l = 0xFFu;
             if (idx < end) {
                 m_l = ld_stream_i32(adj_idx + idx);
                 if (DROP) mk_l = edgemask[ld_stream_i32(adj_eid + idx)];
             }
-        }
-        const int cnt = min(16, end - base);
+            const int cnt = min(16, end - base);
 #pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            const int m = __shfl_sync(gm, m_l, j, 16);
-            const float sm = __ldg(s + (int64_t)m * H + head);
-            const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
-            const float w = edge_weight(sn + sm);
-            rs += w;
-            float wd = w;
-            if (DROP) {
-                const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
-                wd = ((mk >> head) & 1u) ? w * scale : 0.f;
+            for (int j = 0; j < cnt; ++j) {
+                const int m = __shfl_sync(gm, m_l, j, 16);
+                const float sm = __ldg(s + (int64_t)m * H + head);
+                const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                const float w = edge_weight(sn + sm);
+                rs += w;
+                float wd = w;
+                if (DROP) {
+                    const unsigned mk = __shfl_sync(gm, mk_l, j, 16);
+                    wd = ((mk >> head) & 1u) ? w * scale : 0.f;
+                }
+                acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
+                acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
             }
-            acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
-            acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
-        }
-        if (PF) {
-            if (DROP && nidx < end) mk_n = edgemask[eid_n];
-            m_l = m_n; mk_l = mk_n;
         }
     }
     if (lid >= 0) {
