@@ -278,3 +278,57 @@ def test_multi_gacf_three_stage_matches_reference(golden):
     grads = port.state_dict_from_params(port.propagate_backward(dF, p, g, caches))
     for k, v in grads.items():
         assert rel_err(v.numpy(), gz["grad_drop_f64/" + k]) < 1e-11, k
+
+
+# ----------------------------------------------------------------------------------------------
+# NegSampling / SampledNeg
+# ----------------------------------------------------------------------------------------------
+def _neg_case(gz):
+    U, I = int(gz["U"]), int(gz["I"])
+    it = port.build_interactions(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"])
+    g = port.build_graph(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]),
+                                   np.concatenate([gz["train_i"], gz["test_i"]])]), U, I)
+    return U, I, it, g, port.AllPositives(it)
+
+
+def test_neg_sampling_epochs_match_reference(golden):
+    """Two reference train_neg_sample epochs (BCE-with-logits on 1 positive + 4 sampled negatives, dropout 0.2, Adam) with the
+    specified negatives and dropout masks injected, then the reference's eval_neg_sample (HR/NDCG@10 over 1 + 99 candidates)."""
+    gz = golden("neg_sampling_small")
+    U, I, it, g, allpos = _neg_case(gz)
+    p = port.params_from_state_dict(sd_from(gz, "sd0/"), torch.float32)
+    st = port.adam_init(p)
+    call, losses = 0, []
+    for ep in range(int(gz["epochs"])):
+        loss, call = port.train_neg_sample(p, g, it, allpos, gz["train_i"].astype(np.int32), int(gz["batch"]), st, float(gz["lr"]),
+                                           float(gz["wd"]), ep, int(gz["sample_seed"]), float(gz["droprate"]), int(gz["drop_seed"]), call)
+        losses.append(loss)
+    assert rel_err(np.array(losses), gz["epoch_losses"]) < 1e-4
+    sd1 = port.state_dict_from_params(p)
+    for k, v in sd1.items():
+        assert rel_err(v.numpy(), gz["sd1/" + k]) < 2e-3, k
+    # evaluation on the reference's trained weights
+    p1 = port.params_from_state_dict(sd_from(gz, "sd1/"), torch.float32)
+    F, _ = port.propagate(p1, g)
+    hr, nd, _ = port.eval_sampled_neg(F.numpy(), it, allpos, gz["test_u"].astype(np.int32), gz["test_i"].astype(np.int32),
+                                      int(gz["eval_seed"]), int(gz["top_k"]))
+    assert abs(hr - float(gz["eval/hr"])) < 1e-12 and abs(nd - float(gz["eval/ndcg"])) < 1e-9
+
+
+def test_sample_negs_properties():
+    """K distinct negatives, none of them a positive of the user, column 0 = the row's own item; deterministic in (seed, epoch)."""
+    U, I, E = 80, 150, 1500
+    u, i = port.synth_bipartite(U, I, E, 3)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, 4)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    ap = port.AllPositives(it)
+    a = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), 5, 70, 9, 2, 4, port.NEG_TAG_TRAIN)
+    b = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), 5, 70, 9, 2, 4, port.NEG_TAG_TRAIN)
+    c = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), 5, 70, 9, 3, 4, port.NEG_TAG_TRAIN)
+    assert np.array_equal(a[1], b[1]) and not np.array_equal(a[1], c[1])
+    users, items = a
+    assert np.array_equal(items[:, 0], ti[5:70]) and np.array_equal(users[:, 0], tu[5:70])
+    for r in range(users.shape[0]):
+        pos = set(ap.items[ap.ptr[users[r, 0]]:ap.ptr[users[r, 0] + 1]].tolist())
+        negs = items[r, 1:].tolist()
+        assert len(set(negs)) == 4 and not (set(negs) & pos) and set(negs) <= set(it.pool.tolist())
