@@ -215,6 +215,24 @@ int ngacf_eval_metrics(const int32_t* top_ids, const int32_t* users, int32_t n_u
                        const int32_t* test_items, uint8_t* hits, double* sums, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NegSampling training / SampledNeg evaluation (the CLI's default modes, run_Gowalla.py:179-180).
+ * Replaces loadGowalla.py:56-60,80-83,101-105 (negative sets + random.sample), the tensor building of
+ * train_eval_Gowalla.py:58-77,226-243, BCEWithLogitsLoss (run_Gowalla.py:110) and torch.topk + hit/ndcg
+ * (train_eval_Gowalla.py:251-270, graphattention/evaluation.py).  Propagation, ngacf_score_pairs(_bwd) and Adam are shared.
+ *   sample_negs: rows [row_begin,row_end) of (rows_user, rows_item); all_ptr/all_rank = CSR of every user's train+test items as
+ *     ranks in the sorted pool; writes users/items int64[(n)(K+1)]: column 0 the row's positive, then K distinct negatives
+ *     (specified Philox stream, oracle/port.py:sample_negs); tag = 0x4E54 train / 0x4E45 eval; row_dev as in ngacf_sample_pairs.
+ *   bce_logits_loss: mean over n scores of softplus(x) - y x with y = 1 at every `group`-th element; dscore may be NULL.
+ *   rank_metrics: per row of `group` scores, rank of column 0 (strictly larger scores); sums[0] += [rank < top_k],
+ *     sums[1] += 1/log2(rank+2) for hits (caller zero-fills sums; HR/NDCG = sums / n_rows).
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_sample_negs(const int32_t* rows_user, const int32_t* rows_item, const int32_t* all_ptr, const int32_t* all_rank,
+                      const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end, const int64_t* row_dev, uint64_t seed,
+                      uint32_t epoch, int32_t K, uint32_t tag, int64_t* users, int64_t* items, void* stream);
+int ngacf_bce_logits_loss(const float* scores, int64_t n, int32_t group, float* loss, float* dscore, void* stream);
+int ngacf_rank_metrics(const float* scores, int64_t n_rows, int32_t group, int32_t top_k, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,9 @@ SIGNATURES = {
     "ngacf_feature_mask": (c_int32, [P, c_int64, c_uint64, c_uint32, P, c_uint32, c_float, P]),
     "ngacf_edge_mask": (c_int32, [P, c_int64, c_int32, c_uint64, c_uint32, P, c_uint32, c_float, P]),
     "ngacf_dropout_masks": (c_int32, [P, P, P, c_int32, c_int64, c_int64, c_uint64, c_uint32, P, c_float, P]),
+    "ngacf_sample_negs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, c_int32, c_uint32, P, P, P]),
+    "ngacf_bce_logits_loss": (c_int32, [P, c_int64, c_int32, P, P, P]),
+    "ngacf_rank_metrics": (c_int32, [P, c_int64, c_int32, c_int32, P, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_transform_fwd": (c_int32, [P, P, c_int32, P, c_float, P, c_int32, c_int32, c_int32, P, P, P]),
     "ngacf_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, c_int32, P]),

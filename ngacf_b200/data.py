@@ -18,6 +18,8 @@ class Interactions:
     pool / in_pool  : sorted unique item ids of rt = train+test (item_pool, loadGowalla.py:64) / its bitmap
     test_ptr/items  : CSR of test items per user, sorted
     eval_users      : users present in train AND test (inner merge, loadGowalla.py:91)
+    train_rows_item, test_rows_user/item : the (user, item) rows of train_df / test_df in file order (NegSampling, SampledNeg)
+    all_ptr/all_rank: CSR of train+test items per user as pool ranks (positives_negtives, loadGowalla.py:56-60)
     n_train_users   : divisor of the metrics (train_eval_Gowalla.py:283)
     """
 
@@ -54,6 +56,14 @@ class Interactions:
         self.pool, self.in_pool = t(pool), t(in_pool, torch.uint8)
         self.test_ptr, self.test_items = t(sp), t(si)
         self.eval_users = t(np.nonzero(has_train & has_test)[0])
+        # NegSampling / SampledNeg: the rows' own items in file order, and the per-user union of train and test
+        # items (positives_negtives, loadGowalla.py:56-60) as ranks in the pool -- the negatives are "pool minus this row"
+        self.train_rows_item = t(train_i)
+        self.test_rows_user, self.test_rows_item = t(test_u), t(test_i)
+        self.n_test_rows = int(test_u.shape[0])
+        ap, ai = csr(np.concatenate([train_u, test_u]), np.concatenate([train_i, test_i]))
+        self.all_ptr, self.all_rank = t(ap), t(np.searchsorted(pool, ai))
+        self.host.update(all_ptr=ap, all_items=ai)
         self.device = torch.device(device)
 
     def __len__(self):      # len(train_df) in train_bpr, len(test_pos_neg) in eval_neg_all
@@ -85,4 +95,29 @@ class Interactions:
             si = np.concatenate([np.fromiter(s, np.int64, len(s)) for s in test_pos["positive_items"].values])
         else:
             su = si = np.zeros(0, np.int64)
+        return cls(U, I, tu, ti, su, si, device, pool=pool)
+
+    @classmethod
+    def from_negsampling_frames(cls, U, I, pos_neg, train_df=None, test_df=None, device="cuda"):
+        """NegSampling / SampledNeg structures of the reference (run_Gowalla.py:89-92): pos_neg = positives_negtives(rt) with ALL
+        positives of a user (train and test, loadGowalla.py:56-60), train_df / test_df = (userId, itemId) rows in file order.
+        Whichever of the two frames is absent is reconstructed as "all positives minus the given rows" (its row order is not used)."""
+        first = pos_neg.iloc[0]
+        pool = np.array(sorted(set(first["positive_items"]) | set(first["negative_items"])), np.int64)
+        au = np.concatenate([np.full(len(s), int(u), np.int64) for u, s in zip(pos_neg["userId"].values, pos_neg["positive_items"].values)])
+        ai = np.concatenate([np.fromiter(s, np.int64, len(s)) for s in pos_neg["positive_items"].values])
+
+        def rows(df):
+            return np.asarray(df["userId"].values, np.int64), np.asarray(df["itemId"].values, np.int64)
+
+        def minus(u, i):       # all positives not among the rows (u, i)
+            key_all = au * np.int64(I) + ai
+            rest = np.setdiff1d(key_all, u * np.int64(I) + i)
+            return rest // I, rest % I
+        if train_df is not None:
+            tu, ti = rows(train_df)
+            su, si = rows(test_df) if test_df is not None else minus(tu, ti)
+        else:
+            su, si = rows(test_df)
+            tu, ti = minus(su, si)
         return cls(U, I, tu, ti, su, si, device, pool=pool)

@@ -160,3 +160,20 @@ def score_topk_tc(F, U, I, users, inter, top_ids, top_scores, fallback, ws):
 def eval_metrics(top_ids, users, inter, hits, sums, ws):
     _lib.call("ngacf_eval_metrics", _p(top_ids), _p(users), users.numel(), _p(inter.test_ptr), _p(inter.test_items), _p(hits),
               _p(sums), _p(ws), ws.numel() * ws.element_size(), _s())
+
+
+NEG_TAG_TRAIN, NEG_TAG_EVAL = 0x4E54, 0x4E45
+
+
+def sample_negs(inter, rows_user, rows_item, row_begin, row_end, seed, epoch, K, tag, users, items, row_dev=None):
+    """K distinct negatives per (user, positive) row: users/items int64[(row_end-row_begin)*(K+1)], column 0 = the positive"""
+    _lib.call("ngacf_sample_negs", _p(rows_user), _p(rows_item), _p(inter.all_ptr), _p(inter.all_rank), _p(inter.pool), int(inter.pool.numel()),
+              int(row_begin), int(row_end), _p(row_dev), int(seed), int(epoch), int(K), int(tag), _p(users), _p(items), _s())
+
+
+def bce_logits_loss(scores, group, loss, dscore=None):
+    _lib.call("ngacf_bce_logits_loss", _p(scores), scores.numel(), int(group), _p(loss), _p(dscore), _s())
+
+
+def rank_metrics(scores, group, top_k, sums):
+    _lib.call("ngacf_rank_metrics", _p(scores), scores.numel() // int(group), int(group), int(top_k), _p(sums), _s())

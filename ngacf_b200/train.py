@@ -21,6 +21,8 @@ from .propagation import Propagation
 
 
 class FusedTrainer:
+    CALLS_PER_STEP = 2          # dropout call indices consumed per step (pos and neg propagation)
+
     def __init__(self, model, inter: Interactions, graph: BipartiteGraph, batch_size: int, optim, sample_seed: int,
                  use_cuda_graph: bool = True, two_streams: bool = True, split_dense_backward: bool = False):
         self.model, self.inter, self.g = model, inter, graph
@@ -240,16 +242,16 @@ class FusedTrainer:
             cur = torch.cuda.current_stream()
             mask_stream.wait_stream(cur)
             with torch.cuda.stream(mask_stream):
-                ops.counter_add(self.call_dev, 2)
+                ops.counter_add(self.call_dev, self.CALLS_PER_STEP)
                 self._generate_masks(*margs)
         ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
         self.total.add_(self.loss.double())
         if dev_counters:
             ops.counter_add(self.row_dev, self._row_stride())
             if margs is None:
-                ops.counter_add(self.call_dev, 2)
+                ops.counter_add(self.call_dev, self.CALLS_PER_STEP)
             elif mask_stream is None:
-                ops.counter_add(self.call_dev, 2)
+                ops.counter_add(self.call_dev, self.CALLS_PER_STEP)
                 self._generate_masks(*margs)
             else:
                 torch.cuda.current_stream().wait_stream(mask_stream)
@@ -294,11 +296,11 @@ class FusedTrainer:
             self._prime_masks(droprate, seed)
             for _ in range(n_full):
                 self._replay()
-            m._call += 2 * n_full
+            m._call += self.CALLS_PER_STEP * n_full
         else:
             for bi in range(n_full):
                 self._step_body(self.B, epoch, droprate, seed, bi * stride + self._row_offset(), m._call, False)
-                m._call += 2
+                m._call += self.CALLS_PER_STEP
         if n_batches > n_full:         # tail step (len % stride rows), eager; a rank may get fewer rows or none
             lo = min(n, n_full * stride + self._row_offset())
             hi = min(n, lo + self.B)
@@ -307,7 +309,7 @@ class FusedTrainer:
                     self._step_body(hi - lo, epoch, droprate, seed, lo, m._call, False)
                 else:
                     self._empty_step()
-                m._call += 2
+                m._call += self.CALLS_PER_STEP
         self._sync_optimizer_state()
         return self._epoch_loss(n)
 
@@ -394,7 +396,7 @@ class FusedTrainer:
             self._cursor += stride
             if read_loss:
                 losses.append(float(self.loss.item()))
-        m._call += 2 * n_steps
+        m._call += self.CALLS_PER_STEP * n_steps
         return losses
 
     def units_per_step(self) -> int:
@@ -423,7 +425,7 @@ class FusedTrainer:
         _lib.PROFILE = []
         try:
             for k in range(n_steps):
-                self._step_body(self.B, 0, droprate, self._dropout_seed(m._seed()), k * self.B, 2 * k, False)
+                self._step_body(self.B, 0, droprate, self._dropout_seed(m._seed()), k * self.B, self.CALLS_PER_STEP * k, False)
             torch.cuda.synchronize(self.dev)
             out = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in _lib.PROFILE]
         finally:

@@ -533,3 +533,108 @@ def test_dense_transforms_vs_fp64(dense):
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "exp_dense_tc.py"), "--check"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# NegSampling training / SampledNeg evaluation
+# ------------------------------------------------------------------------------------------------
+def test_sample_negs_bit_exact():
+    """K distinct negatives per row from the specified Philox stream: kernel == oracle, for the train (K=4) and eval (K=99) tags,
+    with and without the device-resident row/epoch offsets."""
+    from ngacf_b200 import ops
+    it, dit, _ = make_interactions(300, 517, 9000, 5)
+    ap = port.AllPositives(it)
+    assert np.array_equal(dit.all_ptr.cpu().numpy(), ap.ptr) and np.array_equal(dit.all_rank.cpu().numpy(), ap.rank)
+    for K, tag, rows_u, rows_i, hu, hi in ((4, ops.NEG_TAG_TRAIN, dit.train_rows_user, dit.train_rows_item, it.train_rows_user, None),
+                                            (99, ops.NEG_TAG_EVAL, dit.test_rows_user, dit.test_rows_item, None, None)):
+        hu = rows_u.cpu().numpy()
+        hi = rows_i.cpu().numpy()
+        lo, hi_row = 7, min(7 + 600, hu.shape[0])
+        n = hi_row - lo
+        pu = torch.zeros(n * (K + 1), dtype=torch.int64, device=DEV)
+        pi = torch.zeros_like(pu)
+        ops.sample_negs(dit, rows_u, rows_i, lo, hi_row, 0xABCDEF0123, 3, K, tag, pu, pi)
+        eu, ei = port.sample_negs(it, ap, hu, hi, lo, hi_row, 0xABCDEF0123, 3, K, tag)
+        assert np.array_equal(pu.cpu().numpy().reshape(n, K + 1), eu) and np.array_equal(pi.cpu().numpy().reshape(n, K + 1), ei)
+        # device counters: row_begin + row_dev[0], epoch + row_dev[1]
+        rd = torch.tensor([lo, 3], dtype=torch.int64, device=DEV)
+        pi2 = torch.zeros_like(pi)
+        ops.sample_negs(dit, rows_u, rows_i, 0, n, 0xABCDEF0123, 0, K, tag, pu, pi2, rd)
+        assert torch.equal(pi, pi2)
+
+
+def test_bce_loss_and_rank_metrics():
+    from ngacf_b200 import ops
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal(5 * 777) * 4).astype(np.float32)
+    xt = torch.from_numpy(x).to(DEV)
+    loss = torch.zeros((), device=DEV)
+    dx = torch.zeros_like(xt)
+    ops.bce_logits_loss(xt, 5, loss, dx)
+    y = torch.zeros(777, 5, dtype=torch.float64)
+    y[:, 0] = 1
+    l_ref, d_ref = port.bce_logits(torch.from_numpy(x).double(), y.reshape(-1))
+    assert abs(loss.item() - float(l_ref)) / float(l_ref) < 1e-5
+    assert rel_err(dx.cpu().numpy(), d_ref.numpy()) < 1e-5
+    sc = rng.standard_normal((333, 100)).astype(np.float32)
+    sc[5, 7] = sc[5, 0]            # a tie with the positive does not outrank it
+    sums = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ops.rank_metrics(torch.from_numpy(sc).to(DEV).reshape(-1), 100, 10, sums)
+    hr, nd = port.rank_metrics(sc, 10)
+    got = (sums / 333).tolist()
+    assert abs(got[0] - hr) < 1e-12 and abs(got[1] - nd) < 1e-12
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_neg_sampling_epochs_vs_reference(golden, fused):
+    """Two NegSampling epochs (BCE on 1 + 4 sampled items per train row, dropout 0.2, Adam; GPU sampler + GPU Philox masks) vs the
+    reference's train_neg_sample with the same samples and masks injected, then SampledNeg HR/NDCG@10 vs its eval_neg_sample
+    (tests/golden/neg_sampling_small.npz)."""
+    import train_eval_Gowalla as T
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.optim import FusedAdam
+    gz = golden("neg_sampling_small")
+    model = make_model(gz, "sd0/", float(gz["droprate"]))
+    U, I = int(gz["U"]), int(gz["I"])
+    dit = Interactions.from_arrays(U, I, gz["train_u"], gz["train_i"], gz["test_u"], gz["test_i"], device=DEV)
+    adj = torch.from_numpy(np.stack([np.concatenate([gz["train_u"], gz["test_u"]]), np.concatenate([gz["train_i"], gz["test_i"]])]))
+    optim = FusedAdam(model.parameters(), lr=float(gz["lr"]), weight_decay=float(gz["wd"]))
+    model.drop_seed = int(gz["drop_seed"])
+    lossfn = torch.nn.BCEWithLogitsLoss()
+    losses = [T.train_neg_sample(model, int(gz["batch"]), dit, dit, adj, optim, lossfn, False, epoch=ep, sample_seed=int(gz["sample_seed"]),
+                                 fused=fused) for ep in range(int(gz["epochs"]))]
+    assert rel_err(np.array(losses), gz["epoch_losses"]) < 1e-4
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    for k in sd:
+        assert rel_err(sd[k], gz["sd1/" + k]) < 5e-3, k
+    # evaluation on the REFERENCE's trained weights: the same candidates, scores equal to 1e-4 -> identical ranks
+    ref = make_model(gz, "sd1/", float(gz["droprate"]))
+    hr, nd = T.eval_neg_sample(ref, 512, dit, dit, adj, int(gz["top_k"]), False, seed=int(gz["eval_seed"]))
+    assert abs(hr - float(gz["eval/hr"])) < 1e-12 and abs(nd - float(gz["eval/ndcg"])) < 1e-9
+    hr2, nd2 = T.eval_neg_sample(model, 512, dit, dit, adj, int(gz["top_k"]), False, seed=int(gz["eval_seed"]))
+    assert abs(hr2 - float(gz["eval/hr"])) < 0.05 and abs(nd2 - float(gz["eval/ndcg"])) < 0.05
+
+
+def test_neg_sampling_reference_frames():
+    """train_neg_sample / eval_neg_sample accept the reference's pandas structures (positives_negtives sets + (userId,itemId) rows)."""
+    import pandas as pd
+    import train_eval_Gowalla as T
+    from ngacf_b200.data import Interactions
+    U, I, E = 90, 140, 1500
+    u, i = port.synth_bipartite(U, I, E, 8)
+    order = np.lexsort((np.arange(u.shape[0]), u))
+    u, i = u[order], i[order]
+    first = np.r_[True, u[1:] != u[:-1]]
+    su, si, tu, ti = u[first], i[first], u[~first], i[~first]
+    train_df = pd.DataFrame(dict(userId=tu, itemId=ti, rating=1))
+    test_df = pd.DataFrame(dict(userId=su, itemId=si, rating=1))
+    pool = set(np.unique(i).tolist())
+    pos = pd.DataFrame(dict(userId=np.arange(U))).assign(positive_items=[set(i[u == k].tolist()) for k in range(U)])
+    pos["negative_items"] = pos["positive_items"].apply(lambda s: pool - s)
+    a = Interactions.from_negsampling_frames(U, I, pos, train_df=train_df, device=DEV)
+    b = Interactions.from_arrays(U, I, tu, ti, su, si, device=DEV)
+    for k in ("train_rows_user", "train_rows_item", "all_ptr", "all_rank", "pool"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    c = Interactions.from_negsampling_frames(U, I, pos, test_df=test_df, device=DEV)
+    for k in ("test_rows_user", "test_rows_item", "all_ptr", "all_rank", "pool"):
+        assert torch.equal(getattr(c, k), getattr(b, k)), k

@@ -48,11 +48,14 @@ def _device_adj(model, adj):
     return t
 
 
-def _fused_ok(m, optim, lossfn):
+def _fused_ok(m, optim, lossfn, loss_type=None):
     from ngacf_b200.loss import BPRLoss
     from ngacf_b200.model import SPUIGACF
     from ngacf_b200.optim import FusedAdam
-    if not isinstance(m, SPUIGACF) or not isinstance(lossfn, BPRLoss) or len(optim.param_groups) != 1:
+    loss_type = BPRLoss if loss_type is None else loss_type
+    if not isinstance(m, SPUIGACF) or not isinstance(lossfn, loss_type) or len(optim.param_groups) != 1:
+        return False
+    if loss_type is torch.nn.BCEWithLogitsLoss and (lossfn.reduction != "mean" or lossfn.weight is not None or lossfn.pos_weight is not None):
         return False
     if not isinstance(optim, (torch.optim.Adam, FusedAdam)) or isinstance(optim, torch.optim.AdamW):
         return False
@@ -133,4 +136,85 @@ def eval_neg_all(model, batch_size, test_df, test_pos_neg, adj, itemNum, is_para
         if ev is None or ev.inter is not inter or ev.mode != mode:
             ev = AllNegEvaluator(inter, mode)
             m._evaluator = ev
+        return ev(Z)
+
+
+# ------------------------------------------------------------------------------------------------
+# NegSampling training / SampledNeg evaluation (the reference CLI's default modes)
+# ------------------------------------------------------------------------------------------------
+def _neg_interactions(model, pos_neg, train_df=None, test_df=None):
+    for cand in (train_df, pos_neg, test_df):
+        if isinstance(cand, Interactions):
+            return cand
+    key = ("neg", id(pos_neg), id(train_df), id(test_df))
+    if key not in _INTER_CACHE:
+        m = _unwrap(model)
+        _INTER_CACHE[key] = Interactions.from_negsampling_frames(m.userNum, m.itemNum, pos_neg, train_df, test_df, device=m.uEmbd.weight.device)
+    return _INTER_CACHE[key]
+
+
+def train_neg_sample(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is_parallel, epoch=0, sample_seed=None, fused=None,
+                     max_steps=None):
+    """One epoch of train_neg_sample (train_eval_Gowalla.py:36-88): per train row 1 positive + 4 sampled negatives, ONE propagation per
+    batch, BCEWithLogitsLoss on the B*5 scores, backward, optimizer step.  Returns sum(batch-mean loss) / len(train_df) (:84,88).
+    train_pos_neg = positives_negtives(rt) (or an ngacf_b200.data.Interactions); `epoch`/`sample_seed` select the sampler's stream."""
+    if is_parallel:
+        raise NotImplementedError("--parallel True is replaced by one process per GPU (ngacf_b200/dist.py)")
+    m = _unwrap(model)
+    model.train()
+    inter = _neg_interactions(model, train_pos_neg, train_df=train_df)
+    dev = m.uEmbd.weight.device
+    graph = m.graph_for(_device_adj(model, adj))
+    if sample_seed is None:
+        sample_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    if fused is None:
+        fused = os.environ.get("NGACF_FUSED", "1") != "0"
+    K = 4
+    if fused and _fused_ok(m, optim, lossfn, loss_type=torch.nn.BCEWithLogitsLoss):
+        from ngacf_b200.negsampling import NegSamplingTrainer
+        tr = getattr(m, "_neg_trainer", None)
+        key = (id(inter), id(graph), int(batch_size), id(optim), int(sample_seed))
+        if tr is None or tr.key != key:
+            tr = NegSamplingTrainer(m, inter, graph, batch_size, optim, sample_seed, K=K)
+            tr.key = key
+            m._neg_trainer = tr
+        return tr.train_epoch(epoch, max_steps)
+    n = len(inter)
+    n_batches = n // batch_size + 1
+    if max_steps is not None:
+        n_batches = min(n_batches, max_steps)
+    pu = torch.empty(batch_size * (K + 1), dtype=torch.int64, device=dev)
+    pi = torch.empty_like(pu)
+    labels = torch.zeros(batch_size, K + 1, device=dev)
+    labels[:, 0] = 1
+    total = torch.zeros((), dtype=torch.float64, device=dev)
+    for batch_id in range(n_batches):
+        lo, hi = batch_id * batch_size, min(n, (batch_id + 1) * batch_size)
+        if hi <= lo:
+            continue
+        nb = (hi - lo) * (K + 1)
+        ops.sample_negs(inter, inter.train_rows_user, inter.train_rows_item, lo, hi, sample_seed, epoch, K, ops.NEG_TAG_TRAIN, pu, pi)
+        optim.zero_grad()
+        predictions = model(pu[:nb], pi[:nb], graph)
+        loss = lossfn(predictions, labels[:hi - lo].reshape(-1))
+        loss.backward()
+        optim.step()
+        total += loss.detach().double()
+    return float(total.item()) / n
+
+
+def eval_neg_sample(model, batch_size, test_df, test_pos_neg, adj, top_k, is_parallel, seed=0):
+    """eval_neg_sample (train_eval_Gowalla.py:193-257): per test row 1 positive + 99 sampled negatives, HR@top_k and NDCG@top_k
+    averaged over the test rows.  All rows are scored against one propagation.  Returns (HR, NDCG)."""
+    m = _unwrap(model)
+    model.eval()
+    inter = _neg_interactions(model, test_pos_neg, test_df=test_df)
+    adj_t = _device_adj(model, adj)
+    from ngacf_b200.negsampling import SampledNegEvaluator
+    with torch.no_grad():
+        Z = m.propagate(adj_t)
+        ev = getattr(m, "_neg_evaluator", None)
+        if ev is None or ev.inter is not inter or ev.top_k != int(top_k) or ev.seed != int(seed):
+            ev = SampledNegEvaluator(inter, top_k, 99, seed)
+            m._neg_evaluator = ev
         return ev(Z)
