@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--workload", default="gowalla", choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--train-mode", default="pair", choices=["pair", "neg"],
+                    help="pair: PairSampling + AllNeg (the headline, SURVEY 8); neg: NegSampling + SampledNeg (8f-3, single GPU)")
     ap.add_argument("--split-bwd", action="store_true", help="dense backward as dX (on the chain) + dW/da (gradient stream)")
     ap.add_argument("--eval-mode", default="auto")
     ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
@@ -232,7 +234,11 @@ def main():
             trainer = ReplicaTrainer(model, inter, graph, B, optim, sample_seed=0)
     else:
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
-        trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0, split_dense_backward=args.split_bwd)
+        if args.train_mode == "neg":
+            from ngacf_b200.negsampling import NegSamplingTrainer
+            trainer = NegSamplingTrainer(model, inter, graph, B, optim, sample_seed=0)
+        else:
+            trainer = FusedTrainer(model, inter, graph, B, optim, sample_seed=0, split_dense_backward=args.split_bwd)
     launches_per_step = trainer.launches_per_step(HYPER["droprate"])
 
     def barrier():
@@ -314,7 +320,8 @@ def main():
                  else roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params))
     top_avg_ms = top_ms_step / top_n
     achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
-    step_bytes = roofline.step_bytes_compulsory(U, I, E, 2, B)
+    step_bytes = (roofline.step_bytes_compulsory(U, I, E, 2, B, 1, 5) if args.train_mode == "neg"
+                  else roofline.step_bytes_compulsory(U, I, E, 2, B))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if args.workload == "gowalla" and os.path.exists(tpath):      # DRAM bytes per launch from the committed ncu --set full capture
@@ -332,7 +339,30 @@ def main():
 
     # ---------------- AllNeg evaluation ----------------
     ev_out = None
-    if not args.no_eval:
+    if not args.no_eval and args.train_mode == "neg":
+        # SampledNeg evaluation (8f-3): 1 positive + 99 sampled negatives per test row, HR/NDCG@10, one propagation
+        from ngacf_b200.negsampling import SampledNegEvaluator
+        model.eval()
+        sev = SampledNegEvaluator(inter, 10, 99, 0)
+
+        def sampled_once():
+            with torch.no_grad():
+                model._eval_key = None
+                return sev(model.propagate(graph))          # the HR/NDCG read-back is part of the call
+        for _ in range(3):
+            hr, nd = sampled_once()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            hr, nd = sampled_once()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_eval = e0.elapsed_time(e1) / 5
+        ev_out = dict(metric="sampledneg_eval_rows_per_s", value=inter.n_test_rows / (ms_eval / 1000.0), unit="rows/s", ms=ms_eval,
+                      rows=inter.n_test_rows, candidates_per_row=100, hr_at_10=hr, ndcg_at_10=nd,
+                      e2e=dict(value=inter.n_test_rows / (ms_eval / 1000.0), unit="rows/s", d2h_bytes=16))
+    elif not args.no_eval:
         model.eval()
         from ngacf_b200.dist import shard_eval_users
         ev = AllNegEvaluator(inter, args.eval_mode, users=shard_eval_users(inter.eval_users, rank, world))
@@ -399,8 +429,10 @@ def main():
                     ms_per_step=ms_step, higher_is_better=True, scaling="strong" if (world > 1 and args.dist == "shard") else "weak",
                     vs_baseline=None, dtype="f32",
                     data="synthetic",
-                    config=dict(workload="%s-shape SPUIGACF (U=%d I=%d E=%d d=64, 2 attention stages) PairSampling step: sampler + 2 propagations "
-                                         "(dropout %.1f) + BPR + backward + Adam" % (args.workload, U, I, E, HYPER["droprate"]),
+                    config=dict(workload=("%s-shape SPUIGACF (U=%d I=%d E=%d d=64, 2 attention stages) " % (args.workload, U, I, E)) +
+                                         ("NegSampling step: sampler (4 negatives per row) + 1 propagation (dropout %.1f) + BCE on B*5 pairs + "
+                                          "backward + Adam" if args.train_mode == "neg" else
+                                          "PairSampling step: sampler + 2 propagations (dropout %.1f) + BPR + backward + Adam") % HYPER["droprate"],
                                 batch=B, l2="per-step working set ~%d MB > 126 MB L2, no flush" % (trainer.working_set_bytes() // 2 ** 20),
                                 parallelism=trainer.parallelism(), graph_build_ms=graph_build_ms,
                                 train_rows_per_s=B / (ms_step / 1000.0) * (world if getattr(trainer, "weak", False) else 1)),

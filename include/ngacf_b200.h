@@ -115,7 +115,9 @@ int ngacf_aggregate_finalize(float* Z, const float* h, const float* norm, int32_
  * ------------------------------------------------------------------------------------------- */
 int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream);
 int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const int64_t* items, const float* dscore,
-                          int32_t B, float* G, void* stream);
+                          int32_t B, float* G, int32_t accumulate, void* stream);
+/* accumulate != 0: G[row] += ... for the batch's distinct rows (NegSampling scatters its B*(K+1) pairs one column of B pairs at a
+ * time: the kernel's cost grows with the square of the pairs per call) */
 
 /* F = ELU(Z) materialised for evaluation (SPUIGACF.py:214) */
 int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream);
@@ -222,14 +224,16 @@ int ngacf_eval_metrics(const int32_t* top_ids, const int32_t* users, int32_t n_u
  * (train_eval_Gowalla.py:251-270, graphattention/evaluation.py).  Propagation, ngacf_score_pairs(_bwd) and Adam are shared.
  *   sample_negs: rows [row_begin,row_end) of (rows_user, rows_item); all_ptr/all_rank = CSR of every user's train+test items as
  *     ranks in the sorted pool; writes users/items int64[(n)(K+1)]: column 0 the row's positive, then K distinct negatives
- *     (specified Philox stream, oracle/port.py:sample_negs); tag = 0x4E54 train / 0x4E45 eval; row_dev as in ngacf_sample_pairs.
- *   bce_logits_loss: mean over n scores of softplus(x) - y x with y = 1 at every `group`-th element; dscore may be NULL.
+ *     (specified Philox stream, oracle/port.py:sample_negs); tag = 0x4E54 train / 0x4E45 eval; row_dev as in ngacf_sample_pairs;
+ *     col_stride = 0: row-major (n, K+1); > 0: column-major, element (row b, column j) at j*col_stride + b.
+ *   bce_logits_loss: mean over n scores of softplus(x) - y x; y = 1 at every `group`-th element (group > 0) or for the first
+ *     -group elements (group < 0, column-major pairs); dscore may be NULL.
  *   rank_metrics: per row of `group` scores, rank of column 0 (strictly larger scores); sums[0] += [rank < top_k],
  *     sums[1] += 1/log2(rank+2) for hits (caller zero-fills sums; HR/NDCG = sums / n_rows).
  * ------------------------------------------------------------------------------------------- */
 int ngacf_sample_negs(const int32_t* rows_user, const int32_t* rows_item, const int32_t* all_ptr, const int32_t* all_rank,
                       const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end, const int64_t* row_dev, uint64_t seed,
-                      uint32_t epoch, int32_t K, uint32_t tag, int64_t* users, int64_t* items, void* stream);
+                      uint32_t epoch, int32_t K, uint32_t tag, int64_t col_stride, int64_t* users, int64_t* items, void* stream);
 int ngacf_bce_logits_loss(const float* scores, int64_t n, int32_t group, float* loss, float* dscore, void* stream);
 int ngacf_rank_metrics(const float* scores, int64_t n_rows, int32_t group, int32_t top_k, double* sums, void* stream);
 

@@ -20,7 +20,7 @@ SIGNATURES = {
     "ngacf_feature_mask": (c_int32, [P, c_int64, c_uint64, c_uint32, P, c_uint32, c_float, P]),
     "ngacf_edge_mask": (c_int32, [P, c_int64, c_int32, c_uint64, c_uint32, P, c_uint32, c_float, P]),
     "ngacf_dropout_masks": (c_int32, [P, P, P, c_int32, c_int64, c_int64, c_uint64, c_uint32, P, c_float, P]),
-    "ngacf_sample_negs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, c_int32, c_uint32, P, P, P]),
+    "ngacf_sample_negs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, c_int32, c_uint32, c_int64, P, P, P]),
     "ngacf_bce_logits_loss": (c_int32, [P, c_int64, c_int32, P, P, P]),
     "ngacf_rank_metrics": (c_int32, [P, c_int64, c_int32, c_int32, P, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
@@ -30,7 +30,7 @@ SIGNATURES = {
     "ngacf_stage_bwd_finalize": (c_int32, [P, P, P, P, c_int32, c_int32, c_int64, P]),
     "ngacf_bpr_loss_owned": (c_int32, [P, P, c_int32, c_float, P, P, P, P, c_int64, c_int64, P]),
     "ngacf_score_pairs": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
-    "ngacf_score_pairs_bwd": (c_int32, [P, c_int32, P, P, P, c_int32, P, P]),
+    "ngacf_score_pairs_bwd": (c_int32, [P, c_int32, P, P, P, c_int32, P, c_int32, P]),
     "ngacf_final_features": (c_int32, [P, c_int64, P, P]),
     "ngacf_bpr_loss": (c_int32, [P, P, c_int32, c_float, P, P, P, P]),
     "ngacf_stage_bwd_prep": (c_int32, [P, P, P, P, c_int32, c_int64, P, P, P]),

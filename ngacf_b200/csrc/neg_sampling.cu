@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(128) sample_negs_kernel(const int* __restrict_
                                                           const int* __restrict__ all_ptr, const int* __restrict__ all_rank,
                                                           const int* __restrict__ pool, int P, int64_t row_begin, int64_t n,
                                                           const int64_t* __restrict__ row_dev, uint32_t k0, uint32_t k1, uint32_t epoch, int K,
-                                                          uint32_t tag, int64_t* __restrict__ users, int64_t* __restrict__ items) {
+                                                          uint32_t tag, int64_t col_stride, int64_t* __restrict__ users, int64_t* __restrict__ items) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
     if (row_dev) { row_begin += row_dev[0]; epoch += (uint32_t)row_dev[1]; }
@@ -20,12 +20,14 @@ __global__ void __launch_bounds__(128) sample_negs_kernel(const int* __restrict_
     const int u = rows_user[r];
     const int beg = all_ptr[u], deg = all_ptr[u + 1] - beg;
     const int nneg = P - deg;
-    int64_t* out_u = users + b * (K + 1);
-    int64_t* out_i = items + b * (K + 1);
-    for (int j = 0; j <= K; ++j) out_u[j] = u;
+    // element (row b, column j): row-major b*(K+1) + j, or column-major j*col_stride + b (one column = one contiguous batch of pairs)
+    const int64_t o0 = col_stride > 0 ? b : b * (K + 1), os = col_stride > 0 ? col_stride : 1;
+    int64_t* out_u = users + o0;
+    int64_t* out_i = items + o0;
+    for (int j = 0; j <= K; ++j) out_u[j * os] = u;
     out_i[0] = rows_item[r];
     if (nneg < K) {                       // random.sample would raise; flagged to the host as -1
-        for (int j = 1; j <= K; ++j) out_i[j] = -1;
+        for (int j = 1; j <= K; ++j) out_i[j * os] = -1;
         return;
     }
     uint32_t w[4];
@@ -40,9 +42,9 @@ __global__ void __launch_bounds__(128) sample_negs_kernel(const int* __restrict_
         }
         const int64_t cand = pool[k + lo];
         bool dup = false;
-        for (int j = 1; j <= got; ++j) dup |= out_i[j] == cand;
+        for (int j = 1; j <= got; ++j) dup |= out_i[j * os] == cand;
         if (dup) continue;
-        out_i[++got] = cand;
+        out_i[++got * os] = cand;
     }
 }
 
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(1024) bce_logits_kernel(const float* __restric
     const float inv = 1.0f / (float)n;
     for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
         const float v = x[e];
-        const float y = (e % group) == 0 ? 1.f : 0.f;
+        const float y = (group > 0 ? (e % group) == 0 : e < (int64_t)(-group)) ? 1.f : 0.f;
         const float sp = fmaxf(v, 0.f) + log1pf(__expf(-fabsf(v)));       // softplus, stable
         local += sp - y * v;
         if (dx) dx[e] = (1.0f / (1.0f + __expf(-v)) - y) * inv;
@@ -96,18 +98,19 @@ using namespace ngacf;
 
 extern "C" int ngacf_sample_negs(const int32_t* rows_user, const int32_t* rows_item, const int32_t* all_ptr, const int32_t* all_rank,
                                  const int32_t* pool, int32_t P, int64_t row_begin, int64_t row_end, const int64_t* row_dev, uint64_t seed,
-                                 uint32_t epoch, int32_t K, uint32_t tag, int64_t* users, int64_t* items, void* stream) {
+                                 uint32_t epoch, int32_t K, uint32_t tag, int64_t col_stride, int64_t* users, int64_t* items, void* stream) {
     NGACF_REQUIRE(rows_user && rows_item && all_ptr && all_rank && pool && users && items, "sample_negs: null argument");
     NGACF_REQUIRE(row_end >= row_begin && P > 0 && K >= 1 && K <= 4096 && tag < 0x10000u, "sample_negs: bad range / K / tag");
     const int64_t n = row_end - row_begin;
+    NGACF_REQUIRE(col_stride == 0 || col_stride >= n, "sample_negs: column stride smaller than the number of rows");
     if (n == 0) return NGACF_OK;
     sample_negs_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rows_user, rows_item, all_ptr, all_rank, pool, P, row_begin, n, row_dev,
-                                                                          (uint32_t)seed, (uint32_t)(seed >> 32), epoch, K, tag, users, items);
+                                                                          (uint32_t)seed, (uint32_t)(seed >> 32), epoch, K, tag, col_stride, users, items);
     return check_launch("sample_negs");
 }
 
 extern "C" int ngacf_bce_logits_loss(const float* scores, int64_t n, int32_t group, float* loss, float* dscore, void* stream) {
-    NGACF_REQUIRE(scores && n > 0 && group >= 1, "bce_logits_loss: null/empty argument");
+    NGACF_REQUIRE(scores && n > 0 && group != 0, "bce_logits_loss: null/empty argument");
     bce_logits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, n, group, loss, dscore);
     return check_launch("bce_logits_loss");
 }

@@ -48,7 +48,7 @@ __global__ void final_features_kernel(const float* __restrict__ Z, int64_t n4, f
 constexpr int SPB_SUPER = 2048;
 __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
                                                               const int64_t* __restrict__ items, const float* __restrict__ dscore, int B,
-                                                              float* __restrict__ G) {
+                                                              float* __restrict__ G, int accumulate) {
     __shared__ int list[SPB_SUPER];
     __shared__ int warp_cnt[8][8];
     __shared__ float part[16][D];
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) score_pairs_bwd_kernel(const float* __res
 #pragma unroll
         for (int g = 0; g < 16; ++g) sum += part[g][tid];
         const int64_t row = user_row ? key : key + U;
-        G[row * D + tid] = sum * elu_grad(Z[row * D + tid]);
+        const float gnew = sum * elu_grad(Z[row * D + tid]);
+        G[row * D + tid] = accumulate ? G[row * D + tid] + gnew : gnew;
     }
 }
 
@@ -293,10 +294,10 @@ extern "C" int ngacf_final_features(const float* Z, int64_t N, float* F, void* s
 }
 
 extern "C" int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const int64_t* items, const float* dscore, int32_t B,
-                                     float* G, void* stream) {
+                                     float* G, int32_t accumulate, void* stream) {
     NGACF_REQUIRE(Z && users && items && dscore && G && B >= 0, "score_pairs_bwd: null argument");
     if (B == 0) return NGACF_OK;
-    score_pairs_bwd_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, dscore, B, G);
+    score_pairs_bwd_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, dscore, B, G, accumulate);
     return check_launch("score_pairs_bwd");
 }
 

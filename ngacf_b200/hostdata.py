@@ -59,7 +59,13 @@ def load_dataset(name, data_root=None, train_mode="PairSampling"):
     if name in SYNTH_SHAPES:
         U, I, E = SYNTH_SHAPES[name]
         u, i = synth_bipartite(U, I, E, 0)
-        (tu, ti), (su, si) = split_per_user(u, i, U, 1)
+        if train_mode == "NegSampling":     # leave-one-out like split_loo (loadGowalla.py:307-313): one held-out row per user
+            order = np.lexsort((np.random.default_rng(1).random(u.shape[0]), u))
+            u, i = u[order], i[order]
+            first = np.r_[True, u[1:] != u[:-1]]
+            (tu, ti), (su, si) = (u[~first], i[~first]), (u[first], i[first])
+        else:
+            (tu, ti), (su, si) = split_per_user(u, i, U, 1)
     elif name in ("Gowalla", "Yelp"):
         sub, pre = ("Gowalla", "g") if name == "Gowalla" else ("Yelp", "y")
         cols = dict(names=["userId", "itemId", "rating"], dtype={"userId": np.int64, "itemId": np.int64})
@@ -77,9 +83,11 @@ def load_dataset(name, data_root=None, train_mode="PairSampling"):
         U, I = int(rt["userId"].max()), int(rt["itemId"].max())     # ids start at 1 (run_Gowalla.py:60-63,72-76)
         rt["userId"] -= 1
         rt["itemId"] -= 1
-        if train_mode != "PairSampling":
-            raise NotImplementedError("only --train_mode PairSampling is in scope (SURVEY.md section 8)")
-        tr, te = train_test_split(rt, test_size=0.2)
+        if train_mode == "NegSampling":     # split_loo (loadGowalla.py:307-313): the latest rating of every user is the test row
+            rt["rank_latest"] = rt.groupby(["userId"])["timestamp"].rank(method="first", ascending=False)
+            tr, te = rt[rt["rank_latest"] > 1], rt[rt["rank_latest"] == 1]
+        else:
+            tr, te = train_test_split(rt, test_size=0.2)
         tu, ti, su, si = tr["userId"].values, tr["itemId"].values, te["userId"].values, te["itemId"].values
     else:
         raise ValueError("unknown dataset %r" % name)

@@ -37,8 +37,9 @@ class NegSamplingTrainer(FusedTrainer):
         cd = self.call_dev if dev_counters else None
         row0 = row0 + (self._row_offset() if dev_counters else 0)
         n = b * (self.K + 1)
+        # column-major pairs: column j (0 = positives, 1..K = negatives) is the contiguous slice [j*b, (j+1)*b)
         ops.sample_negs(it, it.train_rows_user, it.train_rows_item, row0, row0 + b, self.sample_seed, 0 if dev_counters else epoch, self.K,
-                        ops.NEG_TAG_TRAIN, self.pu, self.pi, rd)
+                        ops.NEG_TAG_TRAIN, self.pu, self.pi, rd, col_stride=b)
         premask = dev_counters and self.prefetch_masks
         self._mask_args = (droprate, seed) if premask else None
         prop = self.props[0]
@@ -48,10 +49,13 @@ class NegSamplingTrainer(FusedTrainer):
             prop.set_dropout(droprate, seed, call0, None, cd)
         Z = prop.forward(uE, iE, self.wtabs)
         ops.score_pairs(Z, g.U, self.pu[:n], self.pi[:n], self.sc[:n])
-        ops.bce_logits_loss(self.sc[:n], self.K + 1, self.loss, self.dsc[:n])
+        ops.bce_logits_loss(self.sc[:n], -b, self.loss, self.dsc[:n])
         G = prop.grad_in()
         G.zero_()
-        ops.score_pairs_bwd(prop.Z[-1], g.U, self.pu[:n], self.pi[:n], self.dsc[:n], G)
+        # the scatter's cost grows with the square of the pairs per call: one column of b pairs at a time, accumulating
+        for j in range(self.K + 1):
+            sl = slice(j * b, (j + 1) * b)
+            ops.score_pairs_bwd(prop.Z[-1], g.U, self.pu[sl], self.pi[sl], self.dsc[sl], G, accumulate=j > 0)
         inline = (lambda k, fn: fn()) if self.split_dense_backward else None
         prop.backward(G, uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, False, dw_launcher=inline)
         if part == "compute":
@@ -65,7 +69,7 @@ class NegSamplingTrainer(FusedTrainer):
     def launches_per_step(self, droprate: float) -> int:
         S = len(self.props[0].stages)
         fwd = (1 if droprate > 0 else 0) + 2 * S + 1                  # masks, transform+aggregate per stage, pair scores
-        bwd = 1 + S * (1 + 2 + (4 if self.split_dense_backward else 2))   # scatter; prep + 2 edge passes + dense backward per stage
+        bwd = (self.K + 1) + S * (1 + 2 + (4 if self.split_dense_backward else 2))   # scatter per column; prep + 2 edge passes + dense backward per stage
         return 1 + fwd + 1 + bwd + 2 + 2                               # sampler, ..., loss, ..., adam(2), counters(2)
 
     def units_per_step(self) -> int:

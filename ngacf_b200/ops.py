@@ -83,8 +83,8 @@ def score_pairs(Z, U, users, items, out):
     _lib.call("ngacf_score_pairs", _p(Z), U, _p(users), _p(items), users.numel(), _p(out), _s())
 
 
-def score_pairs_bwd(Z, U, users, items, dscore, G):
-    _lib.call("ngacf_score_pairs_bwd", _p(Z), U, _p(users), _p(items), _p(dscore), users.numel(), _p(G), _s())
+def score_pairs_bwd(Z, U, users, items, dscore, G, accumulate=False):
+    _lib.call("ngacf_score_pairs_bwd", _p(Z), U, _p(users), _p(items), _p(dscore), users.numel(), _p(G), int(accumulate), _s())
 
 
 def final_features(Z, F):
@@ -165,13 +165,15 @@ def eval_metrics(top_ids, users, inter, hits, sums, ws):
 NEG_TAG_TRAIN, NEG_TAG_EVAL = 0x4E54, 0x4E45
 
 
-def sample_negs(inter, rows_user, rows_item, row_begin, row_end, seed, epoch, K, tag, users, items, row_dev=None):
-    """K distinct negatives per (user, positive) row: users/items int64[(row_end-row_begin)*(K+1)], column 0 = the positive"""
+def sample_negs(inter, rows_user, rows_item, row_begin, row_end, seed, epoch, K, tag, users, items, row_dev=None, col_stride=0):
+    """K distinct negatives per (user, positive) row: users/items int64[(row_end-row_begin)*(K+1)], column 0 = the positive.
+    col_stride = 0: row-major (n, K+1); > 0: column-major, element (row b, column j) at j*col_stride + b."""
     _lib.call("ngacf_sample_negs", _p(rows_user), _p(rows_item), _p(inter.all_ptr), _p(inter.all_rank), _p(inter.pool), int(inter.pool.numel()),
-              int(row_begin), int(row_end), _p(row_dev), int(seed), int(epoch), int(K), int(tag), _p(users), _p(items), _s())
+              int(row_begin), int(row_end), _p(row_dev), int(seed), int(epoch), int(K), int(tag), int(col_stride), _p(users), _p(items), _s())
 
 
 def bce_logits_loss(scores, group, loss, dscore=None):
+    """group > 0: every group-th score is a positive (row-major pairs); group < 0: the first -group scores are the positives"""
     _lib.call("ngacf_bce_logits_loss", _p(scores), scores.numel(), int(group), _p(loss), _p(dscore), _s())
 
 

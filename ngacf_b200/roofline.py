@@ -54,13 +54,14 @@ def kernel_bytes_gather(name: str, U: int, I: int, E: int, H: int, dropout: bool
     raise KeyError(name)
 
 
-def step_bytes_compulsory(U: int, I: int, E: int, S: int = 2, B: int = 2048) -> int:
+def step_bytes_compulsory(U: int, I: int, E: int, S: int = 2, B: int = 2048, propagations: int = 2, pairs_per_row: int = 2) -> int:
     """fwd_stage = 5 N r + 12 E, bwd_stage = 9 N r + 12 E,
-    step = 2 S (fwd + bwd) + 7 N r (Adam) + 6 B r (BPR gather + scatter)."""
+    step = 2 S (fwd + bwd) + 7 N r (Adam) + 6 B r (BPR gather + scatter).  A NegSampling step (8f-3) has ONE propagation and
+    5 (user, item) pairs per train row: propagations=1, pairs_per_row=5."""
     N = U + I
     fwd = 5 * N * R + 12 * E
     bwd = 9 * N * R + 12 * E
-    return 2 * S * (fwd + bwd) + 7 * N * R + 6 * B * R
+    return propagations * S * (fwd + bwd) + 7 * N * R + 3 * pairs_per_row * B * R
 
 
 def eval_flops(n_users: int, I: int, D: int = 64) -> int:

@@ -19,7 +19,7 @@ from graphattention.BPRLoss import BPRLoss
 from graphattention.SPUIGACF import SPUIGACF, SPUIMultiGACF
 from ngacf_b200.data import Interactions
 from ngacf_b200.hostdata import load_dataset
-from train_eval_Gowalla import eval_neg_all, train_bpr
+from train_eval_Gowalla import eval_neg_all, eval_neg_sample, train_bpr, train_neg_sample
 
 
 def prepareData(args):
@@ -27,13 +27,14 @@ def prepareData(args):
     data frames are ONE Interactions object and adj is the (2,E) index tensor of ui_mat built from ALL interactions)."""
     if args.adj_type != "ui_mat":
         raise NotImplementedError("SPUIGACF consumes --adj_type ui_mat only (run_Gowalla.py:94 passes adj.indices())")
-    if not (args.train_mode == "PairSampling" and args.eval_mode == "AllNeg"):
-        raise NotImplementedError("in scope: --train_mode PairSampling --eval_mode AllNeg (SURVEY.md section 8)")
+    if (args.train_mode, args.eval_mode) not in (("PairSampling", "AllNeg"), ("NegSampling", "SampledNeg")):
+        raise NotImplementedError("built: --train_mode PairSampling --eval_mode AllNeg (SURVEY.md section 8) and "
+                                  "--train_mode NegSampling --eval_mode SampledNeg (8f-3), the pairs run_Gowalla.py:84-92 prepares")
     d = load_dataset(args.dataset, args.data_root, args.train_mode)
     print("userNum:{}, itemNum:{}".format(d["userNum"], d["itemNum"]))
     inter = Interactions.from_arrays(d["userNum"], d["itemNum"], d["train_u"], d["train_i"], d["test_u"], d["test_i"], device="cuda")
     adj = torch.from_numpy(np.stack([d["rt_u"], d["rt_i"]]).astype(np.int64))      # coalesced by the graph builder on the GPU
-    print("lenth of traindf", len(d["train_u"]), "lenth of test_df", int(inter.eval_users.numel()))
+    print("lenth of traindf", len(d["train_u"]), "lenth of test_df", int(inter.eval_users.numel()) if args.eval_mode == "AllNeg" else inter.n_test_rows)
     return inter, inter, inter, inter, d["userNum"], d["itemNum"], adj
 
 
@@ -42,7 +43,7 @@ def createModels(args, userNum, itemNum):
         raise NotImplementedError("--model SPUIGACF (in scope) and SPUIMultiGACF (SURVEY.md 8f-1) are built; SPUIGAGPCF is not")
     cls = SPUIGACF if args.model == "SPUIGACF" else SPUIMultiGACF
     model = cls(userNum, itemNum, embedSize=args.embedSize, layers=args.layers, droprate=args.droprate).cuda()
-    lossfn = BPRLoss()
+    lossfn = BPRLoss() if args.train_mode == "PairSampling" else torch.nn.BCEWithLogitsLoss()      # run_Gowalla.py:104-110
     optim = Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
     return model, lossfn, optim
 
@@ -73,14 +74,22 @@ def main(args):
         print("=> loaded checkpoint '{}'".format("ckpts/{}_{:03d}.pkl".format(args.model, args.resume_from)))
     for epoch in range(args.resume_from, args.epochs):
         t0 = time.time()
-        train_loss = train_bpr(model, args.batch_size, train_df, train_pos_neg, adj, optim, lossfn, args.parallel, epoch=epoch,
-                               sample_seed=args.seed)
+        train_fn = train_bpr if args.train_mode == "PairSampling" else train_neg_sample
+        train_loss = train_fn(model, args.batch_size, train_df, train_pos_neg, adj, optim, lossfn, args.parallel, epoch=epoch,
+                              sample_seed=args.seed)
         summaryWriter.add_scalar("loss/train_loss", train_loss, epoch)
         print("------epoch:{}, train_loss:{:5f}, time consuming:{}s".format(epoch, train_loss, time.strftime("%H: %M: %S", time.gmtime(time.time() - t0))))
         if (epoch + 1) % args.save_every == 0:
             torch.save({"model": model.state_dict(), "optim": optim.state_dict()}, "ckpts/{}_{}_{:03d}.pkl".format(args.model, args.dataset, epoch + 1))
         if (epoch + 1) % args.eval_every == 0:
             t0 = time.time()
+            if args.eval_mode == "SampledNeg":        # run_Gowalla.py:155-160
+                HR, NDCG = eval_neg_sample(model, args.batch_size, test_df, test_pos_neg, adj, 10, args.parallel, seed=args.seed)
+                summaryWriter.add_scalar("metrics/HR", HR, epoch)
+                summaryWriter.add_scalar("metrics/NDCG", NDCG, epoch)
+                print("The time of evaluate epoch {:03d}".format(epoch) + " is: " + time.strftime("%H: %M: %S", time.gmtime(time.time() - t0)))
+                print("epoch:{}, HR:{:5f}, NDCG:{:5f}".format(epoch, HR, NDCG))
+                continue
             metrics = eval_neg_all(model, args.batch_size, test_df, test_pos_neg, adj, itemNum, args.parallel)
             print("epoch:{} metrics:{}".format(epoch, metrics))
             for i, K in enumerate([1, 5, 10, 20]):

@@ -561,6 +561,11 @@ def test_sample_negs_bit_exact():
         pi2 = torch.zeros_like(pi)
         ops.sample_negs(dit, rows_u, rows_i, 0, n, 0xABCDEF0123, 0, K, tag, pu, pi2, rd)
         assert torch.equal(pi, pi2)
+        # column-major layout (what the captured NegSampling step uses): element (row, column) at column*stride + row
+        pu3, pi3 = torch.full(((K + 1) * (n + 3),), -7, dtype=torch.int64, device=DEV), torch.full(((K + 1) * (n + 3),), -7, dtype=torch.int64, device=DEV)
+        ops.sample_negs(dit, rows_u, rows_i, lo, hi_row, 0xABCDEF0123, 3, K, tag, pu3, pi3, col_stride=n + 3)
+        assert np.array_equal(pi3.cpu().numpy().reshape(K + 1, n + 3)[:, :n].T, ei) and np.array_equal(pu3.cpu().numpy().reshape(K + 1, n + 3)[:, :n].T, eu)
+        assert (pi3.cpu().numpy().reshape(K + 1, n + 3)[:, n:] == -7).all()
 
 
 def test_bce_loss_and_rank_metrics():
@@ -576,6 +581,8 @@ def test_bce_loss_and_rank_metrics():
     l_ref, d_ref = port.bce_logits(torch.from_numpy(x).double(), y.reshape(-1))
     assert abs(loss.item() - float(l_ref)) / float(l_ref) < 1e-5
     assert rel_err(dx.cpu().numpy(), d_ref.numpy()) < 1e-5
+    ops.bce_logits_loss(xt.reshape(777, 5).t().contiguous().reshape(-1), -777, loss, None)      # column-major: the first 777 are the positives
+    assert abs(loss.item() - float(l_ref)) / float(l_ref) < 1e-5
     sc = rng.standard_normal((333, 100)).astype(np.float32)
     sc[5, 7] = sc[5, 0]            # a tie with the positive does not outrank it
     sums = torch.zeros(2, dtype=torch.float64, device=DEV)
@@ -638,3 +645,22 @@ def test_neg_sampling_reference_frames():
     c = Interactions.from_negsampling_frames(U, I, pos, test_df=test_df, device=DEV)
     for k in ("test_rows_user", "test_rows_item", "all_ptr", "all_rank", "pool"):
         assert torch.equal(getattr(c, k), getattr(b, k)), k
+
+
+def test_score_pairs_bwd_accumulates_over_calls():
+    """One call on all pairs == the same pairs split over several accumulating calls (what the NegSampling step does per column),
+    up to the fp32 summation order of rows that occur in more than one call."""
+    from ngacf_b200 import ops
+    rng = np.random.default_rng(4)
+    U, I, n = 50, 70, 1500
+    Z = torch.from_numpy(rng.standard_normal((U + I, 64)).astype(np.float32)).to(DEV)
+    users = torch.from_numpy(rng.integers(0, U, n)).to(DEV)
+    items = torch.from_numpy(rng.integers(0, I, n)).to(DEV)
+    d = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(DEV)
+    G1 = torch.zeros_like(Z)
+    ops.score_pairs_bwd(Z, U, users, items, d, G1)
+    G2 = torch.zeros_like(Z)
+    for j in range(3):
+        sl = slice(j * 500, (j + 1) * 500)
+        ops.score_pairs_bwd(Z, U, users[sl], items[sl], d[sl], G2, accumulate=j > 0)
+    assert rel_err(G2.cpu().numpy(), G1.cpu().numpy()) < 1e-5
