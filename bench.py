@@ -112,7 +112,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_train_steps(workload, n_steps, warmup, budget_s):
+def cpu_train_steps(workload, n_steps, warmup, budget_s, train_mode="pair"):
     import torch
     from oracle import port
     U, I, u, i, tu, ti, su, si = make_data(workload)
@@ -122,16 +122,21 @@ def cpu_train_steps(workload, n_steps, warmup, budget_s):
     p = port.init_params(U, I, 2019)
     st = port.adam_init(p)
     B = HYPER["batch"]
+    allpos = port.AllPositives(it) if train_mode == "neg" else None
     times = []
     t_start = time.time()
     k = 0
     while k < warmup + n_steps:
         t0 = time.time()
         lo = (k * B) % max(1, len(it.train_rows_user) - B)
-        users, pos, neg = port.sample_pairs(it, lo, lo + B, 0, 0)
-        mp = port.dropout_masks(g, 0, 2 * k, HYPER["droprate"])
-        mn = port.dropout_masks(g, 0, 2 * k + 1, HYPER["droprate"])
-        loss, grads, _, _ = port.train_step_grads(p, g, users, pos, neg, mp, mn, HYPER["droprate"])
+        if train_mode == "neg":        # NegSampling step (8f-3): one propagation, BCE on B*5 pairs
+            users, items = port.sample_negs(it, allpos, it.train_rows_user, np.asarray(ti, np.int32), lo, lo + B, 0, 0, 4, port.NEG_TAG_TRAIN)
+            loss, grads, _ = port.train_neg_step_grads(p, g, users, items, port.dropout_masks(g, 0, k, HYPER["droprate"]), HYPER["droprate"])
+        else:
+            users, pos, neg = port.sample_pairs(it, lo, lo + B, 0, 0)
+            mp = port.dropout_masks(g, 0, 2 * k, HYPER["droprate"])
+            mn = port.dropout_masks(g, 0, 2 * k + 1, HYPER["droprate"])
+            loss, grads, _, _ = port.train_step_grads(p, g, users, pos, neg, mp, mn, HYPER["droprate"])
         port.adam_step(p, grads, st, HYPER["lr"], HYPER["weight_decay"])
         dt = time.time() - t0
         if k >= warmup:
@@ -149,14 +154,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    E, times, threads = cpu_train_steps(args.workload, args.steps, min(args.warmup, 1), budget_s=150.0)
+    neg = args.train_mode == "neg"
+    E, times, threads = cpu_train_steps(args.workload, args.steps, min(args.warmup, 1), budget_s=150.0, train_mode=args.train_mode)
     ms = 1000.0 * float(np.mean(times))
-    val = 2 * E / (ms / 1000.0)
-    sample = "%d of %d requested steps timed (each a full %s-shape step: 2 propagations fwd+bwd + Adam); %d warm-up" % (
-        len(times), args.steps, args.workload, min(args.warmup, 1))
+    val = (1 if neg else 2) * E / (ms / 1000.0)
+    sample = "%d of %d requested steps timed (each a full %s-shape step: %d propagation%s fwd+bwd + Adam); %d warm-up" % (
+        len(times), args.steps, args.workload, 1 if neg else 2, "" if neg else "s", min(args.warmup, 1))
     line = dict(metric="spuigacf_train_propagated_edges_per_s", value=val, unit="edges/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=args.workload + "-shape SPUIGACF PairSampling step", batch=HYPER["batch"], droprate=HYPER["droprate"]),
+                config=dict(workload=args.workload + "-shape SPUIGACF %s step" % ("NegSampling" if neg else "PairSampling"), batch=HYPER["batch"],
+                            droprate=HYPER["droprate"]),
                 cpu_baseline=dict(value=val, unit="edges/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=val, unit="edges/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     _STDOUT.write(json.dumps(line) + "\n")
@@ -418,11 +425,11 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Ecpu, times, threads = cpu_train_steps(args.workload, 2, 1, budget_s=25.0)
+        Ecpu, times, threads = cpu_train_steps(args.workload, 2, 1, budget_s=25.0, train_mode=args.train_mode)
         cpu_ms = 1000.0 * float(np.mean(times))
-        cpu = dict(value=2 * Ecpu / (cpu_ms / 1000.0), unit="edges/s", cores=threads, kind="port",
-                   sample="%d full %s-shape training steps of the oracle port (closed form, torch CPU), 1 warm-up; %.2f s/step"
-                          % (len(times), args.workload, cpu_ms / 1000.0))
+        cpu = dict(value=(1 if args.train_mode == "neg" else 2) * Ecpu / (cpu_ms / 1000.0), unit="edges/s", cores=threads, kind="port",
+                   sample="%d full %s-shape %s training steps of the oracle port (closed form, torch CPU), 1 warm-up; %.2f s/step"
+                          % (len(times), args.workload, "NegSampling" if args.train_mode == "neg" else "PairSampling", cpu_ms / 1000.0))
 
     if rank == 0:
         line = dict(metric="spuigacf_train_propagated_edges_per_s", value=value, unit="edges/s", n_gpus=world, steps=K, warmup=W,
