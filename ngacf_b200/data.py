@@ -66,6 +66,13 @@ class Interactions:
         self.host.update(all_ptr=ap, all_items=ai)
         self.device = torch.device(device)
 
+    def min_negatives(self) -> int:
+        """Smallest number of negatives (item_pool minus a user's train and test items) over the users that have any row."""
+        ap = self.host["all_ptr"]
+        deg = np.diff(ap)
+        deg = deg[deg > 0]
+        return int(self.host["pool"].shape[0] - (deg.max() if deg.size else 0))
+
     def __len__(self):      # len(train_df) in train_bpr, len(test_pos_neg) in eval_neg_all
         return self.n_train_rows
 

@@ -24,6 +24,8 @@ class NegSamplingTrainer(FusedTrainer):
                  use_cuda_graph: bool = True):
         super().__init__(model, inter, graph, batch_size, optim, sample_seed, use_cuda_graph=use_cuda_graph, two_streams=False)
         self.K = int(K)
+        if inter.min_negatives() < self.K:      # random.sample(negative_items, K) raises in the reference (loadGowalla.py:82)
+            raise ValueError("a user has fewer than K=%d negatives (item pool minus the user's positives)" % self.K)
         n = self.B * (self.K + 1)
         i64, f32 = dict(dtype=torch.int64, device=self.dev), dict(dtype=torch.float32, device=self.dev)
         self.pu, self.pi = torch.zeros(n, **i64), torch.zeros(n, **i64)
@@ -85,6 +87,8 @@ class SampledNegEvaluator:
 
     def __init__(self, inter: Interactions, top_k: int = 10, K: int = 99, seed: int = 0):
         self.inter, self.top_k, self.K, self.seed = inter, int(top_k), int(K), int(seed)
+        if inter.n_test_rows and inter.min_negatives() < self.K:      # loadGowalla.py:103
+            raise ValueError("a user has fewer than K=%d negatives (item pool minus the user's positives)" % self.K)
         n = inter.n_test_rows * (self.K + 1)
         dev = inter.device
         self.pu = torch.zeros(n, dtype=torch.int64, device=dev)

@@ -142,3 +142,18 @@ def test_interactions_from_reference_frames_matches_arrays():
     assert np.array_equal(a.train_ptr.numpy(), ref.train_ptr) and np.array_equal(a.train_rank.numpy(), ref.train_rank)
     users, div = port.eval_users(ref)
     assert np.array_equal(a.eval_users.numpy(), users) and a.n_train_users == div
+
+
+def test_interactions_negsampling_views_on_cpu():
+    """Row-order item columns, test rows and the train+test union used by the NegSampling / SampledNeg kernels (host logic only)."""
+    from ngacf_b200.data import Interactions
+    U, I, E = 40, 60, 500
+    u, i = port.synth_bipartite(U, I, E, 1)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, 2)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    ap = port.AllPositives(it)
+    d = Interactions.from_arrays(U, I, tu, ti, su, si, device="cpu")
+    assert np.array_equal(d.train_rows_item.numpy(), ti) and np.array_equal(d.test_rows_user.numpy(), su) and np.array_equal(d.test_rows_item.numpy(), si)
+    assert np.array_equal(d.all_ptr.numpy(), ap.ptr) and np.array_equal(d.all_rank.numpy(), ap.rank)
+    assert d.n_test_rows == su.shape[0]
+    assert d.min_negatives() == it.pool.shape[0] - int(np.diff(ap.ptr).max())
