@@ -1,4 +1,8 @@
-"""Explores tcgen05 tf32 descriptor settings: D[m][n] = sum_r A[r][m] B[r][n] (both MN-major over [chunk][row][16 B] images)."""
+"""Explores tcgen05 descriptor settings (kind::tf32 and kind::f16, K-major vs MN-major operands over [chunk][row][16 B] images):
+D[m][n] = sum_r A[r][m] B[r][n].  Findings: profiles/r1e_umma_probe.txt.  Build the probe first:
+
+    nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -Xcompiler -fPIC -shared scripts/probe/umma_probe.cu -o scripts/probe/libprobe.so
+"""
 import ctypes, os, sys, itertools
 import torch
 here = os.path.dirname(os.path.abspath(__file__))
