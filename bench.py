@@ -232,6 +232,8 @@ def main():
     B = HYPER["batch"]
     optim = FusedAdam(model.parameters(), lr=HYPER["lr"], weight_decay=HYPER["weight_decay"])
 
+    if world > 1 and args.train_mode == "neg":
+        raise SystemExit("--train-mode neg is a single-GPU bench line (SURVEY 8f-3); the multi-GPU modes cover the PairSampling path")
     if world > 1:
         from ngacf_b200.dist import ReplicaTrainer, ShardedTrainer
         inter = Interactions.from_arrays(U, I, tu, ti, su, si, device=dev)
