@@ -36,6 +36,10 @@ class FusedTrainer:
         self.split_dense_backward = split_dense_backward
         # captured steps: masks of step t+1 are generated next to Adam of step t (NGACF_PREFETCH_MASKS=0: at the head of the step)
         self.prefetch_masks = os.environ.get("NGACF_PREFETCH_MASKS", "1") != "0"
+        # NGACF_STAGGER=1: the neg propagation starts one kernel after the pos one.  That paid while the dense kernels were long
+        # FFMA kernels (1.44 -> 1.34 ms/step); with the tensor-core kernels both pipelines starting together is faster
+        # (in-box A/B: 0.995 -> 0.983 ms/step), so it is off by default
+        self.stagger = os.environ.get("NGACF_STAGGER", "0") == "1"
         dev = graph.device
         self.dev = dev
         self.props = [Propagation(graph, model.stages), Propagation(graph, model.stages)]      # pos / neg
@@ -155,8 +159,7 @@ class FusedTrainer:
         premask = dev_counters and self.prefetch_masks
         self._mask_args = (droprate, seed) if premask else None
         if side is not None:
-            # the neg propagation starts one kernel after the pos one: its dense transform then overlaps the pos gather
-            # kernel (FFMA-bound vs L2-fabric-bound), and so on down the two pipelines
+            # two pipelines on two streams; optionally (self.stagger) the neg propagation starts one kernel after the pos one
             ev = torch.cuda.Event()
             side.wait_stream(cur)
 
@@ -170,7 +173,9 @@ class FusedTrainer:
                 with torch.cuda.stream(side):
                     self.props[1].set_dropout(droprate, seed, call0 + 1, None, cd)
                 self.props[0].set_dropout(droprate, seed, call0, None, cd)
-            Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side)
+            if not self.stagger:
+                ev.record(cur)
+            Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side if self.stagger else None)
             ops.score_pairs(Z0, g.U, self.users[:b], items[0][:b], scores[0][:b])
             with torch.cuda.stream(side):
                 side.wait_event(ev)
@@ -212,8 +217,10 @@ class FusedTrainer:
                 scatter(1)
             scatter(0)
             split = self.split_dense_backward
+            if not self.stagger:
+                ev_go.record(cur)
             self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False,
-                                   after_first_kernel=lambda: ev_go.record(cur), after_grads=lambda k: evs[k].record(cur),
+                                   after_first_kernel=(lambda: ev_go.record(cur)) if self.stagger else None, after_grads=lambda k: evs[k].record(cur),
                                    dw_launcher=defer(cur) if split else None)
             with torch.cuda.stream(side):
                 side.wait_event(ev_go)
