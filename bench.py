@@ -339,9 +339,10 @@ def main():
                 peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
                 byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
                 share_of_step=top_ms_step / total_prof,
-                note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by L2->SM traffic (0.6-1.1 GB per "
-                     "launch at 9-12 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic ~= algorithmic bytes (no re-reads); in the "
-                     "HBM regime (sweep-30m) the same kernels reach 0.9-1.0 of the measured HBM peak (profiles/r1c_bench_sweep-30m.json)",
+                note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by the L2->SM path (0.37-0.61 GB of "
+                     "tex sectors per launch at 6-9 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic <= algorithmic bytes (no "
+                     "re-reads, profiles/ncu_traffic.json); in the HBM regime (sweep-10m/30m) the same kernels reach 0.9-1.06 of the measured "
+                     "HBM peak (profiles/r1e_bench_sweep-30m.json)",
                 step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
                                 frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
                 kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
