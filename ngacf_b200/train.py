@@ -1,7 +1,7 @@
 """Fused PairSampling training step (train_eval_Gowalla.py:109-139 of the reference), resident on the GPU:
 
-    sampler -> dropout masks x2 -> propagation x2 -> pair scores -> BPR loss + dscore -> gradient scatter
-    -> backward x2 -> Adam
+    sampler -> propagation x2 (two streams) -> pair scores -> BPR loss + dscore -> gradient scatter
+    -> backward x2 -> Adam || dropout masks of the NEXT step (eager steps draw their masks first instead)
 
 over persistent HBM buffers, with no host synchronisation (the reference has 55 per step) and, for the
 full-size batches, replayed from ONE captured CUDA graph whose train-row cursor and dropout-stream
