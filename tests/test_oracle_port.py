@@ -332,3 +332,34 @@ def test_sample_negs_properties():
         pos = set(ap.items[ap.ptr[users[r, 0]]:ap.ptr[users[r, 0] + 1]].tolist())
         negs = items[r, 1:].tolist()
         assert len(set(negs)) == 4 and not (set(negs) & pos) and set(negs) <= set(it.pool.tolist())
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference checkout absent (GPU box)")
+def test_neg_step_against_live_reference_fp64():
+    """One NegSampling step in fp64 (no dropout): BCEWithLogitsLoss of the reference model on the oracle's sampled (user, item) pairs,
+    loss and every parameter gradient vs the port's closed-form backward."""
+    ns = rh.load()
+    U, I, E = 45, 80, 600
+    u, i = port.synth_bipartite(U, I, E, 22)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, 23)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    ap = port.AllPositives(it)
+    g = port.build_graph(np.stack([u, i]), U, I)
+    model = rh.make_model(ns, U, I, 0.0, 7, torch.float64)
+    with torch.no_grad():
+        model.uEmbd.weight.mul_(25.0)
+        model.iEmbd.weight.mul_(25.0)
+    users, items = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), 3, 51, 5, 1, 4, port.NEG_TAG_TRAIN)
+    labels = torch.zeros(users.shape, dtype=torch.float64)
+    labels[:, 0] = 1
+    with rh.default_dtype(torch.float64):
+        pred = model(torch.from_numpy(users.reshape(-1)), torch.from_numpy(items.reshape(-1)), torch.from_numpy(np.stack([g.eu, g.ei])))
+        loss = torch.nn.BCEWithLogitsLoss()(pred, labels.reshape(-1))
+        loss.backward()
+    p = port.params_from_state_dict(model.state_dict())
+    ploss, grads, x = port.train_neg_step_grads(p, g, users, items)
+    assert abs(float(ploss) - float(loss)) < 1e-12 * abs(float(loss))
+    assert rel_err(x.numpy(), pred.detach().numpy()) < 1e-12
+    gsd = port.state_dict_from_params(grads)
+    for k, prm in model.named_parameters():
+        assert rel_err(gsd[k].numpy(), prm.grad.numpy()) < 1e-10, k
