@@ -157,3 +157,50 @@ def test_interactions_negsampling_views_on_cpu():
     assert np.array_equal(d.all_ptr.numpy(), ap.ptr) and np.array_equal(d.all_rank.numpy(), ap.rank)
     assert d.n_test_rows == su.shape[0]
     assert d.min_negatives() == it.pool.shape[0] - int(np.diff(ap.ptr).max())
+
+
+def test_host_data_layer_csv_and_splits(tmp_path):
+    """run_Gowalla.py's prepareData without python sets: the Gowalla/Yelp CSV layout, the synthetic shapes and both
+    split rules (80/20 per user for PairSampling, leave-one-out for NegSampling)."""
+    from ngacf_b200 import hostdata
+    rng = np.random.default_rng(0)
+    U, I = 30, 50
+    rows = np.unique(np.stack([rng.integers(0, U, 600), rng.integers(0, I, 600)], 1), axis=0)
+    rows = np.concatenate([rows, np.stack([np.arange(U), np.arange(U) % I], 1)])          # every user present
+    rows = np.unique(rows, axis=0)
+    is_test = np.zeros(len(rows), bool)
+    is_test[::5] = True
+    te, tr = rows[is_test], rows[~is_test]
+    os.makedirs(tmp_path / "Gowalla")
+    np.savetxt(tmp_path / "Gowalla" / "g_train.csv", np.c_[tr, np.ones(len(tr), int)], fmt="%d", delimiter=",")
+    np.savetxt(tmp_path / "Gowalla" / "g_test.csv", np.c_[te, np.ones(len(te), int)], fmt="%d", delimiter=",")
+    d = hostdata.load_dataset("Gowalla", str(tmp_path))
+    assert d["userNum"] == rows[:, 0].max() + 1 and d["itemNum"] == rows[:, 1].max() + 1
+    assert np.array_equal(d["train_u"], tr[:, 0]) and np.array_equal(d["train_i"], tr[:, 1])
+    assert np.array_equal(d["test_u"], te[:, 0]) and np.array_equal(d["test_i"], te[:, 1])
+    assert np.array_equal(np.sort(d["rt_u"] * 1000 + d["rt_i"]), np.sort(rows[:, 0] * 1000 + rows[:, 1]))
+    with pytest.raises(FileNotFoundError):
+        hostdata.load_dataset("Yelp", str(tmp_path))
+    # synthetic shapes: PairSampling keeps >= 1 train edge per user; NegSampling holds out exactly one row per user
+    a = hostdata.load_dataset("synth-tiny", None, "PairSampling")
+    b = hostdata.load_dataset("synth-tiny", None, "NegSampling")
+    Ut = a["userNum"]
+    assert np.bincount(a["train_u"], minlength=Ut).min() >= 1 and len(a["train_u"]) + len(a["test_u"]) == 60000
+    assert np.array_equal(np.bincount(b["test_u"], minlength=Ut), np.ones(Ut, np.int64)) and len(b["train_u"]) + Ut == 60000
+    assert np.array_equal(np.sort(a["rt_u"] * 10000 + a["rt_i"]), np.sort(b["rt_u"] * 10000 + b["rt_i"]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/1K/u.data"), reason="ml100k ships with the reference checkout only")
+def test_ml100k_leave_one_out_matches_reference_split_loo():
+    """--train_mode NegSampling on ml100k: hostdata's split == the reference's split_loo (loadGowalla.py:307-313) on the same file."""
+    import pandas as pd
+    from ngacf_b200 import hostdata
+    d = hostdata.load_dataset("ml100k", "/root/reference/data", "NegSampling")
+    ns = rh.load()
+    rt = pd.read_table("/root/reference/data/1K/u.data", sep="\t", names=["userId", "itemId", "rating", "timestamp"])
+    rt["userId"] -= 1
+    rt["itemId"] -= 1
+    tr, te = ns["loadGowalla"].split_loo(rt)
+    assert np.array_equal(d["train_u"], tr["userId"].values) and np.array_equal(d["train_i"], tr["itemId"].values)
+    assert np.array_equal(d["test_u"], te["userId"].values) and np.array_equal(d["test_i"], te["itemId"].values)
+    assert d["userNum"] == 943 and d["itemNum"] == 1682 and len(d["test_u"]) == 943
