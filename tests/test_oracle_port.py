@@ -363,3 +363,70 @@ def test_neg_step_against_live_reference_fp64():
     gsd = port.state_dict_from_params(grads)
     for k, prm in model.named_parameters():
         assert rel_err(gsd[k].numpy(), prm.grad.numpy()) < 1e-10, k
+
+
+# ----------------------------------------------------------------------------------------------
+# property tests (hypothesis): invariants of the specified generators and metrics on random shapes
+# ----------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(U=st.integers(3, 40), I=st.integers(12, 60), density=st.floats(0.05, 0.5), seed=st.integers(0, 10 ** 6), K=st.integers(1, 6))
+def test_sample_negs_invariants(U, I, density, seed, K):
+    """For any graph / split / seed: K distinct negatives, none a positive of the user, all from the pool; the positive column and
+    the user column echo the rows; rows are independent of the requested window (row r gets the same draw in any batch)."""
+    E = max(U, int(U * I * density))
+    u, i = port.synth_bipartite(U, I, min(E, U * I), seed % 97)
+    (tu, ti), (su, si) = port.split_train_test(u, i, U, seed % 89)
+    it = port.build_interactions(U, I, tu, ti, su, si)
+    ap = port.AllPositives(it)
+    if it.pool.shape[0] - int(np.diff(ap.ptr).max()) < K:
+        return
+    n = tu.shape[0]
+    users, items = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), 0, n, seed, 1, K, port.NEG_TAG_TRAIN)
+    assert np.array_equal(users[:, 0], tu) and np.array_equal(items[:, 0], ti)
+    pool = set(it.pool.tolist())
+    for r in range(n):
+        pos = set(ap.items[ap.ptr[tu[r]]:ap.ptr[tu[r] + 1]].tolist())
+        negs = items[r, 1:].tolist()
+        assert len(set(negs)) == K and not (set(negs) & pos) and set(negs) <= pool
+    lo = n // 3
+    _, part = port.sample_negs(it, ap, it.train_rows_user, ti.astype(np.int32), lo, n, seed, 1, K, port.NEG_TAG_TRAIN)
+    assert np.array_equal(part, items[lo:])
+
+
+@settings(max_examples=50, deadline=None)
+@given(rows=st.integers(1, 30), cands=st.integers(2, 40), top_k=st.integers(1, 12), seed=st.integers(0, 10 ** 6))
+def test_rank_metrics_properties(rows, cands, top_k, seed):
+    """HR is the fraction of rows whose positive has fewer than top_k strictly better candidates; NDCG <= HR; raising the positive's
+    score never lowers either; a positive that beats everything gives 1 / 1."""
+    rng = np.random.default_rng(seed)
+    sc = rng.standard_normal((rows, cands)).astype(np.float32)
+    hr, nd = port.rank_metrics(sc, top_k)
+    rank = (sc[:, 1:] > sc[:, :1]).sum(1)
+    assert abs(hr - float((rank < top_k).mean())) < 1e-12 and nd <= hr + 1e-12 and 0.0 <= nd
+    better = sc.copy()
+    better[:, 0] += 1.0
+    hr2, nd2 = port.rank_metrics(better, top_k)
+    assert hr2 >= hr - 1e-12 and nd2 >= nd - 1e-12
+    best = sc.copy()
+    best[:, 0] = sc.max() + 1
+    assert port.rank_metrics(best, top_k) == (1.0, 1.0)
+
+
+@settings(max_examples=20, deadline=None)
+@given(U=st.integers(2, 30), I=st.integers(2, 40), E=st.integers(1, 300), seed=st.integers(0, 10 ** 6))
+def test_build_graph_invariants(U, I, E, seed):
+    """CSR and CSC describe the same coalesced edge set; perm maps CSC positions to CSR edge ids; duplicates collapse."""
+    rng = np.random.default_rng(seed)
+    u = np.concatenate([np.arange(U), rng.integers(0, U, E)])       # every user has an edge (the reference asserts it)
+    i = np.concatenate([rng.integers(0, I, U), rng.integers(0, I, E)])
+    g = port.build_graph(np.stack([u, i]), U, I)
+    key = np.unique(u.astype(np.int64) * I + i)
+    assert g.E == key.shape[0]
+    assert np.array_equal(g.eu.astype(np.int64) * I + g.ei, key)                       # coalesced row-major, like adj.indices()
+    assert np.array_equal(np.repeat(np.arange(U), np.diff(g.rowptr)), g.eu) and np.array_equal(g.colidx, g.ei)
+    cols = np.repeat(np.arange(I), np.diff(g.colptr))
+    assert np.array_equal(g.eu[g.perm], g.rowidx) and np.array_equal(g.ei[g.perm], cols)
+    assert np.array_equal(np.sort(g.perm), np.arange(g.E))
