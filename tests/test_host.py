@@ -204,3 +204,18 @@ def test_ml100k_leave_one_out_matches_reference_split_loo():
     assert np.array_equal(d["train_u"], tr["userId"].values) and np.array_equal(d["train_i"], tr["itemId"].values)
     assert np.array_equal(d["test_u"], te["userId"].values) and np.array_equal(d["test_i"], te["itemId"].values)
     assert d["userNum"] == 943 and d["itemNum"] == 1682 and len(d["test_u"]) == 943
+
+
+def test_integration_stub_matches_the_abi():
+    """The ctypes stub shown in INTEGRATION.md binds ngacf_aggregate_fwd with as many arguments as the library's signature table."""
+    from ngacf_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"lib\.ngacf_aggregate_fwd\.argtypes = \[(.*?)\]", text)
+    assert m, "stub not found"
+    shown = [a.strip() for a in m.group(1).split(",")]
+    sig = _lib.SIGNATURES["ngacf_aggregate_fwd"][1]
+    assert len(shown) == len(sig), (len(shown), len(sig))
+    for name in re.findall(r"`(ngacf_[a-z_0-9]+)`", text):       # every entry point the document names exists
+        base = name
+        assert base in _lib.SIGNATURES or any(k.startswith(base) for k in _lib.SIGNATURES), name
