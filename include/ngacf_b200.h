@@ -111,13 +111,55 @@ int ngacf_aggregate_finalize(float* Z, const float* h, const float* norm, int32_
 /* ---------------------------------------------------------------------------------------------
  * (a10) pair scoring: score[b] = ELU(Z[u_b]) . ELU(Z[U+i_b])   (SPUIGACF.py:49-52), fixed summation
  * tree, and its backward G[row] += dscore * ELU(Z[other]) * ELU'(Z[row]),
- * deterministic (no atomics).  G must be zero-filled by the caller.
+ * deterministic (no atomics).  Only the batch's distinct rows of G are written: the caller zero-fills G, or treats every
+ * other row as zero (ngacf_stage_bwd_prep_active).
  * ------------------------------------------------------------------------------------------- */
 int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream);
 int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const int64_t* items, const float* dscore,
                           int32_t B, float* G, int32_t accumulate, void* stream);
 /* accumulate != 0: G[row] += ... for the batch's distinct rows (NegSampling scatters its B*(K+1) pairs one column of B pairs at a
  * time: the kernel's cost grows with the square of the pairs per call) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Pruned output stage of a TRAINING step (exact; csrc/pruned_stage.cu; used by the fused trainer, the semantics of
+ * train_eval_Gowalla.py:131-137 are kept).  The loss reads the last stage's output only at the batch rows
+ * (SPUIGACF.py:49-52), so that stage's aggregation is computed for those rows only, its gradient G is defined on those
+ * rows only, and d s_e vanishes on every edge without such an endpoint.  Results equal the full computation up to the
+ * order of additions (everything skipped is an exact zero).
+ *   mark_active : stamp[users[b]] = stamp[U+items[b]] = val (+ *val_dev); a node is active for a propagation iff its stamp
+ *                 equals that propagation's value (the trainer uses the dropout call index: no clearing is ever needed).
+ *                 task_count (may be NULL) is reset to 0 for the plan call that follows.
+ *   active_plan : task_list/task_count = compacted list of the tasks (ngacf_graph_build) whose row is active;
+ *                 edge_bits uint32[(n_adj+31)/32]: bit p = neighbour adj_idx[p] is active (n_adj = 2E positions).
+ *   aggregate_fwd_active     : ngacf_aggregate_fwd over the listed tasks only (Z/norm of every other row keep stale data).
+ *   stage_bwd_prep_active    : Ghat/dN of the listed rows only (H = 1).
+ *   stage_bwd_edges_active   : the pruned pair of edge passes (H = 1): mode 0 = user rows (stores (d s_e, e*keep) of the
+ *                 visited edges), mode 1 = item rows.  G / Ghat / dN are read at active rows only; dh / dS are written for
+ *                 every row of the side.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_mark_active(int32_t* stamp, const int64_t* users, const int64_t* items, int32_t B, int32_t U, int32_t val,
+                      const int64_t* val_dev, int32_t* task_count, void* stream);
+int ngacf_active_plan(const int32_t* stamp, int32_t val, const int64_t* val_dev, const int32_t* tasks, int32_t T,
+                      const int32_t* adj_idx, int64_t n_adj, int32_t* task_list, int32_t* task_count, uint32_t* edge_bits,
+                      void* stream);
+int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
+                               const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
+                               const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
+                               const float* h, const float* s, int32_t H, const uint8_t* edgemask, float scale,
+                               float* Z, float* norm, void* stream);
+int ngacf_stage_bwd_prep_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
+                                const float* G, const float* Z, const float* h, const float* norm, int32_t H,
+                                float* Ghat, float* dN, void* stream);
+int ngacf_stage_bwd_edges_active(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end, const int32_t* adj_ptr,
+                                 const int32_t* adj_idx, const int32_t* adj_eid,
+                                 const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
+                                 const float* G, const float* Ghat, const float* dN, const float* h, const float* s, int32_t H,
+                                 const uint8_t* edgemask, float scale, const float* const* wtab, int32_t U,
+                                 const int32_t* stamp, int32_t stamp_val, const int64_t* stamp_dev, const uint32_t* edge_bits,
+                                 float* ds_store, float* dh, float* dS, void* stream);
+/* end-of-step bookkeeping of a captured step (train_eval_Gowalla.py:139 `total_loss += loss`, :111-115 row cursor):
+ * *total += *loss (either may be NULL together), row_dev[0] += row_stride (row_dev may be NULL) */
+int ngacf_step_counters(double* total, const float* loss, int64_t* row_dev, int64_t row_stride, void* stream);
 
 /* F = ELU(Z) materialised for evaluation (SPUIGACF.py:214) */
 int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream);

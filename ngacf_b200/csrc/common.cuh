@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include "../../include/ngacf_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -40,6 +41,23 @@ void transform_bwd_tc(const float* dh, const float* dS, const float* Xu, const f
                       int* nb_u, int* nb_i, cudaStream_t st);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute is per DEVICE: a process that touches a second GPU must set it there too.  `first()` is true exactly once
+// per device (and holds a lock while the caller sets the attributes, so a concurrent first launch cannot overtake them).
+struct PerDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;
+    template <class F>
+    void run(F&& set_attributes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        std::lock_guard<std::mutex> lock(mu);
+        if (done & bit) return;
+        set_attributes();
+        done |= bit;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // loads / stores with cache intent: gathered tables go through L1 (popular rows hit), streamed
@@ -128,6 +146,108 @@ __device__ __forceinline__ float head_reduce(float v, unsigned mask) {
         v += __shfl_xor_sync(mask, v, 8, 16);
     }
     return v;
+}
+
+// Issue fence: an empty asm that names one register of each of eight loaded vectors.  ptxas must have all eight loads issued
+// before it and may not start consuming them earlier -- without it the consumers are interleaved with the loads (two or three
+// registers are recycled), and since issue is in order every consumer stalls the loads behind it: eight independent gathers
+// become a chain of three or four round trips.  Matters for the kernels that run few rows (latency-, not throughput-bound).
+#define NGACF_ISSUE_FENCE8(v)                                                                                                   \
+    asm volatile("" : "+f"((v)[0].x), "+f"((v)[1].x), "+f"((v)[2].x), "+f"((v)[3].x), "+f"((v)[4].x), "+f"((v)[5].x), \
+                 "+f"((v)[6].x), "+f"((v)[7].x))
+#define NGACF_ISSUE_FENCE4(v) asm volatile("" : "+f"((v)[0].x), "+f"((v)[1].x), "+f"((v)[2].x), "+f"((v)[3].x))
+
+// ---------------------------------------------------------------------------------------------
+// long rows (> CHUNK edges) are split into chunk tasks; every chunk writes its partial (64 accumulators + NSUM per-head sums) to
+// its slot, and the group that arrives LAST sums the slots in slot order (deterministic, no atomics on data) and continues with
+// the totals.  Returns false for every other group.  The counter is re-armed for the next launch by the last arriver.
+// ---------------------------------------------------------------------------------------------
+// FAST: eight slots in flight (32 more registers) -- for the kernels that run few rows, where this sum is the critical path; the
+// throughput-bound full-graph kernels keep the plain loop (the extra registers cost them a resident CTA per SM: measured
+// +8..18 % on the stage-0 kernels), their long rows are scheduled first and the sum hides behind the rest of the grid.
+template <int H, int NSUM, bool FAST = false>
+__device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
+                                                 float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
+    const int head = H == 8 ? (lane16 >> 1) : 0;
+    const int first = long_first_slot[lid];
+    const int nslots = long_first_slot[lid + 1] - first;
+    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
+    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
+    // per-head scalars: NSUM values per head at [64 + j*H + head]: the slot has 8 floats of room => NSUM*H <= 8
+    if ((H == 8 && (lane16 & 1) == 0) || (H == 1 && lane16 == 0)) {
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
+    }
+    __threadfence();
+    __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
+    int old = 0;
+    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
+    old = __shfl_sync(gm, old, 0, 16);
+    if (old != nslots - 1) return false;
+    __threadfence();
+    if constexpr (!FAST) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ts[NSUM];
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
+        for (int c = 0; c < nslots; ++c) {
+            const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
+            float4 v = ld_cg4(sl + lane16 * 4);
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+#pragma unroll
+            for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
+        }
+        acc = t;
+#pragma unroll
+        for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
+    } else {
+        // fixed summation order: four interleaved partial sums (slots c, c+4, ...), then ((0+1)+(2+3)).  Eight slots are in flight
+        // at a time: the most popular item of the Gowalla-shape graph has 111 slots, and a dependent chain of 111 L2 round trips was
+        // the critical path of every kernel that runs few rows (the pruned output stage)
+        float4 t4[4];
+        float ts4[4][NSUM];
+    #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+            for (int j = 0; j < NSUM; ++j) ts4[q][j] = 0.f;
+        }
+        for (int c0 = 0; c0 < nslots; c0 += 8) {
+            float4 v[8];
+            float sv[8][NSUM];
+    #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool in = c0 + q < nslots;
+                const float* sl = scratch + (size_t)(first + (in ? c0 + q : 0)) * SCRATCH_STRIDE;
+                v[q] = in ? ld_cg4(sl + lane16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+                for (int j = 0; j < NSUM; ++j) sv[q][j] = in ? __ldcg(sl + D + j * H + head) : 0.f;
+            }
+            NGACF_ISSUE_FENCE8(v);
+    #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4& a = t4[q & 3];
+                a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w;
+    #pragma unroll
+                for (int j = 0; j < NSUM; ++j) ts4[q & 3][j] += sv[q][j];
+            }
+        }
+        float4 t;
+        t.x = (t4[0].x + t4[1].x) + (t4[2].x + t4[3].x);
+        t.y = (t4[0].y + t4[1].y) + (t4[2].y + t4[3].y);
+        t.z = (t4[0].z + t4[1].z) + (t4[2].z + t4[3].z);
+        t.w = (t4[0].w + t4[1].w) + (t4[2].w + t4[3].w);
+        acc = t;
+    #pragma unroll
+        for (int j = 0; j < NSUM; ++j) sums[j] = (ts4[0][j] + ts4[1][j]) + (ts4[2][j] + ts4[3][j]);
+    }
+    if (lane16 == 0) long_counter[lid] = 0;    // re-arm for the next launch
+    return true;
+}
+
+// "active" rows of a pruned last stage (ngacf_mark_active): node n is active iff stamp[n] == value of this propagation
+__device__ __forceinline__ int active_value(int val, const int64_t* __restrict__ val_dev) {
+    return val_dev ? val + (int)*val_dev : val;
 }
 
 }  // namespace ngacf

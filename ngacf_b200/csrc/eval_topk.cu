@@ -216,11 +216,10 @@ extern "C" int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, cons
     NGACF_REQUIRE(F && users && train_ptr && train_items && in_pool && top_ids && top_scores && U > 0 && I > 0 && n_users >= 0,
                   "score_topk_exact: null/empty argument");
     if (n_users == 0) return NGACF_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EX_SMEM);
-        attr_done = true;
-    }
+    });
     score_topk_exact_kernel<<<ceil_div(n_users, EX_USERS), EX_THREADS, EX_SMEM, (cudaStream_t)stream>>>(F, U, I, users, n_users, train_ptr,
                                                                                                          train_items, in_pool, top_ids, top_scores);
     return check_launch("score_topk_exact");

@@ -403,11 +403,10 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     float* cand_thr = (float*)w;
     cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
     tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-        attr_done = true;
-    }
+    });
     tc::score_topk_tc_kernel<<<ceil_div(n_users, tc::TM), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, train_ptr, train_items, pool_bits,
                                                                                              img, n_tiles, cand_ids, cand_thr);
     tc::rescore_kernel<<<ceil_div((int64_t)n_users * 16, 256), 256, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, maxnorm, top_ids, top_scores,

@@ -38,45 +38,6 @@ __global__ void __launch_bounds__(256) stage_bwd_prep_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// defined in propagate_fwd.cu's translation unit as a template; re-declared here (same body) to keep
-// the two .cu files independently compilable
-template <int H, int NSUM>
-__device__ __forceinline__ bool long_row_combine_b(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
-                                                   float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
-    const int head = lane_head_b<H>(lane16);
-    const int first = long_first_slot[lid];
-    const int nslots = long_first_slot[lid + 1] - first;
-    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
-    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
-    if (head_writer<H>(lane16)) {
-#pragma unroll
-        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
-    }
-    __threadfence();
-    __syncwarp(gm);
-    int old = 0;
-    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
-    old = __shfl_sync(gm, old, 0, 16);
-    if (old != nslots - 1) return false;
-    __threadfence();
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ts[NSUM];
-#pragma unroll
-    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
-    for (int c = 0; c < nslots; ++c) {
-        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
-        float4 v = ld_cg4(sl + lane16 * 4);
-        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-#pragma unroll
-        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
-    }
-    acc = t;
-#pragma unroll
-    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
-    if (lane16 == 0) long_counter[lid] = 0;
-    return true;
-}
-
 template <int H, int MODE, bool DROP, bool PARTIAL>
 __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_edges_kernel(const int4* __restrict__ tasks, int T_begin, int T_end,
                                                               const int* __restrict__ adj_ptr, const int* __restrict__ adj_idx,
@@ -175,7 +136,7 @@ __global__ void __launch_bounds__(256, (MODE == 1 && H == 1) ? 5 : 0) stage_bwd_
     if (lid >= 0) {
         float sums[1] = {dSacc};
         const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
-        if (!long_row_combine_b<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         dSacc = sums[0];
     }
     if (PARTIAL) {     // multi-GPU: raw partial sums over this rank's slice of the row; reduced across ranks, then stage_bwd_finalize
@@ -456,14 +417,13 @@ extern "C" int ngacf_stage_bwd_edges(int32_t mode, const int32_t* tasks, int32_t
     const int blocks = ceil_div((int64_t)(T_end - T_begin) * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
+    static PerDeviceOnce once;
+    once.run([] {
 #define CARVE(HH, MM, DR) cudaFuncSetAttribute(stage_bwd_edges_kernel<HH, MM, DR, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0)
-    static bool carve_done = false;
-    if (!carve_done) {
         CARVE(8, 0, true); CARVE(8, 0, false); CARVE(8, 1, true); CARVE(8, 1, false);
         CARVE(1, 0, true); CARVE(1, 0, false); CARVE(1, 1, true); CARVE(1, 1, false);
-        carve_done = true;
-    }
 #undef CARVE
+    });
 #define LAUNCH(HH, MM, DR, PA)                                                                                                              \
     stage_bwd_edges_kernel<HH, MM, DR, PA><<<blocks, 256, 0, st>>>(tk, T_begin, T_end, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, \
                                                                    scratch, G, Ghat, dN, h, s, edgemask, scale, wtab, U, ds_store, dh, dS)
@@ -522,12 +482,11 @@ extern "C" int ngacf_transform_bwd(const float* dh, const float* dS, const float
         return check_launch("transform_bwd(tc)");
     }
     transform_bwd_grid(U, I, &bu, &bi);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(transform_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
         cudaFuncSetAttribute(transform_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
-        attr_done = true;
-    }
+    });
     cudaStream_t st = (cudaStream_t)stream;
     float* partials = (float*)workspace;
     if (H == 8) {

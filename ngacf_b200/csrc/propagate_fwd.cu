@@ -207,55 +207,15 @@ __global__ void __launch_bounds__(256, 4) transform_fwd_kernel(const float* __re
 template <int H>
 __device__ __forceinline__ int lane_head(int lane16) { return H == 8 ? (lane16 >> 1) : 0; }
 
-// combine the partials of a long row: called by every group that finishes a chunk; returns true for
-// the group that arrived last (which then holds the totals, summed in slot order -> deterministic)
-template <int H, int NSUM>
-__device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* __restrict__ long_first_slot, int* long_counter,
-                                                 float* scratch, int lane16, unsigned gm, float4& acc, float (&sums)[NSUM]) {
-    const int head = lane_head<H>(lane16);
-    const int first = long_first_slot[lid];
-    const int nslots = long_first_slot[lid + 1] - first;
-    float* slot = scratch + (size_t)(first + chunk) * SCRATCH_STRIDE;
-    *reinterpret_cast<float4*>(slot + lane16 * 4) = acc;
-    // per-head scalars: NSUM values per head, stored at [64 + j*H... ]: slot has 8 floats of room => NSUM*H <= 8
-    if ((H == 8 && (lane16 & 1) == 0) || (H == 1 && lane16 == 0)) {
-#pragma unroll
-        for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
-    }
-    __threadfence();
-    __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
-    int old = 0;
-    if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
-    old = __shfl_sync(gm, old, 0, 16);
-    if (old != nslots - 1) return false;
-    __threadfence();
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ts[NSUM];
-#pragma unroll
-    for (int j = 0; j < NSUM; ++j) ts[j] = 0.f;
-    for (int c = 0; c < nslots; ++c) {
-        const float* sl = scratch + (size_t)(first + c) * SCRATCH_STRIDE;
-        float4 v = ld_cg4(sl + lane16 * 4);
-        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-#pragma unroll
-        for (int j = 0; j < NSUM; ++j) ts[j] += __ldcg(sl + D + j * H + head);
-    }
-    acc = t;
-#pragma unroll
-    for (int j = 0; j < NSUM; ++j) sums[j] = ts[j];
-    if (lane16 == 0) long_counter[lid] = 0;    // re-arm for the next launch
-    return true;
-}
-
-template <int H, bool DROP, bool PARTIAL>
-__global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ adj_ptr,
-                                                            const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
-                                                            const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
-                                                            const float* __restrict__ h, const float* __restrict__ s,
-                                                            const uint8_t* __restrict__ edgemask, float scale,
-                                                            float* __restrict__ Z, float* __restrict__ norm, int partial_from) {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    if (t >= T) return;                                  // whole 16-lane groups exit together
+// body of one task; the kernels below call it for task t = group index (every row) or for the tasks of a compacted list
+// LAT: latency-optimised variant for launches that run few rows (the pruned output stage)
+template <int H, bool DROP, bool PARTIAL, bool LAT = false>
+__device__ __forceinline__ void aggregate_task(const int t, const int4* __restrict__ tasks, const int* __restrict__ adj_ptr,
+                                               const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
+                                               const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
+                                               const float* __restrict__ h, const float* __restrict__ s,
+                                               const uint8_t* __restrict__ edgemask, float scale,
+                                               float* __restrict__ Z, float* __restrict__ norm, int partial_from) {
     const int lane16 = threadIdx.x & 15;
     const unsigned gm = group_mask();
     const int head = lane_head<H>(lane16);
@@ -300,13 +260,36 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
             rs_l += w_l;
             const float wd_l = DROP ? ((mk_c & 1u) ? w_l * scale : 0.f) : w_l;
             const int cnt = min(16, end - base);
+            if constexpr (LAT) {
+                // eight row gathers in flight before the first is consumed (NGACF_ISSUE_FENCE8); predicated loads for the tail
+                for (int j0 = 0; j0 < cnt; j0 += 8) {
+                    float4 hm[8];
+                    float wd[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int j = (j0 + q) & 15;
+                        const int m = __shfl_sync(gm, m_c, j, 16);
+                        wd[q] = __shfl_sync(gm, wd_l, j, 16);
+                        hm[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j0 + q < cnt) hm[q] = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                        else wd[q] = 0.f;
+                    }
+                    NGACF_ISSUE_FENCE8(hm);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        acc.x = fmaf(wd[q], hm[q].x, acc.x); acc.y = fmaf(wd[q], hm[q].y, acc.y);
+                        acc.z = fmaf(wd[q], hm[q].z, acc.z); acc.w = fmaf(wd[q], hm[q].w, acc.w);
+                    }
+                }
+            } else {
 #pragma unroll 8
-            for (int j = 0; j < cnt; ++j) {
-                const int m = __shfl_sync(gm, m_c, j, 16);
-                const float wd = __shfl_sync(gm, wd_l, j, 16);
-                const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
-                acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
-                acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
+                for (int j = 0; j < cnt; ++j) {
+                    const int m = __shfl_sync(gm, m_c, j, 16);
+                    const float wd = __shfl_sync(gm, wd_l, j, 16);
+                    const float4 hm = ld_gather4(h + (int64_t)m * D + lane16 * 4);
+                    acc.x = fmaf(wd, hm.x, acc.x); acc.y = fmaf(wd, hm.y, acc.y);
+                    acc.z = fmaf(wd, hm.z, acc.z); acc.w = fmaf(wd, hm.w, acc.w);
+                }
             }
             m_c = m_1; m_1 = m_2; eid_1 = eid_2; s_c = s_1; mk_c = mk_1;
         }
@@ -345,7 +328,7 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
     if (lid >= 0) {
         float sums[1] = {rs};
         const int chunk = (beg - __ldg(adj_ptr + node)) / CHUNK;
-        if (!long_row_combine<H, 1>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
+        if (!long_row_combine<H, 1, LAT>(lid, chunk, long_first_slot, long_counter, scratch, lane16, gm, acc, sums)) return;
         rs = sums[0];
     }
     if (PARTIAL && t >= partial_from) {
@@ -363,6 +346,37 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
                make_float4(fmaf(acc.x, inv, hn.x), fmaf(acc.y, inv, hn.y), fmaf(acc.z, inv, hn.z), fmaf(acc.w, inv, hn.w)));
     if (H == 8) { if ((lane16 & 1) == 0) norm[(int64_t)node * 8 + head] = rs; }
     else        { if (lane16 == 0) norm[node] = rs; }
+}
+
+template <int H, bool DROP, bool PARTIAL>
+__global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ adj_ptr,
+                                                            const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
+                                                            const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
+                                                            const float* __restrict__ h, const float* __restrict__ s,
+                                                            const uint8_t* __restrict__ edgemask, float scale,
+                                                            float* __restrict__ Z, float* __restrict__ norm, int partial_from) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (t >= T) return;                                  // whole 16-lane groups exit together
+    aggregate_task<H, DROP, PARTIAL>(t, tasks, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm,
+                                     partial_from);
+}
+
+// Pruned last stage (FusedTrainer): only the tasks of the rows marked active are run (list built by ngacf_active_plan) -- the
+// step reads nothing else of the last stage's output (the pair scores gather the batch rows, every other row has a zero
+// gradient).  Persistent grid over the compacted list: the working groups are dense however few rows are active.
+template <int H, bool DROP>
+__global__ void __launch_bounds__(256) aggregate_fwd_list_kernel(const int4* __restrict__ tasks, const int* __restrict__ task_list,
+                                                                 const int* __restrict__ task_count, const int* __restrict__ adj_ptr,
+                                                                 const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
+                                                                 const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
+                                                                 const float* __restrict__ h, const float* __restrict__ s,
+                                                                 const uint8_t* __restrict__ edgemask, float scale,
+                                                                 float* __restrict__ Z, float* __restrict__ norm) {
+    const int n = __ldg(task_count);
+    const int stride = (gridDim.x * blockDim.x) >> 4;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; g < n; g += stride)
+        aggregate_task<H, DROP, false, true>(__ldg(task_list + g), tasks, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s,
+                                       edgemask, scale, Z, norm, 0x7fffffff);
 }
 
 // Z[n] = h[n] + P[n] / norm[n] for rows whose partial sums P (stored in Z) were reduced across ranks
@@ -440,12 +454,11 @@ extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t app
         return check_launch("transform_fwd(tc)");
     }
     const int tiles_u = ceil_div(U, TF_TM), tiles_i = ceil_div(I, TF_TM);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(transform_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
         cudaFuncSetAttribute(transform_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
-        attr_done = true;
-    }
+    });
     if (H == 8)
         transform_fwd_kernel<8><<<tiles_u + tiles_i, 256, TF_SMEM, (cudaStream_t)stream>>>(Xu, Xi, apply_elu, featmask, scale, wtab, U, I, tiles_u, h, s);
     else
@@ -464,14 +477,12 @@ extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_
     const int blocks = ceil_div((int64_t)T * 16, 256);
     cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
-    static bool carve_done = false;
-    if (!carve_done) {     // gather kernels use no shared memory: ask for the whole unified array as L1 (popular rows hit)
-        cudaFuncSetAttribute(aggregate_fwd_kernel<8, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        cudaFuncSetAttribute(aggregate_fwd_kernel<8, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        cudaFuncSetAttribute(aggregate_fwd_kernel<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        cudaFuncSetAttribute(aggregate_fwd_kernel<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        carve_done = true;
-    }
+    static PerDeviceOnce once;
+    once.run([] {     // gather kernels use no shared memory: ask for the whole unified array as L1
+#define CARVE(HH, DR, PA) cudaFuncSetAttribute(aggregate_fwd_kernel<HH, DR, PA>, cudaFuncAttributePreferredSharedMemoryCarveout, 0)
+        CARVE(8, true, false); CARVE(8, false, false); CARVE(1, true, false); CARVE(1, false, false);
+#undef CARVE
+    });
 #define LAUNCH(HH, DR, PA) aggregate_fwd_kernel<HH, DR, PA><<<blocks, 256, 0, st>>>(tk, T, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm, partial_from)
     if (partial_from < T) {
         if (H == 8) { if (edgemask) LAUNCH(8, true, true); else LAUNCH(8, false, true); }
@@ -482,4 +493,23 @@ extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_
     }
 #undef LAUNCH
     return check_launch("aggregate_fwd");
+}
+
+extern "C" int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
+                                          const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
+                                          const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* h,
+                                          const float* s, int32_t H, const uint8_t* edgemask, float scale, float* Z, float* norm,
+                                          void* stream) {
+    NGACF_REQUIRE(tasks && task_list && task_count && adj_ptr && adj_idx && h && s && Z && norm && T > 0, "aggregate_fwd_active: null/empty argument");
+    NGACF_REQUIRE(H == 1 || H == 8, "aggregate_fwd_active: H must be 1 or 8 (got %d)", H);
+    NGACF_REQUIRE(!edgemask || adj_eid, "aggregate_fwd_active: edge dropout needs adj_eid");
+    int blocks = ceil_div((int64_t)T * 16, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;              // persistent: the list length lives on the device
+    cudaStream_t st = (cudaStream_t)stream;
+    const int4* tk = reinterpret_cast<const int4*>(tasks);
+#define LAUNCH(HH, DR) aggregate_fwd_list_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, task_list, task_count, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
+    if (H == 8) { if (edgemask) LAUNCH(8, true); else LAUNCH(8, false); }
+    else        { if (edgemask) LAUNCH(1, true); else LAUNCH(1, false); }
+#undef LAUNCH
+    return check_launch("aggregate_fwd_active");
 }

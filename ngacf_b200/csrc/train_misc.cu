@@ -269,6 +269,13 @@ __global__ void sample_pairs_kernel(const int* __restrict__ rows_user, const int
 
 __global__ void counter_add_kernel(int64_t* c, int64_t d) { *c += d; }
 
+// end-of-step bookkeeping of a captured step in one launch: epoch loss accumulator and train-row cursor
+__global__ void step_counters_kernel(double* total, const float* __restrict__ loss, int64_t* row_dev, int64_t row_stride) {
+    if (total && loss) *total += (double)*loss;
+    if (row_dev) row_dev[0] += row_stride;
+}
+
+
 }  // namespace ngacf
 
 using namespace ngacf;
@@ -277,6 +284,12 @@ extern "C" int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream) 
     NGACF_REQUIRE(counter, "counter_add: null argument");
     counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
     return check_launch("counter_add");
+}
+
+extern "C" int ngacf_step_counters(double* total, const float* loss, int64_t* row_dev, int64_t row_stride, void* stream) {
+    NGACF_REQUIRE((total && loss) || row_dev, "step_counters: nothing to do");
+    step_counters_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(total, loss, row_dev, row_stride);
+    return check_launch("step_counters");
 }
 
 extern "C" int ngacf_score_pairs(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* scores, void* stream) {

@@ -262,12 +262,11 @@ extern "C" int ngacf_transform_bwd_dx(const float* dh, const float* Xu, const fl
         return check_launch("transform_bwd_dx(tc)");
     }
     const int tiles_u = ceil_div(U, DX_TM), tiles_i = ceil_div(I, DX_TM);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(transform_bwd_dx_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DX_SMEM);
         cudaFuncSetAttribute(transform_bwd_dx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DX_SMEM);
-        attr_done = true;
-    }
+    });
     cudaStream_t st = (cudaStream_t)stream;
     if (H == 8) transform_bwd_dx_kernel<8><<<tiles_u + tiles_i, 256, DX_SMEM, st>>>(dh, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, tiles_u, dXu, dXi, accumulate);
     else        transform_bwd_dx_kernel<1><<<tiles_u + tiles_i, 256, DX_SMEM, st>>>(dh, Xu, Xi, apply_elu, featmask, scale, wtab, U, I, tiles_u, dXu, dXi, accumulate);
@@ -289,12 +288,11 @@ extern "C" int ngacf_transform_bwd_dw(const float* dh, const float* dS, const fl
     if (workspace_bytes < ngacf_transform_bwd_dw_workspace_bytes(U, I)) { set_error("transform_bwd_dw: workspace too small"); return NGACF_ERR_WORKSPACE; }
     int bu, bi;
     dw_grid(U, I, &bu, &bi);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(transform_bwd_dw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM);
         cudaFuncSetAttribute(transform_bwd_dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM);
-        attr_done = true;
-    }
+    });
     cudaStream_t st = (cudaStream_t)stream;
     float* partials = (float*)workspace;
     float* vsum = partials + (size_t)(bu + bi) * DW_PART;

@@ -342,11 +342,10 @@ static void side_grid(int U, int I, int* nb_u, int* nb_i) {
 template <int H, int MODE>
 static void launch(const float* Au, const float* Ai, const float* Zu, const float* Zi, int apply_elu, const uint64_t* featmask, float scale,
                    const float* const* wtab, int U, int I, float* Ou, float* Oi, float* s, int accumulate, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(transform_tc_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        attr_done = true;
-    }
+    });
     int bu, bi;
     side_grid(U, I, &bu, &bi);
     transform_tc_kernel<H, MODE><<<bu + bi, THREADS, SMEM_BYTES, st>>>(Au, Ai, Zu, Zi, apply_elu, featmask, scale, wtab, U, I, bu, Ou, Oi, s, accumulate);
@@ -733,12 +732,11 @@ void transform_bwd_dx_tc(const float* dh, const float* Zu, const float* Zi, int 
 void transform_bwd_tc(const float* dh, const float* dS, const float* Xu, const float* Xi, int apply_elu, const uint64_t* featmask, float scale,
                       const float* const* wtab, int H, int U, int I, float* dXu, float* dXi, int accumulate_dx, float* partials,
                       int* nb_u, int* nb_i, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(tcx::bwd::transform_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx::bwd::SMEM_BYTES);
         cudaFuncSetAttribute(tcx::bwd::transform_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx::bwd::SMEM_BYTES);
-        attr_done = true;
-    }
+    });
     tcx::bwd::side_grid1(U, I, nb_u, nb_i);
     const int grid = *nb_u + *nb_i;
     if (H == 8)

@@ -66,6 +66,54 @@ def aggregate_fwd(g: BipartiteGraph, scratch, counter, h, s, H, edgemask, scale,
               _p(counter), _p(scratch), _p(h), _p(s), H, _p(edgemask), float(scale), _p(Z), _p(norm), int(partial_from), _s())
 
 
+class ActiveRows:
+    """Rows a pruned output stage computes (csrc/pruned_stage.cu): stamp int32[N] (a node is active iff stamp[node] == val
+    (+ *val_dev)), the compacted list of their tasks and one activity bit per adjacency position."""
+
+    def __init__(self, g: BipartiteGraph, val=0, val_dev=None):
+        dev = g.device
+        self.g = g
+        self.stamp = torch.full((g.N,), -1, dtype=torch.int32, device=dev)
+        self.task_list = torch.empty(max(g.T, 1), dtype=torch.int32, device=dev)
+        self.task_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.edge_bits = torch.zeros((2 * g.E + 31) // 32 + 1, dtype=torch.int32, device=dev)
+        self.val, self.val_dev = int(val), val_dev
+
+    def at(self, val, val_dev=None):
+        self.val, self.val_dev = int(val) & 0x7FFFFFFF, val_dev
+        return self
+
+    def mark(self, users, items):
+        """stamps the batch rows and builds the task list / activity bits for them"""
+        g = self.g
+        _lib.call("ngacf_mark_active", _p(self.stamp), _p(users), _p(items), users.numel(), g.U, self.val, _p(self.val_dev),
+                  _p(self.task_count), _s())
+        _lib.call("ngacf_active_plan", _p(self.stamp), self.val, _p(self.val_dev), _p(g.tasks), g.T, _p(g.adj_idx), 2 * g.E,
+                  _p(self.task_list), _p(self.task_count), _p(self.edge_bits), _s())
+
+
+def aggregate_fwd_active(g: BipartiteGraph, scratch, counter, h, s, H, edgemask, scale, Z, norm, act: ActiveRows):
+    _lib.call("ngacf_aggregate_fwd_active", _p(g.tasks), g.T, _p(act.task_list), _p(act.task_count), _p(g.adj_ptr), _p(g.adj_idx),
+              _p(g.adj_eid), _p(g.long_first_slot), _p(counter), _p(scratch), _p(h), _p(s), H, _p(edgemask), float(scale), _p(Z),
+              _p(norm), _s())
+
+
+def stage_bwd_prep_active(g: BipartiteGraph, G, Z, h, norm, H, Ghat, dN, act: ActiveRows):
+    _lib.call("ngacf_stage_bwd_prep_active", _p(g.tasks), g.T, _p(act.task_list), _p(act.task_count), _p(G), _p(Z), _p(h), _p(norm), H,
+              _p(Ghat), _p(dN), _s())
+
+
+def stage_bwd_edges_active(mode, g: BipartiteGraph, scratch, counter, G, Ghat, dN, h, s, H, edgemask, scale, wtab, ds_store, dh, dS, act: ActiveRows):
+    t0, t1 = (0, g.T_users) if mode == 0 else (g.T_users, g.T)
+    _lib.call("ngacf_stage_bwd_edges_active", mode, _p(g.tasks), t0, t1, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid),
+              _p(g.long_first_slot), _p(counter), _p(scratch), _p(G), _p(Ghat), _p(dN), _p(h), _p(s), H, _p(edgemask),
+              float(scale), _p(wtab), g.U, _p(act.stamp), act.val, _p(act.val_dev), _p(act.edge_bits), _p(ds_store), _p(dh), _p(dS), _s())
+
+
+def step_counters(total, loss, row_dev, row_stride):
+    _lib.call("ngacf_step_counters", _p(total), _p(loss), _p(row_dev), int(row_stride), _s())
+
+
 def aggregate_finalize(Z, h, norm, H):
     _lib.call("ngacf_aggregate_finalize", _p(Z), _p(h), _p(norm), H, Z.shape[0], _s())
 

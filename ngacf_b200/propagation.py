@@ -28,9 +28,9 @@ class Propagation:
         dev, N, E = graph.device, graph.N, graph.E
         f32 = dict(dtype=torch.float32, device=dev)
         self.h = [torch.empty((N, D), **f32) for _ in self.stages]
-        self.Z = [torch.empty((N, D), **f32) for _ in self.stages]
+        self.Z = [torch.zeros((N, D), **f32) for _ in self.stages]        # zeros: rows a pruned last stage skips stay finite
         self.s = [torch.empty((N, H), **f32) for H, _ in self.stages]
-        self.norm = [torch.empty((N, H), **f32) for H, _ in self.stages]
+        self.norm = [torch.zeros((N, H), **f32) for H, _ in self.stages]
         self.featmask: List[Optional[torch.Tensor]] = [None] * len(self.stages)
         self.edgemask: List[Optional[torch.Tensor]] = [None] * len(self.stages)
         self._own_masks = None
@@ -75,17 +75,30 @@ class Propagation:
         self.featmask, self.edgemask = list(fm), [m[:self.g.E] for m in em]
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor], after_first_kernel=None) -> torch.Tensor:
+    def can_prune(self) -> bool:
+        """The pruned last stage (ops.ActiveRows) exists for a single-head output stage, which every model of the family has."""
+        return self.stages[-1][0] == 1
+
+    def forward(self, uEmbd: torch.Tensor, iEmbd: torch.Tensor, wtabs: Sequence[torch.Tensor], after_first_kernel=None,
+                active=None) -> torch.Tensor:
         """after_first_kernel: optional callback run right after the first (dense) kernel was enqueued -- the trainer uses it to
-        start the OTHER propagation one kernel later, so that its dense kernels overlap this one's gather kernels."""
+        start the OTHER propagation one kernel later, so that its dense kernels overlap this one's gather kernels.
+        active (ops.ActiveRows): the caller reads the returned Z at the marked rows only (the batch rows of a training step,
+        SPUIGACF.py:49-52) -- the last stage's aggregation is then computed for those rows alone; every other row of Z[-1] /
+        norm[-1] keeps stale data."""
         g = self.g
         Xu, Xi, act = uEmbd, iEmbd, 0
+        last = len(self.stages) - 1
         for k, (H, _) in enumerate(self.stages):
             ops.transform_fwd(Xu, Xi, act, self.featmask[k], self.scale, wtabs[k], H, g.U, g.I, self.h[k], self.s[k])
             if k == 0 and after_first_kernel is not None:
                 after_first_kernel()
-            ops.aggregate_fwd(g, self.scratch, self.counter, self.h[k], self.s[k], H, self.edgemask[k], self.scale,
-                              self.Z[k], self.norm[k])
+            if active is not None and k == last:
+                ops.aggregate_fwd_active(g, self.scratch, self.counter, self.h[k], self.s[k], H, self.edgemask[k], self.scale,
+                                         self.Z[k], self.norm[k], active)
+            else:
+                ops.aggregate_fwd(g, self.scratch, self.counter, self.h[k], self.s[k], H, self.edgemask[k], self.scale,
+                                  self.Z[k], self.norm[k])
             Xu, Xi, act = self.Z[k], self.Z[k][g.U:], 1
         return self.Z[-1]
 
@@ -95,8 +108,9 @@ class Propagation:
             dev, N, E = self.g.device, self.g.N, self.g.E
             f32 = dict(dtype=torch.float32, device=dev)
             S = len(self.stages)
-            self._bwd = dict(G=[torch.empty((N, D), **f32), torch.empty((N, D), **f32)], Ghat=torch.empty((N, D), **f32),
-                             dh=torch.empty((N, D), **f32), dN=torch.empty((N, 8), **f32), dS=torch.empty((N, 8), **f32),
+            # G / Ghat / dN start as zeros: the pruned output stage leaves the rows of inactive nodes untouched (stale, finite)
+            self._bwd = dict(G=[torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)], Ghat=torch.zeros((N, D), **f32),
+                             dh=torch.empty((N, D), **f32), dN=torch.zeros((N, 8), **f32), dS=torch.empty((N, 8), **f32),
                              ds=torch.empty(max(E, 1) * 8, **f32),
                              ws=torch.empty(ops.transform_bwd_workspace_bytes(self.g.U, self.g.I) // 4, **f32),
                              # split mode: per-stage dh/dS (the deferred dW kernel of stage k reads them while stage k-1 is running)
@@ -109,25 +123,36 @@ class Propagation:
         return self._bwd_buffers()["G"][0]
 
     def backward(self, G_last: torch.Tensor, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate: bool, after_first_kernel=None,
-                 before_grads=None, after_grads=None, dw_launcher=None):
+                 before_grads=None, after_grads=None, dw_launcher=None, active=None):
         """G_last = dL/dZ_last (N,64).  Writes (accumulate=False) or adds (True) every parameter gradient:
         embedding grads into dU/dI, attention grads through the pointer tables gtabs[k].
         before_grads(k)/after_grads(k) bracket the only kernels that touch the shared gradient buffers (stage k's
         transform_bwd), so two propagations can run their backward passes on two streams.
         dw_launcher(k, fn): split mode -- only dX stays on this chain; fn (the dW/da kernel of stage k, needed by the optimizer
-        only) is handed to the caller, which runs it on another stream once this stream reached the current point."""
+        only) is handed to the caller, which runs it on another stream once this stream reached the current point.
+        active (ops.ActiveRows): G_last is defined on the marked rows only and is zero elsewhere (forward ran with the same
+        `active`): the last stage's backward is the pruned pass."""
         g = self.g
         b = self._bwd_buffers()
         G = G_last
-        for k in range(len(self.stages) - 1, -1, -1):
+        last = len(self.stages) - 1
+        for k in range(last, -1, -1):
             H, _ = self.stages[k]
-            ops.stage_bwd_prep(G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"])
-            if k == len(self.stages) - 1 and after_first_kernel is not None:
+            pruned = active is not None and k == last
+            if pruned:
+                ops.stage_bwd_prep_active(g, G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"], active)
+            else:
+                ops.stage_bwd_prep(G, self.Z[k], self.h[k], self.norm[k], H, b["Ghat"], b["dN"])
+            if k == last and after_first_kernel is not None:
                 after_first_kernel()
             dh, dS = (b["dh_k"][k], b["dS_k"][k]) if dw_launcher is not None else (b["dh"], b["dS"])
             for mode in (0, 1):
-                ops.stage_bwd_edges(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
-                                    self.edgemask[k], self.scale, wtabs[k], b["ds"], dh, dS)
+                if pruned:
+                    ops.stage_bwd_edges_active(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
+                                               self.edgemask[k], self.scale, wtabs[k], b["ds"], dh, dS, active)
+                else:
+                    ops.stage_bwd_edges(mode, g, self.scratch, self.counter, G, b["Ghat"], b["dN"], self.h[k], self.s[k], H,
+                                        self.edgemask[k], self.scale, wtabs[k], b["ds"], dh, dS)
             if dw_launcher is not None:
                 Xu, Xi, act = (self.Z[k - 1], self.Z[k - 1][g.U:], 1) if k > 0 else (uEmbd, iEmbd, 0)
                 dw_launcher(k, lambda k=k, H=H, dh=dh, dS=dS, Xu=Xu, Xi=Xi, act=act: ops.transform_bwd_dw(

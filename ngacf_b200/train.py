@@ -45,6 +45,14 @@ class FusedTrainer:
         self.props = [Propagation(graph, model.stages), Propagation(graph, model.stages)]      # pos / neg
         for p in self.props:
             p._bwd_buffers()
+        # The loss reads the last stage's output at the batch rows only (SPUIGACF.py:49-52): that stage's aggregation and its
+        # backward are computed for the rows / edges that matter (exact -- everything skipped is a zero).  NGACF_PRUNE=0
+        # (or prune_last_stage=False) runs the full last stage, for A/B measurements and the parity tests of both paths.
+        self.prune_last_stage = os.environ.get("NGACF_PRUNE", "1") != "0" and self.props[0].can_prune()
+        self.active = [ops.ActiveRows(graph) for _ in self.props] if self.prune_last_stage else [None, None]
+        if inter.host["pool"].shape[0] - int(torch.diff(inter.train_ptr).max().item() if inter.train_ptr.numel() > 1 else 0) < 1:
+            # the reference's random.sample(negative_items, 1) raises for such a user (loadGowalla.py:76)
+            raise ValueError("a user's train items cover the whole item pool: no negative to sample")
         i64 = dict(dtype=torch.int64, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         self.users = torch.zeros(self.B, **i64)
@@ -75,9 +83,7 @@ class FusedTrainer:
         self.wtabs = [ops.pointer_table([p.detach() for p in st]) for st in stage_params]
         self.gtabs = [ops.pointer_table([p.grad for p in st]) for st in stage_params]
         # Adam state lives in the optimizer (torch.optim.Adam's keys), so checkpoints stay interchangeable
-        group = self.optim.param_groups[0]
-        self.hyper = dict(lr=float(group["lr"]), b1=float(group["betas"][0]), b2=float(group["betas"][1]), eps=float(group["eps"]),
-                          wd=float(group["weight_decay"]))
+        self.hyper = self._read_hyper()
         rows, step0 = [], 0
         for p in self.params:
             st = self.optim.state[p]
@@ -91,6 +97,11 @@ class FusedTrainer:
         self.adam_total = sum(p.numel() for p in self.params)
         self.adam_state = torch.tensor([float(step0), 0.0, 0.0, 0.0], dtype=torch.float64, device=self.dev)
         self._ptr_key = tuple(tuple(r[:4]) for r in rows)
+
+    def _read_hyper(self):
+        group = self.optim.param_groups[0]
+        return dict(lr=float(group["lr"]), b1=float(group["betas"][0]), b2=float(group["betas"][1]), eps=float(group["eps"]),
+                    wd=float(group["weight_decay"]))
 
     # hooks overridden by dist.ReplicaTrainer ------------------------------------------------------
     def _row_offset(self):
@@ -133,6 +144,12 @@ class FusedTrainer:
         if rows is None or tuple(tuple(r) for r in rows) != tuple(tuple(r) for r in self._ptr_key):
             self._setup_params()
             self._graph = None
+        hyper = self._read_hyper()
+        if hyper != self.hyper:
+            # lr / betas / eps / weight_decay are kernel arguments baked into the captured step: an LR scheduler (or a manual
+            # change of optim.param_groups between epochs) must invalidate the graph, not be ignored
+            self.hyper = hyper
+            self._graph = None
 
     def _step_body(self, b: int, epoch: int, droprate: float, seed: int, row0: int, call0: int, dev_counters: bool, part: str = "all"):
         m, g = self.model, self.g
@@ -144,6 +161,12 @@ class FusedTrainer:
         cur = torch.cuda.current_stream()
         items = (self.pos, self.neg)
         scores = (self.sc_pos, self.sc_neg)
+        # active rows of propagation k: stamped with its dropout call index (unique per propagation, so never cleared)
+        act = [self.active[k].at(call0 + k, cd) if self.prune_last_stage else None for k in (0, 1)]
+
+        def mark(k):
+            if act[k] is not None:
+                act[k].mark(self.users[:b], items[k][:b])
 
         side = self.side
 
@@ -152,7 +175,8 @@ class FusedTrainer:
                 self.props[k].use_dropout_buffers(droprate)
             else:
                 self.props[k].set_dropout(droprate, seed, call0 + k, None, cd)
-            Z = self.props[k].forward(uE, iE, self.wtabs, hook)
+            mark(k)
+            Z = self.props[k].forward(uE, iE, self.wtabs, hook, active=act[k])
             ops.score_pairs(Z, g.U, self.users[:b], items[k][:b], scores[k][:b])
         # captured steps find their dropout masks ready: they were generated at the end of the previous replay (or by
         # _prime_masks before the first one), next to Adam instead of at the head of the critical path
@@ -175,11 +199,13 @@ class FusedTrainer:
                 self.props[0].set_dropout(droprate, seed, call0, None, cd)
             if not self.stagger:
                 ev.record(cur)
-            Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side if self.stagger else None)
+            mark(0)
+            Z0 = self.props[0].forward(uE, iE, self.wtabs, start_side if self.stagger else None, active=act[0])
             ops.score_pairs(Z0, g.U, self.users[:b], items[0][:b], scores[0][:b])
             with torch.cuda.stream(side):
                 side.wait_event(ev)
-                Z1 = self.props[1].forward(uE, iE, self.wtabs)
+                mark(1)
+                Z1 = self.props[1].forward(uE, iE, self.wtabs, active=act[1])
                 ops.score_pairs(Z1, g.U, self.users[:b], items[1][:b], scores[1][:b])
             cur.wait_stream(side)
         else:
@@ -190,7 +216,8 @@ class FusedTrainer:
 
         def scatter(k):
             G = self.props[k].grad_in()
-            G.zero_()
+            if act[k] is None:
+                G.zero_()          # pruned: the scatter writes exactly the active rows, nothing else of G is read
             ops.score_pairs_bwd(self.props[k].Z[-1], g.U, self.users[:b], items[k][:b], dsc[k][:b], G)
         dU, dI = m.uEmbd.weight.grad, m.iEmbd.weight.grad
         if side is not None:
@@ -221,19 +248,19 @@ class FusedTrainer:
                 ev_go.record(cur)
             self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False,
                                    after_first_kernel=(lambda: ev_go.record(cur)) if self.stagger else None, after_grads=lambda k: evs[k].record(cur),
-                                   dw_launcher=defer(cur) if split else None)
+                                   dw_launcher=defer(cur) if split else None, active=act[0])
             with torch.cuda.stream(side):
                 side.wait_event(ev_go)
                 self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, True,
-                                       before_grads=lambda k: side.wait_event(evs[k]), dw_launcher=defer(side) if split else None)
+                                       before_grads=lambda k: side.wait_event(evs[k]), dw_launcher=defer(side) if split else None, active=act[1])
             cur.wait_stream(side)
             cur.wait_stream(gs)
         else:
             scatter(0)
             scatter(1)
             inline = (lambda k, fn: fn()) if self.split_dense_backward else None
-            self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False, dw_launcher=inline)
-            self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, True, dw_launcher=inline)
+            self.props[0].backward(self.props[0].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, False, dw_launcher=inline, active=act[0])
+            self.props[1].backward(self.props[1].grad_in(), uE, iE, self.wtabs, self.gtabs, dU, dI, True, dw_launcher=inline, active=act[1])
         if part == "compute":
             return
         self._reduce_grads()
@@ -252,9 +279,9 @@ class FusedTrainer:
                 ops.counter_add(self.call_dev, self.CALLS_PER_STEP)
                 self._generate_masks(*margs)
         ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
-        self.total.add_(self.loss.double())
+        # epoch loss accumulator + train-row cursor in one launch of ours (no eager-torch kernels inside the captured step)
+        ops.step_counters(self.total, self.loss, self.row_dev if dev_counters else None, self._row_stride())
         if dev_counters:
-            ops.counter_add(self.row_dev, self._row_stride())
             if margs is None:
                 ops.counter_add(self.call_dev, self.CALLS_PER_STEP)
             elif mask_stream is None:
@@ -279,7 +306,8 @@ class FusedTrainer:
         S = len(self.props[0].stages)
         per_prop_fwd = (1 if droprate > 0 else 0) + 2 * S + 1              # masks (one launch), transform+aggregate, score
         per_prop_bwd = 1 + S * (1 + 2 + (4 if self.split_dense_backward else 2))   # scatter, prep + 2 edge passes + dense backward
-        return 1 + 2 * (per_prop_fwd + per_prop_bwd) + 1 + 2 + 2             # sampler, ..., loss, adam(2), counters(2)
+        marks = 6 if self.prune_last_stage else 0                           # mark_active + plan (2 kernels) per propagation
+        return 1 + marks + 2 * (per_prop_fwd + per_prop_bwd) + 1 + 2 + 2     # sampler, ..., loss, adam(2), counters(2)
 
     def train_epoch(self, epoch: int = 0, max_steps=None) -> float:
         """Returns sum(batch-mean loss)/len(train_df) (train_eval_Gowalla.py:139,144)."""
@@ -427,12 +455,15 @@ class FusedTrainer:
         opt_snap = [(self.optim.state[p]["exp_avg"].clone(), self.optim.state[p]["exp_avg_sq"].clone()) for p in self.params]
         adam_snap, total_snap = self.adam_state.clone(), self.total.clone()
         side, self.side = self.side, None
-        self._step_body(self.B, 0, droprate, m._seed(), 0, 0, False)     # warm
+        # batches from the middle of the train rows: the first rows belong to the heaviest users (one user can fill a whole
+        # batch there), which is not what a typical step looks like
+        row0 = max(0, (len(self.inter) // 2 // self.B) * self.B - n_steps * self.B)
+        self._step_body(self.B, 0, droprate, m._seed(), row0, 0, False)     # warm
         torch.cuda.synchronize(self.dev)
         _lib.PROFILE = []
         try:
             for k in range(n_steps):
-                self._step_body(self.B, 0, droprate, self._dropout_seed(m._seed()), k * self.B, self.CALLS_PER_STEP * k, False)
+                self._step_body(self.B, 0, droprate, self._dropout_seed(m._seed()), row0 + (k + 1) * self.B, self.CALLS_PER_STEP * (k + 1), False)
             torch.cuda.synchronize(self.dev)
             out = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in _lib.PROFILE]
         finally:

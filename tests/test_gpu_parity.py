@@ -664,3 +664,87 @@ def test_score_pairs_bwd_accumulates_over_calls():
         sl = slice(j * 500, (j + 1) * 500)
         ops.score_pairs_bwd(Z, U, users[sl], items[sl], d[sl], G2, accumulate=j > 0)
     assert rel_err(G2.cpu().numpy(), G1.cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# pruned last stage (round 2): the fused trainer computes the output stage for the batch rows only
+# ------------------------------------------------------------------------------------------------
+def _fused_trainer(U, I, u, i, tu, ti, su, si, sd, droprate, batch, prune, monkeypatch):
+    from ngacf_b200.data import Interactions
+    from ngacf_b200.model import SPUIGACF
+    from ngacf_b200.optim import FusedAdam
+    from ngacf_b200.train import FusedTrainer
+    monkeypatch.setenv("NGACF_PRUNE", "1" if prune else "0")
+    model = SPUIGACF(U, I, 64, [64, 64], droprate)
+    model.load_state_dict(sd)
+    model = model.to(DEV).train()
+    model.drop_seed, model._call = 77, 0
+    dit = Interactions.from_arrays(U, I, tu, ti, su, si, device=DEV)
+    g = model.graph_for(torch.from_numpy(np.stack([u, i])).to(DEV))
+    optim = FusedAdam(model.parameters(), lr=0.01, weight_decay=1e-6)
+    tr = FusedTrainer(model, dit, g, batch, optim, sample_seed=5)
+    assert tr.prune_last_stage == prune
+    return model, tr
+
+
+@pytest.mark.parametrize("droprate", [0.0, 0.2])
+@pytest.mark.parametrize("U,I,E,batch", [(300, 500, 6000, 256), (3000, 5000, 200000, 2048)])
+def test_pruned_last_stage_equals_full(U, I, E, batch, droprate, monkeypatch):
+    """The default trainer skips every last-stage row / edge whose contribution to the step is an exact zero (ngacf_*_active).
+    Against the same trainer running the full last stage (NGACF_PRUNE=0): identical losses and parameters after captured AND
+    eager steps, up to the order in which the surviving terms are added (bound 2e-6 relative; long rows, heavy users in the
+    batch and repeated users are all present at the larger size)."""
+    from ngacf_b200 import hostdata
+    from ngacf_b200.model import SPUIGACF
+    u, i = hostdata.synth_bipartite(U, I, E, 3)
+    (tu, ti), (su, si) = hostdata.split_per_user(u, i, U, 1)
+    torch.manual_seed(11)
+    ref = SPUIGACF(U, I, 64, [64, 64], droprate)
+    with torch.no_grad():
+        ref.uEmbd.weight.mul_(10.0)
+        ref.iEmbd.weight.mul_(10.0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    out = {}
+    for prune in (True, False):
+        model, tr = _fused_trainer(U, I, u, i, tu, ti, su, si, sd, droprate, batch, prune, monkeypatch)
+        # (1) one step without the optimizer: loss and EVERY gradient, batches from the head (heavy users) and the middle of the rows
+        grads = []
+        for row0 in (0, (len(tu) // 2 // batch) * batch):
+            tr._step_body(batch, 0, droprate, model._seed(), row0, 40 + row0 % 7, False, part="compute")
+            grads.append([float(tr.loss.item())] + [p.grad.detach().cpu().numpy().copy() for p in tr.params])
+        # (2) captured and eager steps with Adam
+        losses = tr.run_steps(4, read_loss=True)                       # captured graph, device-resident counters
+        ep = tr.train_epoch(epoch=1, max_steps=3)                       # captured steps again + bookkeeping
+        tr.use_cuda_graph = False
+        ep2 = tr.train_epoch(epoch=2, max_steps=2)                      # eager path (host-side counters)
+        out[prune] = (grads, np.array(losses + [ep, ep2]), {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()})
+    for ga, gb in zip(out[True][0], out[False][0]):
+        assert abs(ga[0] - gb[0]) <= 1e-6 * abs(gb[0])
+        for x, y in zip(ga[1:], gb[1:]):
+            assert rel_err(x, y) < 1e-5
+    assert np.isfinite(out[True][1]).all()
+    assert rel_err(out[True][1], out[False][1]) < 1e-4
+    for k in out[True][2]:      # nine Adam steps amplify last-bit gradient differences (update = lr * m / (sqrt(v) + eps), |g| ~ eps rows)
+        assert rel_err(out[True][2][k], out[False][2][k]) < 5e-3, k
+
+
+def test_optimizer_hyperparameters_follow_param_groups(monkeypatch):
+    """lr / weight_decay are arguments baked into the captured step: changing optim.param_groups between epochs (an LR
+    scheduler) must re-capture, not be ignored (round-1 advisor finding)."""
+    from ngacf_b200 import hostdata
+    from ngacf_b200.model import SPUIGACF
+    U, I, E = 300, 500, 6000
+    u, i = hostdata.synth_bipartite(U, I, E, 3)
+    (tu, ti), (su, si) = hostdata.split_per_user(u, i, U, 1)
+    torch.manual_seed(11)
+    sd = {k: v.clone() for k, v in SPUIGACF(U, I, 64, [64, 64], 0.0).state_dict().items()}
+    res = []
+    for change in (False, True):
+        model, tr = _fused_trainer(U, I, u, i, tu, ti, su, si, sd, 0.0, 256, True, monkeypatch)
+        tr.train_epoch(0, max_steps=2)
+        if change:
+            tr.optim.param_groups[0]["lr"] = 0.0          # frozen: nothing may move any more
+        before = model.uEmbd.weight.detach().clone()
+        tr.train_epoch(1, max_steps=2)
+        res.append(float((model.uEmbd.weight.detach() - before).abs().max()))
+    assert res[0] > 0 and res[1] == 0.0

@@ -17,7 +17,21 @@ from ngacf_b200 import ops
 from ngacf_b200.data import Interactions
 from ngacf_b200.evaluate import AllNegEvaluator
 
-_INTER_CACHE = {}
+_INTER_CACHE = {}          # key -> (source objects, Interactions); the sources are kept alive so an id() can never be recycled
+_INTER_CACHE_MAX = 8
+
+
+def _cached_interactions(key, sources, build):
+    """id()-keyed cache that (a) holds the source objects, so a garbage-collected frame cannot hand its id to a new one,
+    (b) re-checks identity on every hit and (c) is bounded (oldest entry evicted; its device arrays are freed with it)."""
+    hit = _INTER_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], sources)):
+        return hit[1]
+    while len(_INTER_CACHE) >= _INTER_CACHE_MAX:
+        _INTER_CACHE.pop(next(iter(_INTER_CACHE)))
+    inter = build()
+    _INTER_CACHE[key] = (tuple(sources), inter)
+    return inter
 
 
 def _unwrap(model):
@@ -29,12 +43,10 @@ def _interactions(model, train_df, pos_neg, test_df=None):
     for cand in (train_df, pos_neg, test_df):
         if isinstance(cand, Interactions):
             return cand
-    key = (id(train_df), id(pos_neg), id(test_df))
-    if key not in _INTER_CACHE:
-        m = _unwrap(model)
-        _INTER_CACHE[key] = Interactions.from_reference_frames(m.userNum, m.itemNum, train_df, pos_neg, test_df,
-                                                               device=m.uEmbd.weight.device)
-    return _INTER_CACHE[key]
+    m = _unwrap(model)
+    return _cached_interactions((id(train_df), id(pos_neg), id(test_df)), (train_df, pos_neg, test_df),
+                                lambda: Interactions.from_reference_frames(m.userNum, m.itemNum, train_df, pos_neg, test_df,
+                                                                           device=m.uEmbd.weight.device))
 
 
 def _device_adj(model, adj):
@@ -146,11 +158,10 @@ def _neg_interactions(model, pos_neg, train_df=None, test_df=None):
     for cand in (train_df, pos_neg, test_df):
         if isinstance(cand, Interactions):
             return cand
-    key = ("neg", id(pos_neg), id(train_df), id(test_df))
-    if key not in _INTER_CACHE:
-        m = _unwrap(model)
-        _INTER_CACHE[key] = Interactions.from_negsampling_frames(m.userNum, m.itemNum, pos_neg, train_df, test_df, device=m.uEmbd.weight.device)
-    return _INTER_CACHE[key]
+    m = _unwrap(model)
+    return _cached_interactions(("neg", id(pos_neg), id(train_df), id(test_df)), (pos_neg, train_df, test_df),
+                                lambda: Interactions.from_negsampling_frames(m.userNum, m.itemNum, pos_neg, train_df, test_df,
+                                                                             device=m.uEmbd.weight.device))
 
 
 def train_neg_sample(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is_parallel, epoch=0, sample_seed=None, fused=None,
