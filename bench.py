@@ -307,7 +307,7 @@ def main():
         prof = [("ngacf_aggregate_fwd", tuple([None] * 10 + [8]), ms_step)]
     hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10,
            "ngacf_transform_bwd_dx": 7, "ngacf_transform_bwd_dw": 9, "ngacf_aggregate_fwd_active": 12, "ngacf_stage_bwd_prep_active": 8,
-           "ngacf_stage_bwd_edges_active": 15}
+           "ngacf_stage_bwd_edges_active": 17}
     agg = {}
     for name, args_, ms in prof:
         key = name

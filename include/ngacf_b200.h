@@ -128,18 +128,19 @@ int ngacf_score_pairs_bwd(const float* Z, int32_t U, const int64_t* users, const
  * order of additions (everything skipped is an exact zero).
  *   mark_active : stamp[users[b]] = stamp[U+items[b]] = val (+ *val_dev); a node is active for a propagation iff its stamp
  *                 equals that propagation's value (the trainer uses the dropout call index: no clearing is ever needed).
- *                 task_count (may be NULL) is reset to 0 for the plan call that follows.
- *   active_plan : task_list/task_count = compacted list of the tasks (ngacf_graph_build) whose row is active;
+ *                 task_count (int32[2], may be NULL) is reset to 0 for the plan call that follows.
+ *   active_plan : task_list int32[T] / task_count int32[2] = the tasks (ngacf_graph_build) whose row is active: user tasks from the
+ *                 front of the list (count[0]), item tasks from its back (count[1]: list[T-1], list[T-2], ...);
  *                 edge_bits uint32[(n_adj+31)/32]: bit p = neighbour adj_idx[p] is active (n_adj = 2E positions).
  *   aggregate_fwd_active     : ngacf_aggregate_fwd over the listed tasks only (Z/norm of every other row keep stale data).
  *   stage_bwd_prep_active    : Ghat/dN of the listed rows only (H = 1).
  *   stage_bwd_edges_active   : the pruned pair of edge passes (H = 1): mode 0 = user rows (stores (d s_e, e*keep) of the
- *                 visited edges), mode 1 = item rows.  G / Ghat / dN are read at active rows only; dh / dS are written for
+ *                 visited edges; the rows of ACTIVE users are walked by one CTA per listed task), mode 1 = item rows.  G / Ghat / dN are read at active rows only; dh / dS are written for
  *                 every row of the side.
  * ------------------------------------------------------------------------------------------- */
 int ngacf_mark_active(int32_t* stamp, const int64_t* users, const int64_t* items, int32_t B, int32_t U, int32_t val,
                       const int64_t* val_dev, int32_t* task_count, void* stream);
-int ngacf_active_plan(const int32_t* stamp, int32_t val, const int64_t* val_dev, const int32_t* tasks, int32_t T,
+int ngacf_active_plan(const int32_t* stamp, int32_t val, const int64_t* val_dev, const int32_t* tasks, int32_t T, int32_t T_users,
                       const int32_t* adj_idx, int64_t n_adj, int32_t* task_list, int32_t* task_count, uint32_t* edge_bits,
                       void* stream);
 int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
@@ -150,7 +151,8 @@ int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const int32_t* t
 int ngacf_stage_bwd_prep_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
                                 const float* G, const float* Z, const float* h, const float* norm, int32_t H,
                                 float* Ghat, float* dN, void* stream);
-int ngacf_stage_bwd_edges_active(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end, const int32_t* adj_ptr,
+int ngacf_stage_bwd_edges_active(int32_t mode, const int32_t* tasks, int32_t T_begin, int32_t T_end,
+                                 const int32_t* task_list, const int32_t* task_count, const int32_t* adj_ptr,
                                  const int32_t* adj_idx, const int32_t* adj_eid,
                                  const int32_t* long_first_slot, int32_t* long_counter, float* scratch,
                                  const float* G, const float* Ghat, const float* dN, const float* h, const float* s, int32_t H,

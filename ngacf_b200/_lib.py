@@ -26,10 +26,10 @@ SIGNATURES = {
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_step_counters": (c_int32, [P, P, P, c_int64, P]),
     "ngacf_mark_active": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P, P]),
-    "ngacf_active_plan": (c_int32, [P, c_int32, P, P, c_int32, P, c_int64, P, P, P, P]),
+    "ngacf_active_plan": (c_int32, [P, c_int32, P, P, c_int32, c_int32, P, c_int64, P, P, P, P]),
     "ngacf_aggregate_fwd_active": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, P]),
     "ngacf_stage_bwd_prep_active": (c_int32, [P, c_int32, P, P, P, P, P, P, c_int32, P, P, P]),
-    "ngacf_stage_bwd_edges_active": (c_int32, [c_int32, P, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, c_int32, P, c_float, P,
+    "ngacf_stage_bwd_edges_active": (c_int32, [c_int32, P, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int32, P, c_float, P,
                                                c_int32, P, c_int32, P, P, P, P, P, P]),
     "ngacf_transform_fwd": (c_int32, [P, P, c_int32, P, c_float, P, c_int32, c_int32, c_int32, P, P, P]),
     "ngacf_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, P, P, c_int32, P]),

@@ -162,6 +162,11 @@ __device__ __forceinline__ float head_reduce(float v, unsigned mask) {
 // its slot, and the group that arrives LAST sums the slots in slot order (deterministic, no atomics on data) and continues with
 // the totals.  Returns false for every other group.  The counter is re-armed for the next launch by the last arriver.
 // ---------------------------------------------------------------------------------------------
+// release / acquire fence of the partial-sum hand-over (message passing: data stores -> fence -> counter atomic on the writer,
+// counter atomic -> fence -> data loads (ld.cg) on the reader).  __threadfence() is the sequentially consistent fence
+// (MEMBAR.SC.GPU + L1 invalidate), which this pattern does not need.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // FAST: eight slots in flight (32 more registers) -- for the kernels that run few rows, where this sum is the critical path; the
 // throughput-bound full-graph kernels keep the plain loop (the extra registers cost them a resident CTA per SM: measured
 // +8..18 % on the stage-0 kernels), their long rows are scheduled first and the sum hides behind the rest of the grid.
@@ -178,13 +183,13 @@ __device__ __forceinline__ bool long_row_combine(int lid, int chunk, const int* 
 #pragma unroll
         for (int j = 0; j < NSUM; ++j) slot[D + j * H + head] = sums[j];
     }
-    __threadfence();
+    fence_acq_rel_gpu();
     __syncwarp(gm);                          // every lane's partial is fenced before lane 0 publishes
     int old = 0;
     if (lane16 == 0) old = atomicAdd(long_counter + lid, 1);
     old = __shfl_sync(gm, old, 0, 16);
     if (old != nslots - 1) return false;
-    __threadfence();
+    fence_acq_rel_gpu();
     if constexpr (!FAST) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         float ts[NSUM];

@@ -365,17 +365,18 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const int4* __restri
 // step reads nothing else of the last stage's output (the pair scores gather the batch rows, every other row has a zero
 // gradient).  Persistent grid over the compacted list: the working groups are dense however few rows are active.
 template <int H, bool DROP>
-__global__ void __launch_bounds__(256) aggregate_fwd_list_kernel(const int4* __restrict__ tasks, const int* __restrict__ task_list,
+__global__ void __launch_bounds__(256) aggregate_fwd_list_kernel(const int4* __restrict__ tasks, int T, const int* __restrict__ task_list,
                                                                  const int* __restrict__ task_count, const int* __restrict__ adj_ptr,
                                                                  const int* __restrict__ adj_idx, const int* __restrict__ adj_eid,
                                                                  const int* __restrict__ long_first_slot, int* long_counter, float* scratch,
                                                                  const float* __restrict__ h, const float* __restrict__ s,
                                                                  const uint8_t* __restrict__ edgemask, float scale,
                                                                  float* __restrict__ Z, float* __restrict__ norm) {
-    const int n = __ldg(task_count);
+    // two lists in one buffer (ngacf_active_plan): user tasks from the front, item tasks from the back
+    const int nu = __ldg(task_count), n = nu + __ldg(task_count + 1);
     const int stride = (gridDim.x * blockDim.x) >> 4;
     for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; g < n; g += stride)
-        aggregate_task<H, DROP, false, true>(__ldg(task_list + g), tasks, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s,
+        aggregate_task<H, DROP, false, true>(__ldg(task_list + (g < nu ? g : T - 1 - (g - nu))), tasks, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s,
                                        edgemask, scale, Z, norm, 0x7fffffff);
 }
 
@@ -495,6 +496,11 @@ extern "C" int ngacf_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_
     return check_launch("aggregate_fwd");
 }
 
+int ngacf_launch_aggregate_fwd_cta(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count, const int32_t* adj_ptr,
+                                   const int32_t* adj_idx, const int32_t* adj_eid, const int32_t* long_first_slot, int32_t* long_counter,
+                                   float* scratch, const float* h, const float* s, const uint8_t* edgemask, float scale, float* Z, float* norm,
+                                   cudaStream_t st);      // csrc/pruned_stage.cu
+
 extern "C" int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const int32_t* task_list, const int32_t* task_count,
                                           const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
                                           const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* h,
@@ -503,11 +509,14 @@ extern "C" int ngacf_aggregate_fwd_active(const int32_t* tasks, int32_t T, const
     NGACF_REQUIRE(tasks && task_list && task_count && adj_ptr && adj_idx && h && s && Z && norm && T > 0, "aggregate_fwd_active: null/empty argument");
     NGACF_REQUIRE(H == 1 || H == 8, "aggregate_fwd_active: H must be 1 or 8 (got %d)", H);
     NGACF_REQUIRE(!edgemask || adj_eid, "aggregate_fwd_active: edge dropout needs adj_eid");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 1)
+        return ngacf_launch_aggregate_fwd_cta(tasks, T, task_list, task_count, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h,
+                                              s, edgemask, scale, Z, norm, st);
     int blocks = ceil_div((int64_t)T * 16, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;              // persistent: the list length lives on the device
-    cudaStream_t st = (cudaStream_t)stream;
     const int4* tk = reinterpret_cast<const int4*>(tasks);
-#define LAUNCH(HH, DR) aggregate_fwd_list_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, task_list, task_count, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
+#define LAUNCH(HH, DR) aggregate_fwd_list_kernel<HH, DR><<<blocks, 256, 0, st>>>(tk, T, task_list, task_count, adj_ptr, adj_idx, adj_eid, long_first_slot, long_counter, scratch, h, s, edgemask, scale, Z, norm)
     if (H == 8) { if (edgemask) LAUNCH(8, true); else LAUNCH(8, false); }
     else        { if (edgemask) LAUNCH(1, true); else LAUNCH(1, false); }
 #undef LAUNCH

@@ -75,7 +75,7 @@ class ActiveRows:
         self.g = g
         self.stamp = torch.full((g.N,), -1, dtype=torch.int32, device=dev)
         self.task_list = torch.empty(max(g.T, 1), dtype=torch.int32, device=dev)
-        self.task_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.task_count = torch.zeros(2, dtype=torch.int32, device=dev)      # {user tasks, item tasks}
         self.edge_bits = torch.zeros((2 * g.E + 31) // 32 + 1, dtype=torch.int32, device=dev)
         self.val, self.val_dev = int(val), val_dev
 
@@ -88,7 +88,7 @@ class ActiveRows:
         g = self.g
         _lib.call("ngacf_mark_active", _p(self.stamp), _p(users), _p(items), users.numel(), g.U, self.val, _p(self.val_dev),
                   _p(self.task_count), _s())
-        _lib.call("ngacf_active_plan", _p(self.stamp), self.val, _p(self.val_dev), _p(g.tasks), g.T, _p(g.adj_idx), 2 * g.E,
+        _lib.call("ngacf_active_plan", _p(self.stamp), self.val, _p(self.val_dev), _p(g.tasks), g.T, g.T_users, _p(g.adj_idx), 2 * g.E,
                   _p(self.task_list), _p(self.task_count), _p(self.edge_bits), _s())
 
 
@@ -105,7 +105,7 @@ def stage_bwd_prep_active(g: BipartiteGraph, G, Z, h, norm, H, Ghat, dN, act: Ac
 
 def stage_bwd_edges_active(mode, g: BipartiteGraph, scratch, counter, G, Ghat, dN, h, s, H, edgemask, scale, wtab, ds_store, dh, dS, act: ActiveRows):
     t0, t1 = (0, g.T_users) if mode == 0 else (g.T_users, g.T)
-    _lib.call("ngacf_stage_bwd_edges_active", mode, _p(g.tasks), t0, t1, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid),
+    _lib.call("ngacf_stage_bwd_edges_active", mode, _p(g.tasks), t0, t1, _p(act.task_list), _p(act.task_count), _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid),
               _p(g.long_first_slot), _p(counter), _p(scratch), _p(G), _p(Ghat), _p(dN), _p(h), _p(s), H, _p(edgemask),
               float(scale), _p(wtab), g.U, _p(act.stamp), act.val, _p(act.val_dev), _p(act.edge_bits), _p(ds_store), _p(dh), _p(dS), _s())
 

@@ -306,7 +306,7 @@ class FusedTrainer:
         S = len(self.props[0].stages)
         per_prop_fwd = (1 if droprate > 0 else 0) + 2 * S + 1              # masks (one launch), transform+aggregate, score
         per_prop_bwd = 1 + S * (1 + 2 + (4 if self.split_dense_backward else 2))   # scatter, prep + 2 edge passes + dense backward
-        marks = 6 if self.prune_last_stage else 0                           # mark_active + plan (2 kernels) per propagation
+        marks = 6 if self.prune_last_stage else 0                           # mark_active + plan + active-user rows kernel per propagation
         return 1 + marks + 2 * (per_prop_fwd + per_prop_bwd) + 1 + 2 + 2     # sampler, ..., loss, adam(2), counters(2)
 
     def train_epoch(self, epoch: int = 0, max_steps=None) -> float:

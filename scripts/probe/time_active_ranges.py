@@ -31,7 +31,7 @@ act = tr.active[0]
 b = p._bwd
 k = len(p.stages) - 1
 H = 1
-print("T", g.T, "T_users", g.T_users, "active tasks", int(act.task_count.item()))
+print("T", g.T, "T_users", g.T_users, "active tasks (users, items)", act.task_count.tolist())
 tasks = g.tasks.cpu().numpy()
 stamp = act.stamp.cpu().numpy()
 val = act.val
@@ -62,7 +62,7 @@ def timed(fn, reps=20):
 
 
 def users_range(t0, t1, mode=0):
-    _lib.call("ngacf_stage_bwd_edges_active", mode, ops._p(g.tasks), t0, t1, ops._p(g.adj_ptr), ops._p(g.adj_idx), ops._p(g.adj_eid),
+    _lib.call("ngacf_stage_bwd_edges_active", mode, ops._p(g.tasks), t0, t1, ops._p(act.task_list), ops._p(act.task_count), ops._p(g.adj_ptr), ops._p(g.adj_idx), ops._p(g.adj_eid),
               ops._p(g.long_first_slot), ops._p(p.counter), ops._p(p.scratch), ops._p(b["G"][0]), ops._p(b["Ghat"]), ops._p(b["dN"]), ops._p(p.h[k]),
               ops._p(p.s[k]), H, ops._p(p.edgemask[k]), float(p.scale), ops._p(tr.wtabs[k]), g.U, ops._p(act.stamp), act.val, ops._p(act.val_dev),
               ops._p(act.edge_bits), ops._p(b["ds"]), ops._p(b["dh"]), ops._p(b["dS"]), ops._s())
@@ -87,3 +87,4 @@ us = timed(lambda: act.mark(tr.users, tr.pos))
 print("mark + plan: %.1f us" % us)
 us = timed(lambda: ops.stage_bwd_prep_active(g, b["G"][0], p.Z[k], p.h[k], p.norm[k], H, b["Ghat"], b["dN"], act))
 print("prep_active: %.1f us" % us)
+
