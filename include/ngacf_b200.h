@@ -72,6 +72,11 @@ int ngacf_edge_mask(uint8_t* edge, int64_t E, int32_t H, uint64_t seed, uint32_t
  * stage k uses Philox sites 2k / 2k+1 -- identical bits to S pairs of the two calls above. */
 int ngacf_dropout_masks(uint64_t* const* feat, uint8_t* const* edge, const int32_t* heads, int32_t S, int64_t N, int64_t E,
                         uint64_t seed, uint32_t call, const int64_t* call_dev, float droprate, void* stream);
+/* the same streams restricted to the node ranges [fa0,fb0) and [fa1,fb1) and the edge range [e0,e1), written at their global
+ * positions (multi-GPU user sharding: a rank needs the masks of the rows it transforms and of the edges it owns only) */
+int ngacf_dropout_masks_ranges(uint64_t* const* feat, uint8_t* const* edge, const int32_t* heads, int32_t S, int64_t fa0, int64_t fb0,
+                               int64_t fa1, int64_t fb1, int64_t e0, int64_t e1, uint64_t seed, uint32_t call, const int64_t* call_dev,
+                               float droprate, void* stream);
 /* call_dev (may be NULL): device-resident int64 added to `call` at run time; likewise ngacf_sample_pairs'
  * row_dev = int64[2] {added to row_begin, added to epoch}.  A CUDA graph captured once then replays with
  * advancing dropout streams, train rows and epochs. */
@@ -162,6 +167,15 @@ int ngacf_stage_bwd_edges_active(int32_t mode, const int32_t* tasks, int32_t T_b
 /* end-of-step bookkeeping of a captured step (train_eval_Gowalla.py:139 `total_loss += loss`, :111-115 row cursor):
  * *total += *loss (either may be NULL together), row_dev[0] += row_stride (row_dev may be NULL) */
 int ngacf_step_counters(double* total, const float* loss, int64_t* row_dev, int64_t row_stride, void* stream);
+
+/* Multi-GPU pair scoring (users range-partitioned, item rows owned by range; replaces the thread-per-GPU scatter/gather of
+ * parallel.py:94-130,165-196): gather writes the batch's rows this rank owns (zeros for the others) into the compact table
+ * Zb[2B][64] = {user rows | item rows}; after an all-reduce of Zb, scatter writes the rows back at their global positions of a
+ * table on which ngacf_score_pairs(_bwd) run unchanged.  memset_zero: cudaMemsetAsync behind the same ABI. */
+int ngacf_batch_rows_gather(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, int64_t u_lo, int64_t u_hi,
+                            int64_t i_lo, int64_t i_hi, float* Zb, void* stream);
+int ngacf_batch_rows_scatter(const float* Zb, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* Z, void* stream);
+int ngacf_memset_zero(void* p, size_t bytes, void* stream);
 
 /* F = ELU(Z) materialised for evaluation (SPUIGACF.py:214) */
 int ngacf_final_features(const float* Z, int64_t N, float* F, void* stream);

@@ -23,6 +23,10 @@ SIGNATURES = {
     "ngacf_sample_negs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, c_int32, c_uint32, c_int64, P, P, P]),
     "ngacf_bce_logits_loss": (c_int32, [P, c_int64, c_int32, P, P, P]),
     "ngacf_rank_metrics": (c_int32, [P, c_int64, c_int32, c_int32, P, P]),
+    "ngacf_dropout_masks_ranges": (c_int32, [P, P, P, c_int32, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_uint64, c_uint32, P, c_float, P]),
+    "ngacf_batch_rows_gather": (c_int32, [P, c_int32, P, P, c_int32, c_int64, c_int64, c_int64, c_int64, P, P]),
+    "ngacf_batch_rows_scatter": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
+    "ngacf_memset_zero": (c_int32, [P, c_size_t, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_step_counters": (c_int32, [P, P, P, c_int64, P]),
     "ngacf_mark_active": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P, P]),

@@ -95,6 +95,43 @@ __global__ void __launch_bounds__(256) dropout_masks_kernel(MaskPlan plan, int64
     }
 }
 
+// the same streams restricted to two node ranges and one edge range, written at their GLOBAL positions (multi-GPU: a rank
+// only needs the masks of the rows it transforms and of the edges it owns)
+struct MaskRanges { int64_t fa0, fb0, fa1, fb1, e0, e1; int fb_blocks0, fb_blocks1, e_blocks; };
+
+__global__ void __launch_bounds__(256) dropout_masks_ranges_kernel(MaskPlan plan, MaskRanges r, uint32_t k0, uint32_t k1, uint32_t call,
+                                                                   const int64_t* __restrict__ call_dev, uint32_t thr) {
+    if (call_dev) call += (uint32_t)*call_dev;
+    int b = blockIdx.x;
+    const int per_stage = r.fb_blocks0 + r.fb_blocks1 + r.e_blocks;
+    const int site = b / per_stage;
+    b -= site * per_stage;
+    uint32_t w[4];
+    if (b < r.fb_blocks0 + r.fb_blocks1) {
+        const bool second = b >= r.fb_blocks0;
+        const int64_t t = (int64_t)(second ? b - r.fb_blocks0 : b) * 256 + threadIdx.x;
+        const int64_t n = (second ? r.fa1 : r.fa0) + (t >> 3);
+        const int64_t hi = second ? r.fb1 : r.fb0;
+        const int c = (int)(t & 7);
+        uint32_t bits = 0;
+        if (n < hi) {
+            const uint64_t idx = (uint64_t)n * 8u + (uint64_t)c;
+            philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)site * 2u, call, k0, k1, w);
+            bits = decisions8(w, thr);
+        }
+        uint64_t word = (uint64_t)bits << (8 * c);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if (n < hi && c == 0) plan.feat[site][n] = word;
+    } else {
+        const int64_t e = r.e0 + (int64_t)(b - r.fb_blocks0 - r.fb_blocks1) * 256 + threadIdx.x;
+        if (e >= r.e1) return;
+        philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)site * 2u + 1u, call, k0, k1, w);
+        plan.edge[site][e] = (uint8_t)(decisions8(w, thr) & ((1u << plan.heads[site]) - 1u));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense transform: h = Xd @ Wcat, s = per-head a . h
 // block = 256 threads, tile = 128 rows of one side; thread = 8 rows x 4 columns
@@ -443,6 +480,30 @@ extern "C" int ngacf_dropout_masks(uint64_t* const* feat, uint8_t* const* edge, 
     dropout_masks_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plan, N, E, (uint32_t)seed, (uint32_t)(seed >> 32), call,
                                                                              call_dev, keep_threshold(droprate));
     return check_launch("dropout_masks");
+}
+
+extern "C" int ngacf_dropout_masks_ranges(uint64_t* const* feat, uint8_t* const* edge, const int32_t* heads, int32_t S, int64_t fa0, int64_t fb0,
+                                          int64_t fa1, int64_t fb1, int64_t e0, int64_t e1, uint64_t seed, uint32_t call, const int64_t* call_dev,
+                                          float droprate, void* stream) {
+    NGACF_REQUIRE(feat && edge && heads && S >= 1 && S <= MASK_MAX_STAGES && fa0 >= 0 && fb0 >= fa0 && fa1 >= 0 && fb1 >= fa1 && e0 >= 0 && e1 >= e0,
+                  "dropout_masks_ranges: bad args");
+    MaskPlan plan;
+    for (int k = 0; k < S; ++k) {
+        NGACF_REQUIRE(feat[k] && (edge[k] || e1 == e0) && (heads[k] == 1 || heads[k] == 8), "dropout_masks_ranges: bad stage %d", k);
+        plan.feat[k] = feat[k]; plan.edge[k] = edge[k]; plan.heads[k] = heads[k];
+    }
+    plan.S = S;
+    plan.feat_blocks = plan.edge_blocks = 0;
+    MaskRanges r;
+    r.fa0 = fa0; r.fb0 = fb0; r.fa1 = fa1; r.fb1 = fb1; r.e0 = e0; r.e1 = e1;
+    r.fb_blocks0 = ceil_div((fb0 - fa0) * 8, 256);
+    r.fb_blocks1 = ceil_div((fb1 - fa1) * 8, 256);
+    r.e_blocks = ceil_div(e1 - e0, 256);
+    const int64_t blocks = (int64_t)S * (r.fb_blocks0 + r.fb_blocks1 + r.e_blocks);
+    if (blocks == 0) return NGACF_OK;
+    dropout_masks_ranges_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plan, r, (uint32_t)seed, (uint32_t)(seed >> 32), call, call_dev,
+                                                                                    keep_threshold(droprate));
+    return check_launch("dropout_masks_ranges");
 }
 
 extern "C" int ngacf_transform_fwd(const float* Xu, const float* Xi, int32_t apply_elu, const uint64_t* featmask, float scale,

@@ -269,6 +269,34 @@ __global__ void sample_pairs_kernel(const int* __restrict__ rows_user, const int
 
 __global__ void counter_add_kernel(int64_t* c, int64_t d) { *c += d; }
 
+// Multi-GPU pair scoring: the rows of the batch live on their owners.  gather: Zb[b] = Z[users[b]] / Zb[B+b] = Z[U+items[b]] if this
+// rank owns the row (users [u_lo,u_hi), items [i_lo,i_hi)), zeros otherwise -- summing Zb over the ranks (one all-reduce) yields
+// every batch row exactly (a row has one owner).  scatter: the summed rows are written back into a table at their global positions
+// so that ngacf_score_pairs(_bwd) run unchanged on every rank.
+__global__ void __launch_bounds__(256) batch_rows_gather_kernel(const float* __restrict__ Z, int U, const int64_t* __restrict__ users,
+                                                                const int64_t* __restrict__ items, int B, int64_t u_lo, int64_t u_hi,
+                                                                int64_t i_lo, int64_t i_hi, float* __restrict__ Zb) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (e >= 2 * B) return;
+    const int lane16 = threadIdx.x & 15;
+    const bool user_row = e < B;
+    const int64_t id = user_row ? users[e] : items[e - B];
+    const bool own = user_row ? (id >= u_lo && id < u_hi) : (id >= i_lo && id < i_hi);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (own) v = ld_gather4(Z + (user_row ? id : id + U) * D + lane16 * 4);
+    *reinterpret_cast<float4*>(Zb + (int64_t)e * D + lane16 * 4) = v;
+}
+
+__global__ void __launch_bounds__(256) batch_rows_scatter_kernel(const float* __restrict__ Zb, int U, const int64_t* __restrict__ users,
+                                                                 const int64_t* __restrict__ items, int B, float* __restrict__ Z) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (e >= 2 * B) return;
+    const int lane16 = threadIdx.x & 15;
+    const bool user_row = e < B;
+    const int64_t row = user_row ? users[e] : items[e - B] + U;
+    *reinterpret_cast<float4*>(Z + row * D + lane16 * 4) = *reinterpret_cast<const float4*>(Zb + (int64_t)e * D + lane16 * 4);   // duplicates write the same row
+}
+
 // end-of-step bookkeeping of a captured step in one launch: epoch loss accumulator and train-row cursor
 __global__ void step_counters_kernel(double* total, const float* __restrict__ loss, int64_t* row_dev, int64_t row_stride) {
     if (total && loss) *total += (double)*loss;
@@ -284,6 +312,28 @@ extern "C" int ngacf_counter_add(int64_t* counter, int64_t delta, void* stream) 
     NGACF_REQUIRE(counter, "counter_add: null argument");
     counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
     return check_launch("counter_add");
+}
+
+extern "C" int ngacf_batch_rows_gather(const float* Z, int32_t U, const int64_t* users, const int64_t* items, int32_t B, int64_t u_lo, int64_t u_hi,
+                                       int64_t i_lo, int64_t i_hi, float* Zb, void* stream) {
+    NGACF_REQUIRE(Z && users && items && Zb && B >= 0, "batch_rows_gather: bad argument");
+    if (B == 0) return NGACF_OK;
+    batch_rows_gather_kernel<<<ceil_div((int64_t)2 * B * 16, 256), 256, 0, (cudaStream_t)stream>>>(Z, U, users, items, B, u_lo, u_hi, i_lo, i_hi, Zb);
+    return check_launch("batch_rows_gather");
+}
+
+extern "C" int ngacf_batch_rows_scatter(const float* Zb, int32_t U, const int64_t* users, const int64_t* items, int32_t B, float* Z, void* stream) {
+    NGACF_REQUIRE(Z && users && items && Zb && B >= 0, "batch_rows_scatter: bad argument");
+    if (B == 0) return NGACF_OK;
+    batch_rows_scatter_kernel<<<ceil_div((int64_t)2 * B * 16, 256), 256, 0, (cudaStream_t)stream>>>(Zb, U, users, items, B, Z);
+    return check_launch("batch_rows_scatter");
+}
+
+extern "C" int ngacf_memset_zero(void* p, size_t bytes, void* stream) {
+    NGACF_REQUIRE(p || bytes == 0, "memset_zero: null pointer");
+    if (bytes == 0) return NGACF_OK;
+    cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
+    return check_launch("memset_zero");
 }
 
 extern "C" int ngacf_step_counters(double* total, const float* loss, int64_t* row_dev, int64_t row_stride, void* stream) {

@@ -115,155 +115,240 @@ class ReplicaTrainer(FusedTrainer):
 
 
 # ------------------------------------------------------------------------------------------------
-# north-star partition: users (and their edge rows) range-partitioned over the GPUs
+# north-star partition: users and their edge rows range-partitioned over the GPUs, item rows OWNED by range;
+# per stage the item rows are all-gathered and the item-side partial sums reduce-scattered
 # ------------------------------------------------------------------------------------------------
-class UserShard:
-    """Contiguous user range of this rank, balanced by EDGE count, and the rank-local graph: the CSR rows of the own
-    users and the CSC restricted to them (items x own users).  Item-side state is replicated: the item-side partial sums
-    of every stage are summed across ranks with ONE all-reduce (= reduce-scatter + all-gather in a single latency-bound
-    NCCL call).  Local CSR edge ids are the global ones minus `edge_offset`, so the dropout streams (keyed
-    by global edge id) are identical to the single-GPU run."""
+class ShardPlan:
+    """Host-side description of the partition (numpy only -- the world_size-2 gloo tests exercise it on the CPU).
 
-    def __init__(self, edge_u, edge_i, U, I, rank, world, device):
+    users : contiguous ranges balanced by EDGE count (rank r owns users [ub[r], ub[r+1]) and their CSR rows, which are the
+            contiguous global edge ids [eb[r], eb[r+1]) -- so the Philox dropout streams, keyed by global edge id, are those of
+            the single-GPU run);
+    items : contiguous equal ranges of `chunk` = ceil(I / world) rows (the NCCL all-gather / reduce-scatter need equal counts);
+            item-side buffers carry I_pad = chunk * world rows, the tail rows stay zero."""
+
+    def __init__(self, edge_u, edge_i, U: int, I: int, world: int):
         import numpy as np
-        from .graph import BipartiteGraph
         key = np.unique(np.asarray(edge_u, np.int64) * np.int64(I) + np.asarray(edge_i, np.int64))     # global coalesce (host, once)
-        eu, ei = key // I, key % I
+        self.eu, self.ei = key // I, key % I
         rowptr = np.zeros(U + 1, np.int64)
-        np.add.at(rowptr, eu + 1, 1)
-        rowptr = np.cumsum(rowptr)
-        E = int(key.shape[0])
-        # boundaries: first user whose cumulative edge count reaches r*E/world
-        bounds = [int(np.searchsorted(rowptr, (E * r) // world, side="left")) for r in range(world)] + [U]
-        bounds[0] = 0
-        self.bounds = bounds
-        self.rank, self.world, self.U, self.I, self.E = rank, world, U, I, E
-        self.u_lo, self.u_hi = bounds[rank], bounds[rank + 1]
-        self.edge_offset = int(rowptr[self.u_lo])
-        sel = slice(int(rowptr[self.u_lo]), int(rowptr[self.u_hi]))
-        idx = torch.from_numpy(np.stack([eu[sel], ei[sel]])).to(device)
-        self.graph = BipartiteGraph(idx, U, I, check_users=False)
-        self.local_edges = self.graph.E
+        np.add.at(rowptr, self.eu + 1, 1)
+        self.rowptr = np.cumsum(rowptr)
+        self.U, self.I, self.E, self.world = int(U), int(I), int(key.shape[0]), int(world)
+        ub = [int(np.searchsorted(self.rowptr, (self.E * r) // world, side="left")) for r in range(world)] + [U]
+        ub[0] = 0
+        for r in range(1, world + 1):              # monotone even when one user holds more than E/world edges
+            ub[r] = max(ub[r], ub[r - 1])
+        self.ub = ub
+        self.eb = [int(self.rowptr[b]) for b in ub]
+        self.chunk = -(-I // world)
+        self.I_pad = self.chunk * world
+
+    def users(self, rank):
+        return self.ub[rank], self.ub[rank + 1]
+
+    def items(self, rank):
+        lo = min(self.I, rank * self.chunk)
+        return lo, min(self.I, lo + self.chunk)
+
+    def edges(self, rank):
+        return self.eb[rank], self.eb[rank + 1]
+
+    def local_edges(self, rank):
+        lo, hi = self.edges(rank)
+        return self.eu[lo:hi], self.ei[lo:hi]
 
 
-class ShardedPropagation:
-    """Propagation over a UserShard: own users complete locally, item rows via partial sums + all-reduce."""
+class NcclTransport:
+    """In-place collectives over torch.distributed (NCCL over NVLink / NVSwitch on the box; gloo in the CPU tests, where the two
+    tensor collectives gloo lacks are expressed through all_gather / all_reduce)."""
 
-    def __init__(self, shard: UserShard, stages=None):
-        from .ops import D, STAGES
-        from .propagation import Propagation
-        self.sh = shard
-        g = shard.graph
-        self.p = Propagation(g, stages or STAGES)
-        for t in self.p.h + self.p.Z + self.p.s + self.p.norm:      # rows of other ranks' users are never written: keep them finite
-            t.zero_()
-        self.p._bwd_buffers()
-        for t in (self.p._bwd["G"] + [self.p._bwd["Ghat"], self.p._bwd["dh"], self.p._bwd["dN"], self.p._bwd["dS"]]):
-            t.zero_()
-        dev = g.device
-        S = len(self.p.stages)
-        self._fm = [torch.empty(g.N, dtype=torch.int64, device=dev) for _ in range(S)]
-        self._em = [torch.empty(max(shard.E, 1), dtype=torch.uint8, device=dev) for _ in range(S)]     # GLOBAL edge ids
-        self.featmask = [None] * S
-        self.edgemask = [None] * S
-        self.scale = 1.0
+    def __init__(self):
+        self.rank, self.world = world_info()
+        self.gloo = dist.is_initialized() and dist.get_backend() == "gloo"
 
-    def set_dropout(self, droprate, seed=0, call=0, call_dev=None):
-        S = len(self.p.stages)
-        if droprate <= 0:
-            self.featmask, self.edgemask, self.scale = [None] * S, [None] * S, 1.0
-            return
-        self.scale = 1.0 / (1.0 - droprate)
-        ops.dropout_masks(self._fm, self._em, [H for H, _ in self.p.stages], self.sh.graph.N, self.sh.E, seed, call, droprate, call_dev)
-        self.featmask = list(self._fm)
-        self.edgemask = [m[self.sh.edge_offset:] for m in self._em]       # local edge id + offset = global edge id
+    def all_gather_rows(self, tensors, chunk):
+        """every tensor is (world*chunk, w): rank r's rows [r*chunk,(r+1)*chunk) are valid and are sent to every rank"""
+        r = self.rank
+        for t in tensors:
+            own = t[r * chunk:(r + 1) * chunk]
+            if self.gloo:
+                parts = [torch.empty_like(own) for _ in range(self.world)]
+                dist.all_gather(parts, own.contiguous())
+                for q, part in enumerate(parts):
+                    t[q * chunk:(q + 1) * chunk].copy_(part)
+            else:
+                dist.all_gather_into_tensor(t, own)
 
-    def forward_plan(self, uEmbd, iEmbd, wtabs):
-        """list of ('k', fn) compute items and ('c', fn) collectives."""
-        p, sh, g = self.p, self.sh, self.sh.graph
-        U, I, lo, hi = sh.U, sh.I, sh.u_lo, sh.u_hi
-        plan = []
-        for k, (H, _) in enumerate(p.stages):
-            Xu = uEmbd if k == 0 else p.Z[k - 1]
-            Xi = iEmbd if k == 0 else p.Z[k - 1][U:]
-            act = 0 if k == 0 else 1
+    def reduce_scatter_rows(self, tensors, chunk):
+        """every tensor is (world*chunk, w) of per-rank partial sums: afterwards rank r's rows [r*chunk,(r+1)*chunk) hold the sum"""
+        r = self.rank
+        for t in tensors:
+            if self.gloo:
+                dist.all_reduce(t)
+            else:
+                dist.reduce_scatter_tensor(t[r * chunk:(r + 1) * chunk], t)
 
-            def compute(k=k, H=H, Xu=Xu, Xi=Xi, act=act):
-                fm = self.featmask[k]
-                ops.transform_fwd(Xu[lo:hi], None, act, None if fm is None else fm[lo:], self.scale, wtabs[k], H, hi - lo, 0,
-                                  p.h[k][lo:hi], p.s[k][lo:hi])
-                ops.transform_fwd(None, Xi, act, None if fm is None else fm[U:], self.scale, wtabs[k], H, 0, I, p.h[k][U:], p.s[k][U:])
-                ops.aggregate_fwd(g, p.scratch, p.counter, p.h[k], p.s[k], H, self.edgemask[k], self.scale, p.Z[k], p.norm[k],
-                                  partial_from=g.T_users)
-            plan.append(("k", compute))
-            plan.append(("c", lambda k=k: (dist.all_reduce(p.Z[k][U:]), dist.all_reduce(p.norm[k][U:]))))
-            plan.append(("k", lambda k=k, H=H: ops.aggregate_finalize(p.Z[k][U:], p.h[k][U:], p.norm[k][U:], H)))
-        return plan
+    def all_reduce(self, tensors):
+        for t in tensors:
+            dist.all_reduce(t)
 
-    def backward_plan(self, uEmbd, iEmbd, wtabs, gtabs, dU, dI, accumulate):
-        """G_last = self.p.grad_in(): own-user rows and ALL item rows valid (item rows already summed across ranks)."""
-        p, sh, g = self.p, self.sh, self.sh.graph
-        U, I, lo, hi = sh.U, sh.I, sh.u_lo, sh.u_hi
-        b = p._bwd
-        plan = []
-        G = b["G"][0]
-        for k in range(len(p.stages) - 1, -1, -1):
-            H, _ = p.stages[k]
 
-            def edges(k=k, H=H, G=G):
-                ops.stage_bwd_prep(G[lo:hi], p.Z[k][lo:hi], p.h[k][lo:hi], p.norm[k][lo:hi], H, b["Ghat"][lo:hi], self._dN(H)[lo:hi])
-                ops.stage_bwd_prep(G[U:], p.Z[k][U:], p.h[k][U:], p.norm[k][U:], H, b["Ghat"][U:], self._dN(H)[U:])
-                for mode in (0, 1):
-                    ops.stage_bwd_edges(mode, g, p.scratch, p.counter, G, b["Ghat"], self._dN(H), p.h[k], p.s[k], H, self.edgemask[k],
-                                        self.scale, wtabs[k], b["ds"], b["dh"], self._dS(H), partial=mode)
-            plan.append(("k", edges))
-            plan.append(("c", lambda H=H: (dist.all_reduce(b["dh"][U:]), dist.all_reduce(self._dS(H)[U:]))))
-            Gprev = b["G"][1] if G is b["G"][0] else b["G"][0]
+class LocalCluster:
+    """All ranks of the partition inside ONE process on one device: the trainers' plans are executed phase by phase and the
+    collectives are applied directly to the ranks' buffers (sums in rank order).  This is how the sharded step is checked
+    against the single-GPU step in the 1-GPU test suite (tests/test_gpu_parity.py) -- the NCCL run only swaps the transport."""
 
-            def dense(k=k, H=H, G=G, Gprev=Gprev):
-                ops.stage_bwd_finalize(b["dh"][U:], self._dS(H)[U:], G[U:], wtabs[k], H, 1)
-                fm = self.featmask[k]
-                if k > 0:
-                    Zp = p.Z[k - 1]
-                    ops.transform_bwd(b["dh"][lo:hi], self._dS(H)[lo:hi], p.h[k][lo:hi], Zp[lo:hi], None, 1, None if fm is None else fm[lo:],
-                                      self.scale, wtabs[k], gtabs[k], H, hi - lo, 0, Gprev[lo:hi], None, 0, int(accumulate), b["ws"])
-                    ops.transform_bwd(b["dh"][U:], self._dS(H)[U:], p.h[k][U:], None, Zp[U:], 1, None if fm is None else fm[U:], self.scale,
-                                      wtabs[k], gtabs[k], H, 0, I, None, Gprev[U:], 0, int(accumulate), b["ws"])
+    def __init__(self, trainers):
+        self.trainers = trainers
+
+    @staticmethod
+    def apply(kind, per_rank, chunk):
+        world = len(per_rank)
+        for j in range(len(per_rank[0])):
+            ts = [per_rank[r][j] for r in range(world)]
+            if kind == "ag":
+                for d in range(world):
+                    for q in range(world):
+                        if d != q:
+                            ts[d][q * chunk:(q + 1) * chunk].copy_(ts[q][q * chunk:(q + 1) * chunk])
+            elif kind == "rs":
+                sums = []
+                for q in range(world):
+                    acc = ts[0][q * chunk:(q + 1) * chunk].clone()
+                    for d in range(1, world):
+                        acc += ts[d][q * chunk:(q + 1) * chunk]
+                    sums.append(acc)
+                for q in range(world):
+                    ts[q][q * chunk:(q + 1) * chunk].copy_(sums[q])
+            else:
+                acc = ts[0].clone()
+                for d in range(1, world):
+                    acc += ts[d]
+                for d in range(world):
+                    ts[d].copy_(acc)
+
+    def run_steps(self, n_steps, read_loss=False):
+        losses = []
+        plans = None
+        for tr in self.trainers:
+            tr.model.train()
+            tr._prepare_run()
+        for _ in range(n_steps):
+            for tr in self.trainers:
+                tr._begin_step()
+            if plans is None:
+                plans = [tr._plan(*tr._mode()) for tr in self.trainers]
+            for phase in zip(*plans):
+                if phase[0][0] == "k":
+                    for tr, (_, name, fn) in zip(self.trainers, phase):
+                        with torch.cuda.device(tr.dev):
+                            fn()
                 else:
-                    ops.transform_bwd(b["dh"][lo:hi], self._dS(H)[lo:hi], p.h[k][lo:hi], uEmbd[lo:hi], None, 0, None if fm is None else fm[lo:],
-                                      self.scale, wtabs[k], gtabs[k], H, hi - lo, 0, dU[lo:hi], None, int(accumulate), int(accumulate), b["ws"])
-                    ops.transform_bwd(b["dh"][U:], self._dS(H)[U:], p.h[k][U:], None, iEmbd, 0, None if fm is None else fm[U:], self.scale,
-                                      wtabs[k], gtabs[k], H, 0, I, None, dI, int(accumulate), int(accumulate), b["ws"])
-            plan.append(("k", dense))
-            G = Gprev
-        return plan
+                    _, name, kind, _ = phase[0]
+                    self.apply(kind, [ph[3] for ph in phase], self.trainers[0].plan.chunk)
+            for tr in self.trainers:
+                tr._end_step()
+            if read_loss:
+                losses.append(float(self.trainers[0].loss.item()))
+        for tr in self.trainers:
+            tr.model._call += 2 * n_steps
+        return losses
 
-    # dN/dS are allocated (N,8); the kernels index them as (N,H): use a compact (N,H) view of the same storage
-    def _dN(self, H):
-        return self.p._bwd["dN"].view(-1)[: self.sh.graph.N * H].view(self.sh.graph.N, H)
+    def gather_state(self):
+        """state_dict of the whole model assembled from the owners' rows (attention parameters from rank 0)"""
+        sd = {k: v.detach().clone() for k, v in self.trainers[0].model.state_dict().items()}
+        for tr in self.trainers:
+            sd["uEmbd.weight"][tr.u_lo:tr.u_hi] = tr.model.uEmbd.weight.detach()[tr.u_lo:tr.u_hi]
+            sd["iEmbd.weight"][tr.i_lo:tr.i_hi] = tr.model.iEmbd.weight.detach()[tr.i_lo:tr.i_hi]
+        return sd
 
-    def _dS(self, H):
-        return self.p._bwd["dS"].view(-1)[: self.sh.graph.N * H].view(self.sh.graph.N, H)
+    def gather_grads(self):
+        """{name: gradient} assembled the same way (after a step: embedding rows from their owners, attention grads summed)"""
+        t0 = self.trainers[0]
+        out = {"uEmbd.weight": torch.zeros_like(t0.model.uEmbd.weight), "iEmbd.weight": torch.zeros_like(t0.model.iEmbd.weight)}
+        for tr in self.trainers:
+            out["uEmbd.weight"][tr.u_lo:tr.u_hi] = tr.model.uEmbd.weight.grad[tr.u_lo:tr.u_hi]
+            out["iEmbd.weight"][tr.i_lo:tr.i_hi] = tr.model.iEmbd.weight.grad[tr.i_lo:tr.i_hi]
+        for name, p in t0.model.named_parameters():
+            if name not in out:
+                out[name] = p.grad.detach().clone()
+        return out
 
 
 class ShardedTrainer:
-    """PairSampling step with the propagation sharded by user range (one process per GPU).  Same maths as the single-GPU
-    FusedTrainer step on the same batch (strong scaling): every rank samples the same batch, scores the pairs whose user
-    it owns, and the item-side partial sums are exchanged with NCCL all-reduces between the compute segments; each
-    compute segment between two collectives is a captured CUDA graph."""
+    """PairSampling step with the propagation partitioned by user range, one process per GPU (the reference's single-process
+    DataParallelModel / DataParallelCriterion2, parallel.py:94-130,165-196 and train_eval_Gowalla.py:97-104,137, recompute the
+    whole graph on every GPU).  Same maths as the single-GPU step on the same batch (strong scaling):
 
-    def __init__(self, model, inter, edge_u, edge_i, batch_size, optim, sample_seed, use_cuda_graph=True):
-        from .train import FusedTrainer   # noqa: F401  (shares the optimizer-state conventions)
-        self.rank, self.world = world_info()
+      stage forward : dense transform of the OWN users and the OWN items -> all-gather of the item rows (h | s) -> user rows
+                      complete locally, item rows as partial sums over the own users' edges -> reduce-scatter to the item
+                      owners -> finalize of the own item rows;
+      pair scores   : every rank samples the same batch; the batch's rows are summed into a compact table by one all-reduce
+                      (a row has one owner), scores / loss / dscore are computed redundantly, the gradient rows land on owners;
+      stage backward: all-gather of the own items' Ghat | dN -> user pass (complete) + item pass (partial) over the local
+                      edges -> reduce-scatter of dh | dS to the item owners -> dense backward of the own rows;
+      update        : one all-reduce of the 17 K attention-parameter gradients (embedding gradients never leave their owner);
+                      Adam on the own user rows, the own item rows and the (replicated) attention parameters.
+
+    The pos and the neg propagation run on two streams between the collectives and share every collective call.  The whole
+    step -- kernels and NCCL calls -- is captured in ONE CUDA graph; if the capture of the collectives is refused, the compute
+    phases are captured separately and the collectives run eagerly between them (the round-1 structure)."""
+
+    def __init__(self, model, inter, edge_u, edge_i, batch_size, optim, sample_seed, use_cuda_graph=True, transport=None, rank=None, world=None,
+                 plan=None):
+        from .graph import BipartiteGraph
+        from .propagation import Propagation
+        self.transport = transport if transport is not None else NcclTransport()
+        self.rank = self.transport.rank if rank is None else int(rank)
+        self.world = self.transport.world if world is None else int(world)
         self.model, self.inter, self.B, self.optim = model, inter, int(batch_size), optim
         self.sample_seed = int(sample_seed)
+        self.use_cuda_graph = use_cuda_graph
         dev = model.uEmbd.weight.device
         self.dev = dev
-        self.shard = UserShard(edge_u, edge_i, model.userNum, model.itemNum, self.rank, self.world, dev)
-        self.g = self.shard.graph
-        self.props = [ShardedPropagation(self.shard, model.stages), ShardedPropagation(self.shard, model.stages)]
-        self.use_cuda_graph = use_cuda_graph
-        i64, f32 = dict(dtype=torch.int64, device=dev), dict(dtype=torch.float32, device=dev)
+        U, I = model.userNum, model.itemNum
+        self.plan = plan if plan is not None else ShardPlan(edge_u, edge_i, U, I, self.world)
+        P = self.plan
+        self.U, self.I = U, I
+        self.u_lo, self.u_hi = P.users(self.rank)
+        self.i_lo, self.i_hi = P.items(self.rank)
+        self.e_lo, self.e_hi = P.edges(self.rank)
+        eu, ei = P.local_edges(self.rank)
+        import numpy as np
+        with torch.cuda.device(dev):
+            self.g = BipartiteGraph(torch.from_numpy(np.stack([eu, ei])).to(dev), U, I, check_users=False)
+        g = self.g
+        self.stages = tuple(model.stages)
+        S = len(self.stages)
+        N_alloc = U + P.I_pad                       # item-side rows padded to world * chunk (the pad rows stay zero)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+
+        def rows(w):
+            return torch.zeros((N_alloc, w), **f32)
+        self.props = []
+        for _ in range(2):       # pos / neg
+            p = Propagation.__new__(Propagation)
+            p.g, p.stages = g, self.stages
+            p.h = [rows(ops.D) for _ in self.stages]
+            p.Z = [rows(ops.D) for _ in self.stages]
+            p.s = [rows(H) for H, _ in self.stages]
+            p.norm = [rows(H) for H, _ in self.stages]
+            p.scratch = torch.empty(max(g.S, 1) * 72, **f32)
+            p.counter = torch.zeros(max(g.L, 1), dtype=torch.int32, device=dev)
+            p.G = [rows(ops.D), rows(ops.D)]
+            p.Ghat, p.dh = rows(ops.D), rows(ops.D)
+            p.dN = [rows(H) for H, _ in self.stages]      # one (N,H) array per stage width (the kernels index them as (N,H))
+            p.dS = [rows(H) for H, _ in self.stages]
+            p.ds = torch.empty(max(g.E, 1) * 8, **f32)
+            p.ws = torch.empty(ops.transform_bwd_workspace_bytes(U, I) // 4, **f32)
+            p.ZS = rows(ops.D)                             # scoring table: the batch's rows at their global positions
+            p.fm = [torch.zeros(N_alloc, **i64) for _ in self.stages]
+            p.em = [torch.zeros(max(P.E, 1), dtype=torch.uint8, device=dev) for _ in self.stages]      # indexed by GLOBAL edge id
+            p.featmask, p.edgemask, p.scale = [None] * S, [None] * S, 1.0
+            self.props.append(p)
+        self.Zb = torch.zeros((2, 2 * self.B, ops.D), **f32)           # compact batch rows of both propagations (one all-reduce)
         self.users, self.pos, self.neg = torch.zeros(self.B, **i64), torch.zeros(self.B, **i64), torch.zeros(self.B, **i64)
         self.sc = [torch.zeros(self.B, **f32), torch.zeros(self.B, **f32)]
         self.dsc = [torch.zeros(self.B, **f32), torch.zeros(self.B, **f32)]
@@ -271,174 +356,442 @@ class ShardedTrainer:
         self.total = torch.zeros((), dtype=torch.float64, device=dev)
         self.row_dev = torch.zeros(2, **i64)
         self.call_dev = torch.zeros(1, **i64)
-        # parameters / gradients (flat buffer -> one all-reduce) / Adam state
+        self.side = torch.cuda.Stream(device=dev)
+        # parameters: embedding gradients stay with the owner of the row; the attention parameters are replicated and their
+        # gradients (partial sums over the own rows) are summed by one small all-reduce
         m = model
-        self.params = [m.uEmbd.weight, m.iEmbd.weight] + m._flat_stage_params()
-        self.flat_grad, views = flat_views(self.params)
-        for p, v in zip(self.params, views):
-            p.grad = v
+        self.small = m._flat_stage_params()
+        self.flat_small, views = flat_views(self.small)
+        for p_, v in zip(self.small, views):
+            p_.grad = v
+        for p_ in (m.uEmbd.weight, m.iEmbd.weight):
+            if p_.grad is None:
+                p_.grad = torch.zeros_like(p_)
         stage_params = m.gat.stage_parameters()
-        self.wtabs = [ops.pointer_table([p.detach() for p in st]) for st in stage_params]
-        self.gtabs = [ops.pointer_table([p.grad for p in st]) for st in stage_params]
+        self.wtabs = [ops.pointer_table([q.detach() for q in st]) for st in stage_params]
+        self.gtabs = [ops.pointer_table([q.grad for q in st]) for st in stage_params]
         group = optim.param_groups[0]
         self.hyper = dict(lr=float(group["lr"]), b1=float(group["betas"][0]), b2=float(group["betas"][1]), eps=float(group["eps"]),
                           wd=float(group["weight_decay"]))
-        rows = []
-        for p in self.params:
-            st = optim.state[p]
+        self.params = [m.uEmbd.weight, m.iEmbd.weight] + self.small
+        for p_ in self.params:
+            st = optim.state[p_]
             if len(st) == 0:
-                st["step"], st["exp_avg"], st["exp_avg_sq"] = torch.tensor(0.0), torch.zeros_like(p), torch.zeros_like(p)
-            rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()])
-        self.adam_tab = torch.tensor(rows, dtype=torch.int64).to(dev)
-        self.adam_total = sum(p.numel() for p in self.params)
+                st["step"], st["exp_avg"], st["exp_avg_sq"] = torch.tensor(0.0), torch.zeros_like(p_), torch.zeros_like(p_)
+        # Adam table: row slices of the embedding tables (own rows only) + the attention parameters
+        entries = []
+
+        def entry(p_, lo=None, hi=None):
+            st = optim.state[p_]
+            sl = slice(lo, hi)
+            return (p_.detach()[sl], p_.grad[sl], st["exp_avg"][sl], st["exp_avg_sq"][sl])
+        if self.u_hi > self.u_lo:
+            entries.append(entry(m.uEmbd.weight, self.u_lo, self.u_hi))
+        if self.i_hi > self.i_lo:
+            entries.append(entry(m.iEmbd.weight, self.i_lo, self.i_hi))
+        entries += [entry(q) for q in self.small]
+        self._adam_entries = entries
+        self.adam_tab = torch.tensor([[a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), a.numel()] for a, b, c, d in entries],
+                                     dtype=torch.int64).to(dev)
+        self.adam_total = sum(a.numel() for a, _, _, _ in entries)
         self.adam_state = torch.tensor([float(optim.state[self.params[0]]["step"]), 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
-        # gradients that every rank computes in full (item side) are summed `world` times by the all-reduce: pre-scale them
-        self._replicated = [m.iEmbd.weight.grad]
-        for (H, DH), st in zip(self.props[0].p.stages, stage_params):
-            self._replicated += [p.grad for p in st[H:2 * H]]                 # W_i heads
-            self._replicated += [p.grad[:, DH:] for p in st[2 * H:3 * H]]     # a_i halves
+        self._graph = None
         self._segments = None
+        self._key = None
         self._cursor = 0
+        self.capture_mode = None
 
     # ------------------------------------------------------------------------------------------
+    def _items_view(self, t):
+        return t[self.U:]                        # (I_pad, w): the item rows of a per-node buffer
+
+    def _mode(self):
+        m = self.model
+        return (m.droprate if m.droprate > 0 else 0.0), m._seed()
+
     def _plan(self, droprate, seed):
-        m, sh = self.model, self.shard
-        U = sh.U
+        """[("k", name, fn) | ("c", name, kind, tensors)]: compute phases (kernels of both propagations on two streams) and
+        collectives ("ag" / "rs" over the item rows, "ar")."""
+        m, P, g = self.model, self.plan, self.g
+        U, I, B = self.U, self.I, self.B
+        ulo, uhi, ilo, ihi = self.u_lo, self.u_hi, self.i_lo, self.i_hi
+        nu, ni = uhi - ulo, ihi - ilo
         uE, iE = m.uEmbd.weight.detach(), m.iEmbd.weight.detach()
+        dU, dI = m.uEmbd.weight.grad, m.iEmbd.weight.grad
         items = (self.pos, self.neg)
-        B = self.B
+        side = self.side
+        S = len(self.stages)
+        heads = [H for H, _ in self.stages]
+        scale = 1.0 / (1.0 - droprate) if droprate > 0 else 1.0
         plan = []
+
+        def both(fn):
+            """fn(k) for the pos propagation on the current stream and the neg propagation on the side stream"""
+            def run():
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    fn(1)
+                fn(0)
+                cur.wait_stream(side)
+            return run
 
         def head():
             ops.sample_pairs(self.inter, 0, B, self.sample_seed, 0, self.users, self.pos, self.neg, self.row_dev)
-            for k in (0, 1):
-                self.props[k].set_dropout(droprate, seed, k, self.call_dev)
-        plan.append(("k", head))
-        for k in (0, 1):
-            plan += self.props[k].forward_plan(uE, iE, self.wtabs)
+        plan.append(("k", "sample", head))
 
-        def score_and_scatter():
-            for k in (0, 1):
-                ops.score_pairs(self.props[k].p.Z[-1], U, self.users, items[k], self.sc[k])
-            ops.bpr_loss_owned(self.sc[0], self.sc[1], 1.0, self.loss, self.dsc[0], self.dsc[1], self.users, sh.u_lo, sh.u_hi)
-            for k in (0, 1):
-                G = self.props[k].p.grad_in()
-                G.zero_()
-                ops.score_pairs_bwd(self.props[k].p.Z[-1], U, self.users, items[k], self.dsc[k], G)
-            m.uEmbd.weight.grad.zero_()          # rows of other ranks' users stay zero for the gradient all-reduce
-        plan.append(("k", score_and_scatter))
-        plan.append(("c", lambda: (dist.all_reduce(self.props[0].p.grad_in()[U:]), dist.all_reduce(self.props[1].p.grad_in()[U:]),
-                                   dist.all_reduce(self.loss))))
+        def masks(k):
+            p = self.props[k]
+            if droprate <= 0:
+                p.featmask, p.edgemask, p.scale = [None] * S, [None] * S, 1.0
+                return
+            p.scale = scale
+            ops.dropout_masks_ranges(p.fm, p.em, heads, ((ulo, uhi), (U + ilo, U + ihi)), (self.e_lo, self.e_hi), seed, k, droprate, self.call_dev)
+            p.featmask = list(p.fm)
+            p.edgemask = [e[self.e_lo:] for e in p.em]          # local edge id + e_lo = global edge id
         for k in (0, 1):
-            plan += self.props[k].backward_plan(uE, iE, self.wtabs, self.gtabs, m.uEmbd.weight.grad, m.iEmbd.weight.grad, accumulate=(k == 1))
+            masks(k) if droprate <= 0 else None
+        if droprate > 0:
+            plan.append(("k", "masks", both(masks)))
 
-        def prescale():
-            inv = 1.0 / self.world
-            for gr in self._replicated:
-                gr.mul_(inv)
-        plan.append(("k", prescale))
-        plan.append(("c", lambda: dist.all_reduce(self.flat_grad)))
+        for k, (H, _) in enumerate(self.stages):
+            act = 0 if k == 0 else 1
+
+            def transform(q, k=k, H=H, act=act):
+                p = self.props[q]
+                Xu = uE if k == 0 else p.Z[k - 1]
+                Xi = iE if k == 0 else p.Z[k - 1][U:]
+                fm = p.featmask[k]
+                if nu:
+                    ops.transform_fwd(Xu[ulo:uhi], None, act, None if fm is None else fm[ulo:], p.scale, self.wtabs[k], H, nu, 0,
+                                      p.h[k][ulo:uhi], p.s[k][ulo:uhi])
+                if ni:
+                    ops.transform_fwd(None, Xi[ilo:ihi], act, None if fm is None else fm[U + ilo:], p.scale, self.wtabs[k], H, 0, ni,
+                                      p.h[k][U + ilo:U + ihi], p.s[k][U + ilo:U + ihi])
+            plan.append(("k", "transform%d" % k, both(transform)))
+            plan.append(("c", "all-gather h|s items, stage %d" % k, "ag",
+                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].h[k], self.props[q].s[k])]))
+
+            def aggregate(q, k=k, H=H):
+                p = self.props[q]
+                ops.aggregate_fwd(g, p.scratch, p.counter, p.h[k], p.s[k], H, p.edgemask[k], p.scale, p.Z[k], p.norm[k], partial_from=g.T_users)
+            plan.append(("k", "aggregate%d" % k, both(aggregate)))
+            plan.append(("c", "reduce-scatter Z|norm items, stage %d" % k, "rs",
+                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].Z[k], self.props[q].norm[k])]))
+
+            def finalize(q, k=k, H=H):
+                p = self.props[q]
+                if ni:
+                    ops.aggregate_finalize(p.Z[k][U + ilo:U + ihi], p.h[k][U + ilo:U + ihi], p.norm[k][U + ilo:U + ihi], H)
+                if k == S - 1:
+                    ops.batch_rows_gather(p.Z[k], U, self.users, items[q], (ulo, uhi), (ilo, ihi), self.Zb[q])
+            plan.append(("k", "finalize%d" % k, both(finalize)))
+
+        plan.append(("c", "all-reduce batch rows", "ar", [self.Zb]))
+
+        def score(q):
+            p = self.props[q]
+            ops.batch_rows_scatter(self.Zb[q], U, self.users, items[q], p.ZS)
+            ops.score_pairs(p.ZS, U, self.users, items[q], self.sc[q])
+
+        def loss_and_scatter():
+            both(score)()
+            ops.bpr_loss(self.sc[0], self.sc[1], 1.0, self.loss, self.dsc[0], self.dsc[1])
+
+            def scatter(q):
+                p = self.props[q]
+                G = p.G[0]
+                if nu:
+                    ops.memset_zero(G[ulo:uhi])
+                if ni:
+                    ops.memset_zero(G[U + ilo:U + ihi])
+                ops.score_pairs_bwd(p.ZS, U, self.users, items[q], self.dsc[q], G)      # rows of other owners are written and never read
+            both(scatter)()
+            ops.memset_zero(self.flat_small)        # attention-parameter gradients are accumulated by every dense backward
+        plan.append(("k", "scores+loss+scatter", loss_and_scatter))
+
+        evs = [torch.cuda.Event() for _ in range(S)]
+        for k in range(S - 1, -1, -1):
+            H, _ = self.stages[k]
+            Gi = (S - 1 - k) % 2                  # G ping-pong: stage S-1 reads G[0]
+
+            def prep(q, k=k, H=H, Gi=Gi):
+                p = self.props[q]
+                G = p.G[Gi]
+                if nu:
+                    ops.stage_bwd_prep(G[ulo:uhi], p.Z[k][ulo:uhi], p.h[k][ulo:uhi], p.norm[k][ulo:uhi], H, p.Ghat[ulo:uhi], p.dN[k][ulo:uhi])
+                if ni:
+                    ops.stage_bwd_prep(G[U + ilo:U + ihi], p.Z[k][U + ilo:U + ihi], p.h[k][U + ilo:U + ihi], p.norm[k][U + ilo:U + ihi], H,
+                                       p.Ghat[U + ilo:U + ihi], p.dN[k][U + ilo:U + ihi])
+            plan.append(("k", "prep%d" % k, both(prep)))
+            plan.append(("c", "all-gather Ghat|dN items, stage %d" % k, "ag",
+                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].Ghat, self.props[q].dN[k])]))
+
+            def edges(q, k=k, H=H, Gi=Gi):
+                p = self.props[q]
+                for mode in (0, 1):
+                    ops.stage_bwd_edges(mode, g, p.scratch, p.counter, p.G[Gi], p.Ghat, p.dN[k], p.h[k], p.s[k], H, p.edgemask[k], p.scale,
+                                        self.wtabs[k], p.ds, p.dh, p.dS[k], partial=mode)
+            plan.append(("k", "edges%d" % k, both(edges)))
+            plan.append(("c", "reduce-scatter dh|dS items, stage %d" % k, "rs",
+                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].dh, self.props[q].dS[k])]))
+
+            def dense(k=k, H=H, Gi=Gi):
+                cur = torch.cuda.current_stream()
+
+                def fin(q):
+                    p = self.props[q]
+                    if ni:
+                        ops.stage_bwd_finalize(p.dh[U + ilo:U + ihi], p.dS[k][U + ilo:U + ihi], p.G[Gi][U + ilo:U + ihi], self.wtabs[k], H, 1)
+
+                def tb(q):
+                    # weight gradients always ACCUMULATE into the (zero-filled) flat buffer: a rank may own no rows of a side
+                    p = self.props[q]
+                    Gprev = p.G[1 - Gi]
+                    acc = int(q == 1)
+                    fm = p.featmask[k]
+                    fu = None if fm is None else fm[ulo:]
+                    fi = None if fm is None else fm[U + ilo:]
+                    if k > 0:
+                        Zp = p.Z[k - 1]
+                        if nu:
+                            ops.transform_bwd(p.dh[ulo:uhi], p.dS[k][ulo:uhi], None, Zp[ulo:uhi], None, 1, fu, p.scale, self.wtabs[k], self.gtabs[k], H,
+                                              nu, 0, Gprev[ulo:uhi], None, 0, 1, p.ws)
+                        if ni:
+                            ops.transform_bwd(p.dh[U + ilo:U + ihi], p.dS[k][U + ilo:U + ihi], None, None, Zp[U + ilo:U + ihi], 1, fi, p.scale,
+                                              self.wtabs[k], self.gtabs[k], H, 0, ni, None, Gprev[U + ilo:U + ihi], 0, 1, p.ws)
+                    else:
+                        if nu:
+                            ops.transform_bwd(p.dh[ulo:uhi], p.dS[k][ulo:uhi], None, uE[ulo:uhi], None, 0, fu, p.scale, self.wtabs[k], self.gtabs[k], H,
+                                              nu, 0, dU[ulo:uhi], None, acc, 1, p.ws)
+                        if ni:
+                            ops.transform_bwd(p.dh[U + ilo:U + ihi], p.dS[k][U + ilo:U + ihi], None, None, iE[ilo:ihi], 0, fi, p.scale, self.wtabs[k],
+                                              self.gtabs[k], H, 0, ni, None, dI[ilo:ihi], acc, 1, p.ws)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    fin(1)
+                fin(0)
+                tb(0)
+                evs[k].record(cur)                # the gradient buffers: pos first, neg accumulates after it
+                with torch.cuda.stream(side):
+                    side.wait_event(evs[k])
+                    tb(1)
+                cur.wait_stream(side)
+            plan.append(("k", "dense-bwd%d" % k, dense))
+
+        plan.append(("c", "all-reduce attention-parameter grads", "ar", [self.flat_small]))
 
         def update():
             h = self.hyper
-            ops.adam_step_dev(self.adam_tab, len(self.params), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
-            self.total.add_(self.loss.double())
-            ops.counter_add(self.row_dev, B)
+            ops.adam_step_dev(self.adam_tab, len(self._adam_entries), self.adam_total, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.adam_state)
+            ops.step_counters(self.total, self.loss, self.row_dev, B)
             ops.counter_add(self.call_dev, 2)
-        plan.append(("k", update))
+        plan.append(("k", "adam", update))
         return plan
 
-    def _compile(self, droprate, seed):
-        """Merge consecutive compute items and capture each run as a CUDA graph; collectives stay eager between them."""
-        plan = self._plan(droprate, seed)
-        groups, cur = [], []
-        for kind, fn in plan:
-            if kind == "k":
-                cur.append(fn)
+    # ------------------------------------------------------------------------------------------
+    def _run_eager(self, plan):
+        for ph in plan:
+            if ph[0] == "k":
+                ph[2]()
             else:
-                if cur:
-                    groups.append(("k", cur))
-                    cur = []
-                groups.append(("c", fn))
-        if cur:
-            groups.append(("k", cur))
-        if not self.use_cuda_graph:
-            self._segments = [(kind, (lambda fs=f: [x() for x in fs]) if kind == "k" else f) for kind, f in groups]
-            return
-        # warm-up pass (eager) with state restored afterwards, then capture every compute group
-        snap = [p.detach().clone() for p in self.params]
-        opt_snap = [(self.optim.state[p]["exp_avg"].clone(), self.optim.state[p]["exp_avg_sq"].clone()) for p in self.params]
-        misc = [t.clone() for t in (self.adam_state, self.total, self.row_dev, self.call_dev)]
-        for kind, f in groups:
-            if kind == "k":
-                for x in f:
-                    x()
-            else:
-                f()
-        torch.cuda.synchronize(self.dev)
-        segs = []
-        for kind, f in groups:
-            if kind == "c":
-                segs.append(("c", f))
-                continue
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                for x in f:
-                    x()
-            segs.append(("k", gr.replay))
+                self._collective(ph[2], ph[3])
+
+    def _collective(self, kind, tensors):
+        t = self.transport
+        if kind == "ag":
+            t.all_gather_rows(tensors, self.plan.chunk)
+        elif kind == "rs":
+            t.reduce_scatter_rows(tensors, self.plan.chunk)
+        else:
+            t.all_reduce(tensors)
+
+    def _snapshot(self):
+        st = self.optim.state
+        return ([p.detach().clone() for p in self.params], [(st[p]["exp_avg"].clone(), st[p]["exp_avg_sq"].clone()) for p in self.params],
+                [t.clone() for t in (self.adam_state, self.total, self.row_dev, self.call_dev)])
+
+    def _restore(self, snap):
+        ps, opt, misc = snap
         with torch.no_grad():
-            for p, sp, (a, b) in zip(self.params, snap, opt_snap):
+            for p, sp, (a, b) in zip(self.params, ps, opt):
                 p.copy_(sp)
                 self.optim.state[p]["exp_avg"].copy_(a)
                 self.optim.state[p]["exp_avg_sq"].copy_(b)
-            for t, s in zip((self.adam_state, self.total, self.row_dev, self.call_dev), misc):
-                t.copy_(s)
-        self._segments = segs
-        self._seg_key = (droprate, seed)
+            for t, v in zip((self.adam_state, self.total, self.row_dev, self.call_dev), misc):
+                t.copy_(v)
 
-    # ------------------------------------------------------------------------------------------
+    def _compile(self, droprate, seed):
+        """Capture the step.  NGACF_DIST_CAPTURE = full (default: kernels AND collectives in one CUDA graph), segments (compute
+        phases captured, collectives eager between them) or eager."""
+        import os
+        plan = self._plan(droprate, seed)
+        self._plan_cache = plan
+        self._key = (droprate, seed)
+        self._graph, self._segments = None, None
+        want = os.environ.get("NGACF_DIST_CAPTURE", "full") if self.use_cuda_graph else "eager"
+        self.capture_mode = "eager"
+        if want == "eager":
+            return
+        snap = self._snapshot()
+        s = torch.cuda.Stream(device=self.dev)           # warm-up (communicators, lazy state) off the default stream
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._run_eager(plan)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        if want == "full":
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+                    self._run_eager(plan)
+                self._graph = gr
+                self.capture_mode = "one CUDA graph (kernels + NCCL)"
+            except Exception as e:       # noqa: BLE001  -- the collectives' capture was refused: fall back to segments
+                import sys
+                print("[ngacf_b200.dist] whole-step capture failed (%s: %s); capturing compute segments only" % (type(e).__name__, e),
+                      file=sys.stderr, flush=True)
+                torch.cuda.synchronize(self.dev)
+                want = "segments"
+        if want == "segments":
+            segs, cur = [], []
+            for ph in plan + [("c", "end", None, None)]:
+                if ph[0] == "k":
+                    cur.append(ph[2])
+                    continue
+                if cur:
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        for fn in cur:
+                            fn()
+                    segs.append(gr.replay)
+                    cur = []
+                if ph[2] is not None:
+                    segs.append(lambda kind=ph[2], ts=ph[3]: self._collective(kind, ts))
+            self._segments = segs
+            self.capture_mode = "CUDA-graph segments, eager collectives"
+        self._restore(snap)
+
+    def _prepare_run(self):
+        self.row_dev.copy_(torch.tensor([self._cursor, 0], dtype=torch.int64))
+        self.call_dev.fill_(self.model._call)
+
+    def _begin_step(self):
+        if self._cursor + self.B > len(self.inter):
+            self._cursor = 0
+            self.row_dev.zero_()
+
+    def _end_step(self):
+        self._cursor += self.B
+
+    def _replay(self):
+        if self._graph is not None:
+            self._graph.replay()
+        elif self._segments is not None:
+            for f in self._segments:
+                f()
+        else:
+            self._run_eager(self._plan_cache)
+
     def run_steps(self, n_steps, host_rows=None, read_loss=False):
         m = self.model
         m.train()
-        droprate = m.droprate if m.droprate > 0 else 0.0
-        seed = m._seed()
-        n = len(self.inter)
-        if self._segments is None or getattr(self, "_seg_key", None) != (droprate, seed):
+        droprate, seed = self._mode()
+        if self._key != (droprate, seed):
             self._compile(droprate, seed)
-            self._seg_key = (droprate, seed)
-        self.row_dev.copy_(torch.tensor([self._cursor, 0], dtype=torch.int64))
-        self.call_dev.fill_(m._call)
+        self._prepare_run()
         losses = []
         for _ in range(n_steps):
-            if self._cursor + self.B > n:
-                self._cursor = 0
-                self.row_dev.zero_()
+            self._begin_step()
             if host_rows is not None:
                 lo = self._cursor
                 self.inter.train_rows_user[lo:lo + self.B].copy_(host_rows[lo:lo + self.B], non_blocking=True)
-            for kind, f in self._segments:
-                f()
-            self._cursor += self.B
+            self._replay()
+            self._end_step()
             if read_loss:
                 losses.append(float(self.loss.item()))
         m._call += 2 * n_steps
         return losses
 
+    def train_epoch(self, epoch: int = 0, max_steps=None) -> float:
+        """Full batches of one epoch (the tail batch of len % batch rows is dropped in the sharded mode); returns
+        sum(batch-mean loss) / len(train_df) like train_bpr (train_eval_Gowalla.py:139,144).  The embedding tables are
+        re-assembled on every rank afterwards."""
+        n = len(self.inter)
+        n_full = n // self.B
+        if max_steps is not None:
+            n_full = min(n_full, max_steps)
+        self.total.zero_()
+        self._cursor = 0
+        self.row_dev.copy_(torch.tensor([0, epoch], dtype=torch.int64))
+        self.run_steps(n_full)
+        self.sync_embeddings()
+        return float(self.total.item()) / n
+
+    def sync_embeddings(self):
+        """every rank ends up with the full, updated embedding tables (rows travel from their owner); once per epoch"""
+        if self.world == 1 or not isinstance(self.transport, NcclTransport):
+            return
+        m, P = self.model, self.plan
+        with torch.no_grad():
+            for r in range(self.world):
+                lo, hi = P.users(r)
+                if hi > lo:
+                    dist.broadcast(m.uEmbd.weight.data[lo:hi], src=r)
+                lo, hi = P.items(r)
+                if hi > lo:
+                    dist.broadcast(m.iEmbd.weight.data[lo:hi], src=r)
+        step = float(self.adam_state[0].item())
+        for p in self.params:
+            self.optim.state[p]["step"] = torch.tensor(step)
+
+    # ------------------------------------------------------------------------------------------
+    def profile_phases(self, n_steps=5):
+        """CUDA-event time of every phase of the step (eager, phases back to back): [(kind, name, ms)] averaged over n_steps.
+        State is restored afterwards."""
+        droprate, seed = self._mode()
+        plan = self._plan(droprate, seed)
+        snap = self._snapshot()
+        self._run_eager(plan)
+        torch.cuda.synchronize(self.dev)
+        evs = []
+        for _ in range(n_steps):
+            row = []
+            for ph in plan:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if ph[0] == "k":
+                    ph[2]()
+                else:
+                    self._collective(ph[2], ph[3])
+                e1.record()
+                row.append((e0, e1))
+            evs.append(row)
+        torch.cuda.synchronize(self.dev)
+        out = []
+        for j, ph in enumerate(plan):
+            ms = sum(evs[i][j][0].elapsed_time(evs[i][j][1]) for i in range(n_steps)) / n_steps
+            nbytes = sum(t.numel() * t.element_size() for t in ph[3]) if ph[0] == "c" else 0
+            out.append(dict(kind="collective" if ph[0] == "c" else "compute", name=ph[1], ms=ms, bytes=nbytes))
+        self._restore(snap)
+        return out
+
     def launches_per_step(self, droprate):
-        S = len(self.props[0].p.stages)
-        per_prop = (2 * S if droprate > 0 else 0) + S * 4 + 1 + 1 + S * (2 + 2 + 1 + 4)
-        return 1 + 2 * per_prop + 1 + 2 + 2 + len(self._replicated)
+        S = len(self.stages)
+        per_prop = (1 if droprate > 0 else 0) + S * (2 + 1 + 1) + 1 + 2 + 1 + S * (2 + 2 + 1 + 4)
+        return 1 + 2 * per_prop + 1 + 2 + 2
 
     def units_per_step(self):
-        return 2 * self.shard.E          # strong scaling: the same global step on every world size
+        return 2 * self.plan.E           # strong scaling: the same global step on every world size
 
     def parallelism(self):
-        return "users range-partitioned over %d GPUs by edge count (rank 0: users [%d,%d), %d of %d edges); item partials: NCCL all-reduce per stage" % (
-            self.world, self.shard.u_lo, self.shard.u_hi, self.shard.local_edges, self.shard.E)
+        return ("users range-partitioned over %d GPUs by edge count (rank %d: users [%d,%d), %d of %d edges), item rows owned by range "
+                "(%d per rank); per stage: all-gather of the item rows, reduce-scatter of the item partials; %s" % (
+                    self.world, self.rank, self.u_lo, self.u_hi, self.e_hi - self.e_lo, self.plan.E, self.plan.chunk, self.capture_mode))
 
     def working_set_bytes(self):
-        N, E = self.g.N, self.shard.local_edges
-        return 2 * (8 * N * 256 + 8 * E * 4) + 7 * self.adam_total * 4
+        N = self.U + self.plan.I_pad
+        return 2 * (9 * N * 256 + 8 * (self.e_hi - self.e_lo) * 4) + 7 * self.adam_total * 4
 
     def profile_kernels(self, n_steps=3):
         return []

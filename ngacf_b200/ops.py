@@ -57,6 +57,30 @@ def dropout_masks(feats, edges, heads, N, E, seed, call, droprate, call_dev=None
     _lib.call("ngacf_dropout_masks", fa, ea, ha, S, int(N), int(E), int(seed), int(call) & 0xFFFFFFFF, _p(call_dev), float(droprate), _s())
 
 
+def dropout_masks_ranges(feats, edges, heads, node_ranges, edge_range, seed, call, droprate, call_dev=None):
+    """masks of the node ranges [(a0,b0),(a1,b1)] and the edge range (e0,e1) only, written at their global positions"""
+    S = len(heads)
+    fa = (ctypes.c_void_p * S)(*[f.data_ptr() for f in feats])
+    ea = (ctypes.c_void_p * S)(*[e.data_ptr() for e in edges])
+    ha = (ctypes.c_int32 * S)(*[int(h) for h in heads])
+    (a0, b0), (a1, b1) = node_ranges
+    _lib.call("ngacf_dropout_masks_ranges", fa, ea, ha, S, int(a0), int(b0), int(a1), int(b1), int(edge_range[0]), int(edge_range[1]), int(seed),
+              int(call) & 0xFFFFFFFF, _p(call_dev), float(droprate), _s())
+
+
+def batch_rows_gather(Z, U, users, items, u_range, i_range, Zb):
+    _lib.call("ngacf_batch_rows_gather", _p(Z), int(U), _p(users), _p(items), users.numel(), int(u_range[0]), int(u_range[1]), int(i_range[0]),
+              int(i_range[1]), _p(Zb), _s())
+
+
+def batch_rows_scatter(Zb, U, users, items, Z):
+    _lib.call("ngacf_batch_rows_scatter", _p(Zb), int(U), _p(users), _p(items), users.numel(), _p(Z), _s())
+
+
+def memset_zero(t):
+    _lib.call("ngacf_memset_zero", _p(t), t.numel() * t.element_size(), _s())
+
+
 def transform_fwd(Xu, Xi, apply_elu, featmask, scale, wtab, H, U, I, h, s):
     _lib.call("ngacf_transform_fwd", _p(Xu), _p(Xi), int(apply_elu), _p(featmask), float(scale), _p(wtab), H, U, I, _p(h), _p(s), _s())
 
