@@ -185,8 +185,9 @@ def main():
     ap.add_argument("--split-bwd", action="store_true", help="dense backward as dX (on the chain) + dW/da (gradient stream)")
     ap.add_argument("--eval-mode", default="auto")
     ap.add_argument("--profile-only", action="store_true", help="run a few steps and exit (for ncu)")
-    ap.add_argument("--dist", default="replica", choices=["replica", "shard"],
-                    help="N>1: 'replica' = the reference's --parallel semantics (weak scaling), 'shard' = users range-partitioned (strong scaling)")
+    ap.add_argument("--dist", default="shard", choices=["replica", "shard"],
+                    help="N>1: 'shard' = users range-partitioned, item rows all-gathered / reduce-scattered per stage (north star, strong "
+                         "scaling); 'replica' = the reference's --parallel semantics (every GPU propagates the whole graph, weak scaling)")
     args = ap.parse_args()
     # exactly ONE JSON line may reach stdout: anything native libraries print to fd 1 (e.g. NCCL's version banner) is
     # diverted to stderr; the JSON line is written to the saved descriptor at the end
@@ -268,43 +269,46 @@ def main():
         return
 
     clocks = ClockSampler(local) if rank == 0 else None
+
+    def timed_blocks(run_block, min_total_ms=500.0, max_blocks=64):
+        """K-step blocks, each bracketed by barrier + synchronize and timed with CUDA events (max over ranks), repeated until the
+        timed region adds up to >= 0.5 s (a single 100-step block is ~80 ms: too short for the clock sampler and for a stable
+        number); the reported time is the MEDIAN block."""
+        times = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        while True:
+            barrier()
+            e0.record()
+            run_block()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            times.append(ms)
+            if sum(times) >= min_total_ms or len(times) >= max_blocks:
+                return times
+
     # ---------------- device-resident timed region ----------------
     trainer.run_steps(W)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    trainer.run_steps(K)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / K
+    blocks = timed_blocks(lambda: trainer.run_steps(K))
+    ms_step = float(np.median(blocks)) / K
     units_per_step = trainer.units_per_step()          # propagated edges per step, all ranks
     value = units_per_step / (ms_step / 1000.0)
 
     # ---------------- e2e: host rows in, loss out, every step ----------------
     rows_host = torch.from_numpy(np.ascontiguousarray(tu.astype(np.int32))).pin_memory()
     trainer.run_steps(2, host_rows=rows_host, read_loss=True)
-    barrier()
-    e0.record()
-    trainer.run_steps(K, host_rows=rows_host, read_loss=True)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    blocks_e2e = timed_blocks(lambda: trainer.run_steps(K, host_rows=rows_host, read_loss=True))
+    ms_e2e = float(np.median(blocks_e2e))
     e2e_value = units_per_step / (ms_e2e / K / 1000.0)
     clk = clocks.stop() if clocks else {}
 
     # ---------------- per-kernel live timing (eager, one stream) -> roofline of the dominant kernel ----------------
-    prof = trainer.profile_kernels(3)
-    if not prof:      # sharded trainer: per-kernel timing is taken from the single-GPU run
-        prof = [("ngacf_aggregate_fwd", tuple([None] * 10 + [8]), ms_step)]
+    phases = trainer.profile_phases(5) if hasattr(trainer, "profile_phases") else None
+    prof = trainer.profile_kernels(3) if phases is None else []
     hdr = {"ngacf_transform_fwd": 6, "ngacf_aggregate_fwd": 10, "ngacf_stage_bwd_prep": 4, "ngacf_stage_bwd_edges": 15, "ngacf_transform_bwd": 10,
            "ngacf_transform_bwd_dx": 7, "ngacf_transform_bwd_dw": 9, "ngacf_aggregate_fwd_active": 12, "ngacf_stage_bwd_prep_active": 8,
            "ngacf_stage_bwd_edges_active": 17}
@@ -318,37 +322,58 @@ def main():
         a = agg.setdefault(key, [0.0, 0])
         a[0] += ms
         a[1] += 1
-    nsteps_prof = 3
-    table = sorted(((k, v[0] / nsteps_prof, v[1] / nsteps_prof) for k, v in agg.items()), key=lambda x: -x[1])
-    total_prof = sum(x[1] for x in table)
-    # dominant kernel = the slowest one with a fixed algorithmic-byte model (the pruned last-stage passes move a batch-dependent
-    # number of bytes and are listed in `kernels` with their times only)
-    top_key, top_ms_step, top_n = next(x for x in table if "_active" not in x[0])
-    top_name, top_H = top_key.split("/H")[0], int(top_key.split("/H")[1]) if "/H" in top_key else 0
-    n_params = sum(p.numel() for p in model.parameters())
     pk = peaks()
-    gather = roofline.gather_regime(U, I) and top_name in ("ngacf_aggregate_fwd", "ngacf_stage_bwd_edges_users", "ngacf_stage_bwd_edges_items")
-    top_bytes = (roofline.kernel_bytes_gather(top_name, U, I, E, top_H or 1, True) if gather
-                 else roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params))
-    top_avg_ms = top_ms_step / top_n
-    achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
+    n_params = sum(p.numel() for p in model.parameters())
     step_bytes = (roofline.step_bytes_compulsory(U, I, E, 2, B, 1, 5) if args.train_mode == "neg"
                   else roofline.step_bytes_compulsory(U, I, E, 2, B))
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if args.workload == "gowalla" and os.path.exists(tpath):      # DRAM bytes per launch from the committed ncu --set full capture
-        traffic = json.load(open(tpath)).get(top_key, {}).get("dram_bytes_per_launch")
-    roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
-                peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
-                byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
-                share_of_step=top_ms_step / total_prof,
-                note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by the L2->SM path (0.37-0.61 GB of "
-                     "tex sectors per launch at 6-9 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic <= algorithmic bytes (no "
-                     "re-reads, profiles/ncu_traffic.json); in the HBM regime (sweep-10m/30m) the same kernels reach 0.9-1.06 of the measured "
-                     "HBM peak (profiles/r1e_bench_sweep-30m.json)",
-                step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
-                                frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
-                kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
+    if phases is not None:
+        # partitioned step: real per-phase CUDA-event times (eager, phases back to back) and the collectives' NVLink rates
+        comp = sum(p["ms"] for p in phases if p["kind"] == "compute")
+        coll = [p for p in phases if p["kind"] == "collective"]
+        for p in coll:      # bytes that cross NVLink per rank: (world-1)/world of the buffer for all-gather / reduce-scatter, 2x that for all-reduce
+            f = 2.0 if "all-reduce" in p["name"] else 1.0
+            p["nvlink_GBs_per_rank"] = f * p["bytes"] * (world - 1) / world / (p["ms"] / 1e3) / 1e9 if p["ms"] > 0 else None
+        worst = max(coll, key=lambda p: p["ms"]) if coll else None
+        per_gpu = step_bytes / world / (ms_step / 1e3) / 1e9
+        roof = dict(bound="hbm", kernel="whole partitioned step, per GPU (the dominant KERNELS are those of the N=1 line)", achieved=per_gpu,
+                    peak=pk["hbm"], unit="GB/s", frac=per_gpu / pk["hbm"], traffic=None, peak_source=pk["source"],
+                    byte_model="compulsory step bytes (SURVEY 8d) / world", phases=[dict(p, ms=round(p["ms"], 4)) for p in phases],
+                    compute_ms_eager=comp, collective_ms_eager=sum(p["ms"] for p in coll),
+                    limiting_collective=None if worst is None else dict(name=worst["name"], us=1e3 * worst["ms"], bytes=worst["bytes"],
+                                                                        nvlink_GBs_per_rank=worst["nvlink_GBs_per_rank"]),
+                    step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak_one_gpu=step_bytes / (pk["hbm"] * 1e9) * 1e3))
+    if phases is None:
+        nsteps_prof = 3
+        table = sorted(((k, v[0] / nsteps_prof, v[1] / nsteps_prof) for k, v in agg.items()), key=lambda x: -x[1])
+        total_prof = sum(x[1] for x in table) if table else 0.0
+        # dominant kernel = the slowest one with a fixed algorithmic-byte model (the pruned last-stage passes move a batch-dependent
+        # number of bytes and are listed in `kernels` with their times only)
+        top_key, top_ms_step, top_n = next(x for x in table if "_active" not in x[0])
+        top_name, top_H = top_key.split("/H")[0], int(top_key.split("/H")[1]) if "/H" in top_key else 0
+        n_params = sum(p.numel() for p in model.parameters())
+        pk = peaks()
+        gather = roofline.gather_regime(U, I) and top_name in ("ngacf_aggregate_fwd", "ngacf_stage_bwd_edges_users", "ngacf_stage_bwd_edges_items")
+        top_bytes = (roofline.kernel_bytes_gather(top_name, U, I, E, top_H or 1, True) if gather
+                     else roofline.kernel_bytes(top_name, U, I, E, top_H or 1, True, B, n_params))
+        top_avg_ms = top_ms_step / top_n
+        achieved = top_bytes / (top_avg_ms / 1000.0) / 1e9
+        step_bytes = (roofline.step_bytes_compulsory(U, I, E, 2, B, 1, 5) if args.train_mode == "neg"
+                      else roofline.step_bytes_compulsory(U, I, E, 2, B))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if args.workload == "gowalla" and os.path.exists(tpath):      # DRAM bytes per launch from the committed ncu --set full capture
+            traffic = json.load(open(tpath)).get(top_key, {}).get("dram_bytes_per_launch")
+        roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
+                    peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
+                    byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
+                    share_of_step=top_ms_step / total_prof,
+                    note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by the L2->SM path (0.37-0.61 GB of "
+                         "tex sectors per launch at 6-9 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic <= algorithmic bytes (no "
+                         "re-reads, profiles/ncu_traffic.json); in the HBM regime (sweep-10m/30m) the same kernels reach 0.9-1.06 of the measured "
+                         "HBM peak (profiles/r1e_bench_sweep-30m.json)",
+                    step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
+                                    frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
+                    kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
 
     # ---------------- AllNeg evaluation ----------------
     ev_out = None
@@ -393,7 +418,8 @@ def main():
         for _ in range(3):
             eval_once(False)
         barrier()
-        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
         e0.record()
         for _ in range(reps):
             res, _ = eval_once(False)
@@ -439,7 +465,9 @@ def main():
 
     if rank == 0:
         line = dict(metric="spuigacf_train_propagated_edges_per_s", value=value, unit="edges/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="strong" if (world > 1 and args.dist == "shard") else "weak",
+                    ms_per_step=ms_step, timed_blocks=dict(n=len(blocks), steps_each=K, ms_per_step_min=min(blocks) / K, ms_per_step_max=max(blocks) / K,
+                                                          total_ms=sum(blocks), statistic="median block"),
+                    higher_is_better=True, scaling="strong" if (world > 1 and args.dist == "shard") else "weak",
                     vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=dict(workload=("%s-shape SPUIGACF (U=%d I=%d E=%d d=64, 2 attention stages) " % (args.workload, U, I, E)) +
@@ -455,7 +483,11 @@ def main():
         _STDOUT.write(json.dumps(line) + "\n")
         _STDOUT.flush()
     if world > 1:
-        dist.destroy_process_group()
+        if hasattr(trainer, "release"):
+            trainer.release()
+        dist.barrier()
+        sys.stderr.flush()
+        os._exit(0)       # tearing NCCL down after graph-captured collectives hung on the box: leave without destroy_process_group
 
 
 if __name__ == "__main__":

@@ -159,39 +159,119 @@ class ShardPlan:
         return self.eu[lo:hi], self.ei[lo:hi]
 
 
+class Topology:
+    """Two-level decomposition of a step over `world` GPUs.
+
+    A PairSampling step is two independent propagations (pos, neg: train_eval_Gowalla.py:131-132).  With an even world size the
+    GPUs form two groups of G = world/2: group q runs propagation q, user-range partitioned over its G ranks -- the per-stage
+    exchanges then involve G ranks instead of `world`, carry one propagation instead of two, and at world = 2 disappear
+    altogether (only the batch rows and the gradients cross NVLink).  With an odd world size (or NGACF_DIST_PROP_PARALLEL=0)
+    every rank runs both propagations over the world-wide partition.
+
+      scope "sub"  : the ranks that partition one propagation        (all-gather / reduce-scatter of item rows)
+      scope "pair" : the ranks holding the SAME row ranges in the two groups (sum of the pos and neg embedding gradients)
+      scope "world": everyone                                         (batch rows, attention-parameter gradients)"""
+
+    def __init__(self, rank: int, world: int, prop_parallel=None):
+        import os
+        if prop_parallel is None:
+            prop_parallel = os.environ.get("NGACF_DIST_PROP_PARALLEL", "1") != "0"
+        self.rank, self.world = int(rank), int(world)
+        self.prop_parallel = bool(prop_parallel) and world % 2 == 0 and world >= 2
+        self.G = world // 2 if self.prop_parallel else world       # ranks per partition
+        self.props = [rank // self.G] if self.prop_parallel else [0, 1]
+        self.sub_rank = rank % self.G
+
+    def members(self, scope, rank=None):
+        r = self.rank if rank is None else rank
+        if scope == "world":
+            return list(range(self.world))
+        if scope == "sub":
+            base = (r // self.G) * self.G
+            return list(range(base, base + self.G))
+        if scope == "pair":
+            return [r % self.G, r % self.G + self.G] if self.prop_parallel else [r]
+        raise KeyError(scope)
+
+    def rank_in(self, scope, rank=None):
+        r = self.rank if rank is None else rank
+        return self.members(scope, r).index(r)
+
+
 class NcclTransport:
     """In-place collectives over torch.distributed (NCCL over NVLink / NVSwitch on the box; gloo in the CPU tests, where the two
     tensor collectives gloo lacks are expressed through all_gather / all_reduce)."""
 
-    def __init__(self):
+    def __init__(self, topo: Topology = None):
+        import os
         self.rank, self.world = world_info()
         self.gloo = dist.is_initialized() and dist.get_backend() == "gloo"
+        self.coalesce = os.environ.get("NGACF_DIST_COALESCE", "1") != "0"
+        self.topo = topo if topo is not None else Topology(self.rank, self.world)
+        self._groups = {"world": None}
+        if self.world > 1 and self.topo.prop_parallel:
+            # every rank creates every group, in the same order
+            G = self.topo.G
+            for q in range(2):
+                pg = dist.new_group(list(range(q * G, (q + 1) * G)))
+                if self.rank // G == q:
+                    self._groups["sub"] = pg
+            for r in range(G):
+                pg = dist.new_group([r, r + G])
+                if self.rank % G == r:
+                    self._groups["pair"] = pg
+        else:
+            self._groups["sub"] = None
+            self._groups["pair"] = None
 
-    def all_gather_rows(self, tensors, chunk):
-        """every tensor is (world*chunk, w): rank r's rows [r*chunk,(r+1)*chunk) are valid and are sent to every rank"""
-        r = self.rank
-        for t in tensors:
-            own = t[r * chunk:(r + 1) * chunk]
-            if self.gloo:
-                parts = [torch.empty_like(own) for _ in range(self.world)]
-                dist.all_gather(parts, own.contiguous())
+    def _coalesced(self, dev, group):
+        """one NCCL group launch for the calls issued inside (ncclGroupStart/End): a collective point of the step exchanges
+        several arrays (h | s, Ghat | dN, ...); issued one by one they cost one launch latency each"""
+        import contextlib
+        cm = getattr(dist, "_coalescing_manager", None)
+        if self.gloo or cm is None or not self.coalesce:
+            return contextlib.nullcontext()
+        return cm(group=group, device=dev)
+
+    def all_gather_rows(self, tensors, chunk, scope="sub"):
+        """every tensor is (n*chunk, w): the rows [r*chunk,(r+1)*chunk) of rank-in-scope r are valid and are sent to the scope"""
+        members = self.topo.members(scope)
+        if len(members) == 1 or not tensors:
+            return
+        r, pg = self.topo.rank_in(scope), self._groups[scope]
+        if self.gloo:
+            for t in tensors:
+                own = t[r * chunk:(r + 1) * chunk]
+                parts = [torch.empty_like(own) for _ in members]
+                dist.all_gather(parts, own.contiguous(), group=pg)
                 for q, part in enumerate(parts):
                     t[q * chunk:(q + 1) * chunk].copy_(part)
-            else:
-                dist.all_gather_into_tensor(t, own)
+            return
+        with self._coalesced(tensors[0].device, pg):
+            for t in tensors:
+                dist.all_gather_into_tensor(t, t[r * chunk:(r + 1) * chunk], group=pg)
 
-    def reduce_scatter_rows(self, tensors, chunk):
-        """every tensor is (world*chunk, w) of per-rank partial sums: afterwards rank r's rows [r*chunk,(r+1)*chunk) hold the sum"""
-        r = self.rank
-        for t in tensors:
-            if self.gloo:
-                dist.all_reduce(t)
-            else:
-                dist.reduce_scatter_tensor(t[r * chunk:(r + 1) * chunk], t)
+    def reduce_scatter_rows(self, tensors, chunk, scope="sub"):
+        """every tensor is (n*chunk, w) of per-rank partial sums: afterwards the rows of rank-in-scope r hold the scope's sum"""
+        members = self.topo.members(scope)
+        if len(members) == 1 or not tensors:
+            return
+        r, pg = self.topo.rank_in(scope), self._groups[scope]
+        if self.gloo:
+            for t in tensors:
+                dist.all_reduce(t, group=pg)
+            return
+        with self._coalesced(tensors[0].device, pg):
+            for t in tensors:
+                dist.reduce_scatter_tensor(t[r * chunk:(r + 1) * chunk], t, group=pg)
 
-    def all_reduce(self, tensors):
-        for t in tensors:
-            dist.all_reduce(t)
+    def all_reduce(self, tensors, scope="world"):
+        if len(self.topo.members(scope)) == 1 or not tensors:
+            return
+        pg = self._groups[scope]
+        with self._coalesced(tensors[0].device, pg):
+            for t in tensors:
+                dist.all_reduce(t, group=pg)
 
 
 class LocalCluster:
@@ -204,7 +284,10 @@ class LocalCluster:
 
     @staticmethod
     def apply(kind, per_rank, chunk):
+        """per_rank: the tensor lists of the members of ONE scope instance, in rank-in-scope order"""
         world = len(per_rank)
+        if world == 1 or not per_rank[0]:
+            return
         for j in range(len(per_rank[0])):
             ts = [per_rank[r][j] for r in range(world)]
             if kind == "ag":
@@ -228,6 +311,18 @@ class LocalCluster:
                 for d in range(world):
                     ts[d].copy_(acc)
 
+    def _collective(self, phase):
+        """phase: the same collective entry of every rank's plan; applied per scope instance"""
+        _, _, kind, _, scope = phase[0]
+        topo = self.trainers[0].topo
+        done = set()
+        for r in range(len(self.trainers)):
+            members = tuple(topo.members(scope, r))
+            if members in done:
+                continue
+            done.add(members)
+            self.apply(kind, [phase[m][3] for m in members], self.trainers[0].plan.chunk)
+
     def run_steps(self, n_steps, read_loss=False):
         losses = []
         plans = None
@@ -245,8 +340,7 @@ class LocalCluster:
                         with torch.cuda.device(tr.dev):
                             fn()
                 else:
-                    _, name, kind, _ = phase[0]
-                    self.apply(kind, [ph[3] for ph in phase], self.trainers[0].plan.chunk)
+                    self._collective(phase)
             for tr in self.trainers:
                 tr._end_step()
             if read_loss:
@@ -258,7 +352,7 @@ class LocalCluster:
     def gather_state(self):
         """state_dict of the whole model assembled from the owners' rows (attention parameters from rank 0)"""
         sd = {k: v.detach().clone() for k, v in self.trainers[0].model.state_dict().items()}
-        for tr in self.trainers:
+        for tr in self.trainers[:self.trainers[0].topo.G]:        # the first partition holds every row once
             sd["uEmbd.weight"][tr.u_lo:tr.u_hi] = tr.model.uEmbd.weight.detach()[tr.u_lo:tr.u_hi]
             sd["iEmbd.weight"][tr.i_lo:tr.i_hi] = tr.model.iEmbd.weight.detach()[tr.i_lo:tr.i_hi]
         return sd
@@ -267,7 +361,7 @@ class LocalCluster:
         """{name: gradient} assembled the same way (after a step: embedding rows from their owners, attention grads summed)"""
         t0 = self.trainers[0]
         out = {"uEmbd.weight": torch.zeros_like(t0.model.uEmbd.weight), "iEmbd.weight": torch.zeros_like(t0.model.iEmbd.weight)}
-        for tr in self.trainers:
+        for tr in self.trainers[:t0.topo.G]:
             out["uEmbd.weight"][tr.u_lo:tr.u_hi] = tr.model.uEmbd.weight.grad[tr.u_lo:tr.u_hi]
             out["iEmbd.weight"][tr.i_lo:tr.i_hi] = tr.model.iEmbd.weight.grad[tr.i_lo:tr.i_hi]
         for name, p in t0.model.named_parameters():
@@ -296,25 +390,33 @@ class ShardedTrainer:
     phases are captured separately and the collectives run eagerly between them (the round-1 structure)."""
 
     def __init__(self, model, inter, edge_u, edge_i, batch_size, optim, sample_seed, use_cuda_graph=True, transport=None, rank=None, world=None,
-                 plan=None):
+                 plan=None, prop_parallel=None):
         from .graph import BipartiteGraph
         from .propagation import Propagation
-        self.transport = transport if transport is not None else NcclTransport()
-        self.rank = self.transport.rank if rank is None else int(rank)
-        self.world = self.transport.world if world is None else int(world)
+        if transport is None:
+            r0, w0 = world_info()
+            self.topo = Topology(r0, w0, prop_parallel)
+            transport = NcclTransport(self.topo)
+        else:
+            self.topo = Topology(rank, world, prop_parallel)
+        self.transport = transport
+        self.rank, self.world = self.topo.rank, self.topo.world
         self.model, self.inter, self.B, self.optim = model, inter, int(batch_size), optim
         self.sample_seed = int(sample_seed)
         self.use_cuda_graph = use_cuda_graph
         dev = model.uEmbd.weight.device
         self.dev = dev
         U, I = model.userNum, model.itemNum
-        self.plan = plan if plan is not None else ShardPlan(edge_u, edge_i, U, I, self.world)
+        self.plan = plan if plan is not None else ShardPlan(edge_u, edge_i, U, I, self.topo.G)
         P = self.plan
+        if P.world != self.topo.G:
+            raise ValueError("the ShardPlan partitions over %d ranks, the topology needs %d" % (P.world, self.topo.G))
+        sr = self.topo.sub_rank
         self.U, self.I = U, I
-        self.u_lo, self.u_hi = P.users(self.rank)
-        self.i_lo, self.i_hi = P.items(self.rank)
-        self.e_lo, self.e_hi = P.edges(self.rank)
-        eu, ei = P.local_edges(self.rank)
+        self.u_lo, self.u_hi = P.users(sr)
+        self.i_lo, self.i_hi = P.items(sr)
+        self.e_lo, self.e_hi = P.edges(sr)
+        eu, ei = P.local_edges(sr)
         import numpy as np
         with torch.cuda.device(dev):
             self.g = BipartiteGraph(torch.from_numpy(np.stack([eu, ei])).to(dev), U, I, check_users=False)
@@ -425,14 +527,21 @@ class ShardedTrainer:
         scale = 1.0 / (1.0 - droprate) if droprate > 0 else 1.0
         plan = []
 
-        def both(fn):
-            """fn(k) for the pos propagation on the current stream and the neg propagation on the side stream"""
+        mine = list(self.topo.props)            # the propagations this rank runs: [0, 1], or [q] in the propagation-parallel layout
+
+        def both(fn, props=None):
+            """fn(q) for each propagation of this rank: the first on the current stream, the second on the side stream"""
+            qs = mine if props is None else props
+
             def run():
+                if len(qs) == 1:
+                    fn(qs[0])
+                    return
                 cur = torch.cuda.current_stream()
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    fn(1)
-                fn(0)
+                    fn(qs[1])
+                fn(qs[0])
                 cur.wait_stream(side)
             return run
 
@@ -470,14 +579,14 @@ class ShardedTrainer:
                                       p.h[k][U + ilo:U + ihi], p.s[k][U + ilo:U + ihi])
             plan.append(("k", "transform%d" % k, both(transform)))
             plan.append(("c", "all-gather h|s items, stage %d" % k, "ag",
-                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].h[k], self.props[q].s[k])]))
+                         [self._items_view(t) for q in mine for t in (self.props[q].h[k], self.props[q].s[k])], "sub"))
 
             def aggregate(q, k=k, H=H):
                 p = self.props[q]
                 ops.aggregate_fwd(g, p.scratch, p.counter, p.h[k], p.s[k], H, p.edgemask[k], p.scale, p.Z[k], p.norm[k], partial_from=g.T_users)
             plan.append(("k", "aggregate%d" % k, both(aggregate)))
             plan.append(("c", "reduce-scatter Z|norm items, stage %d" % k, "rs",
-                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].Z[k], self.props[q].norm[k])]))
+                         [self._items_view(t) for q in mine for t in (self.props[q].Z[k], self.props[q].norm[k])], "sub"))
 
             def finalize(q, k=k, H=H):
                 p = self.props[q]
@@ -487,7 +596,10 @@ class ShardedTrainer:
                     ops.batch_rows_gather(p.Z[k], U, self.users, items[q], (ulo, uhi), (ilo, ihi), self.Zb[q])
             plan.append(("k", "finalize%d" % k, both(finalize)))
 
-        plan.append(("c", "all-reduce batch rows", "ar", [self.Zb]))
+        if len(mine) == 1:
+            other = 1 - mine[0]
+            plan.append(("k", "zero the other propagation's batch rows", lambda: ops.memset_zero(self.Zb[other])))
+        plan.append(("c", "all-reduce batch rows", "ar", [self.Zb], "world"))
 
         def score(q):
             p = self.props[q]
@@ -495,7 +607,7 @@ class ShardedTrainer:
             ops.score_pairs(p.ZS, U, self.users, items[q], self.sc[q])
 
         def loss_and_scatter():
-            both(score)()
+            both(score, [0, 1])()               # every rank scores both propagations' pairs (the loss needs both)
             ops.bpr_loss(self.sc[0], self.sc[1], 1.0, self.loss, self.dsc[0], self.dsc[1])
 
             def scatter(q):
@@ -525,7 +637,7 @@ class ShardedTrainer:
                                        p.Ghat[U + ilo:U + ihi], p.dN[k][U + ilo:U + ihi])
             plan.append(("k", "prep%d" % k, both(prep)))
             plan.append(("c", "all-gather Ghat|dN items, stage %d" % k, "ag",
-                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].Ghat, self.props[q].dN[k])]))
+                         [self._items_view(t) for q in mine for t in (self.props[q].Ghat, self.props[q].dN[k])], "sub"))
 
             def edges(q, k=k, H=H, Gi=Gi):
                 p = self.props[q]
@@ -534,7 +646,7 @@ class ShardedTrainer:
                                         self.wtabs[k], p.ds, p.dh, p.dS[k], partial=mode)
             plan.append(("k", "edges%d" % k, both(edges)))
             plan.append(("c", "reduce-scatter dh|dS items, stage %d" % k, "rs",
-                         [self._items_view(t) for q in (0, 1) for t in (self.props[q].dh, self.props[q].dS[k])]))
+                         [self._items_view(t) for q in mine for t in (self.props[q].dh, self.props[q].dS[k])], "sub"))
 
             def dense(k=k, H=H, Gi=Gi):
                 cur = torch.cuda.current_stream()
@@ -548,7 +660,7 @@ class ShardedTrainer:
                     # weight gradients always ACCUMULATE into the (zero-filled) flat buffer: a rank may own no rows of a side
                     p = self.props[q]
                     Gprev = p.G[1 - Gi]
-                    acc = int(q == 1)
+                    acc = int(mine.index(q) > 0)       # the first propagation of this rank writes the embedding gradients
                     fm = p.featmask[k]
                     fu = None if fm is None else fm[ulo:]
                     fi = None if fm is None else fm[U + ilo:]
@@ -567,6 +679,10 @@ class ShardedTrainer:
                         if ni:
                             ops.transform_bwd(p.dh[U + ilo:U + ihi], p.dS[k][U + ilo:U + ihi], None, None, iE[ilo:ihi], 0, fi, p.scale, self.wtabs[k],
                                               self.gtabs[k], H, 0, ni, None, dI[ilo:ihi], acc, 1, p.ws)
+                if len(mine) == 1:
+                    fin(mine[0])
+                    tb(mine[0])
+                    return
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     fin(1)
@@ -579,7 +695,11 @@ class ShardedTrainer:
                 cur.wait_stream(side)
             plan.append(("k", "dense-bwd%d" % k, dense))
 
-        plan.append(("c", "all-reduce attention-parameter grads", "ar", [self.flat_small]))
+        if self.topo.prop_parallel:
+            # the two groups hold the pos and the neg contribution to the SAME embedding rows: summed between counterparts
+            pair = [t for t in (dU[ulo:uhi] if nu else None, dI[ilo:ihi] if ni else None) if t is not None]
+            plan.append(("c", "all-reduce pos+neg embedding gradients of the own rows (pair)", "ar", pair, "pair"))
+        plan.append(("c", "all-reduce attention-parameter grads", "ar", [self.flat_small], "world"))
 
         def update():
             h = self.hyper
@@ -595,16 +715,16 @@ class ShardedTrainer:
             if ph[0] == "k":
                 ph[2]()
             else:
-                self._collective(ph[2], ph[3])
+                self._collective(ph[2], ph[3], ph[4])
 
-    def _collective(self, kind, tensors):
+    def _collective(self, kind, tensors, scope):
         t = self.transport
         if kind == "ag":
-            t.all_gather_rows(tensors, self.plan.chunk)
+            t.all_gather_rows(tensors, self.plan.chunk, scope)
         elif kind == "rs":
-            t.reduce_scatter_rows(tensors, self.plan.chunk)
+            t.reduce_scatter_rows(tensors, self.plan.chunk, scope)
         else:
-            t.all_reduce(tensors)
+            t.all_reduce(tensors, scope)
 
     def _snapshot(self):
         st = self.optim.state
@@ -655,7 +775,7 @@ class ShardedTrainer:
                 want = "segments"
         if want == "segments":
             segs, cur = [], []
-            for ph in plan + [("c", "end", None, None)]:
+            for ph in plan + [("c", "end", None, None, None)]:
                 if ph[0] == "k":
                     cur.append(ph[2])
                     continue
@@ -667,7 +787,7 @@ class ShardedTrainer:
                     segs.append(gr.replay)
                     cur = []
                 if ph[2] is not None:
-                    segs.append(lambda kind=ph[2], ts=ph[3]: self._collective(kind, ts))
+                    segs.append(lambda kind=ph[2], ts=ph[3], sc=ph[4]: self._collective(kind, ts, sc))
             self._segments = segs
             self.capture_mode = "CUDA-graph segments, eager collectives"
         self._restore(snap)
@@ -675,6 +795,11 @@ class ShardedTrainer:
     def _prepare_run(self):
         self.row_dev.copy_(torch.tensor([self._cursor, 0], dtype=torch.int64))
         self.call_dev.fill_(self.model._call)
+
+    def release(self):
+        """drop the captured graph(s) (they hold NCCL work): call before dist.destroy_process_group()"""
+        torch.cuda.synchronize(self.dev)
+        self._graph, self._segments, self._key = None, None, None
 
     def _begin_step(self):
         if self._cursor + self.B > len(self.inter):
@@ -734,13 +859,12 @@ class ShardedTrainer:
             return
         m, P = self.model, self.plan
         with torch.no_grad():
-            for r in range(self.world):
-                lo, hi = P.users(r)
-                if hi > lo:
-                    dist.broadcast(m.uEmbd.weight.data[lo:hi], src=r)
-                lo, hi = P.items(r)
-                if hi > lo:
-                    dist.broadcast(m.iEmbd.weight.data[lo:hi], src=r)
+            for r in range(self.topo.G):          # the ranks of the first partition hold every row once
+                for w, (lo, hi) in ((m.uEmbd.weight, P.users(r)), (m.iEmbd.weight, P.items(r))):
+                    if hi > lo:        # parameters and Adam moments: rank 0's checkpoint is then the whole model + optimizer
+                        st = self.optim.state[w]
+                        for t in (w.data, st["exp_avg"], st["exp_avg_sq"]):
+                            dist.broadcast(t[lo:hi], src=r)
         step = float(self.adam_state[0].item())
         for p in self.params:
             self.optim.state[p]["step"] = torch.tensor(step)
@@ -763,7 +887,7 @@ class ShardedTrainer:
                 if ph[0] == "k":
                     ph[2]()
                 else:
-                    self._collective(ph[2], ph[3])
+                    self._collective(ph[2], ph[3], ph[4])
                 e1.record()
                 row.append((e0, e1))
             evs.append(row)
@@ -772,7 +896,8 @@ class ShardedTrainer:
         for j, ph in enumerate(plan):
             ms = sum(evs[i][j][0].elapsed_time(evs[i][j][1]) for i in range(n_steps)) / n_steps
             nbytes = sum(t.numel() * t.element_size() for t in ph[3]) if ph[0] == "c" else 0
-            out.append(dict(kind="collective" if ph[0] == "c" else "compute", name=ph[1], ms=ms, bytes=nbytes))
+            out.append(dict(kind="collective" if ph[0] == "c" else "compute", name=ph[1], ms=ms, bytes=nbytes,
+                            ranks=len(self.topo.members(ph[4])) if ph[0] == "c" else 1))
         self._restore(snap)
         return out
 
@@ -785,9 +910,11 @@ class ShardedTrainer:
         return 2 * self.plan.E           # strong scaling: the same global step on every world size
 
     def parallelism(self):
-        return ("users range-partitioned over %d GPUs by edge count (rank %d: users [%d,%d), %d of %d edges), item rows owned by range "
-                "(%d per rank); per stage: all-gather of the item rows, reduce-scatter of the item partials; %s" % (
-                    self.world, self.rank, self.u_lo, self.u_hi, self.e_hi - self.e_lo, self.plan.E, self.plan.chunk, self.capture_mode))
+        lay = ("2 groups of %d GPUs (group q runs propagation q)" % self.topo.G) if self.topo.prop_parallel else "both propagations on every GPU"
+        return ("%d GPUs: %s; users range-partitioned over %d ranks by edge count (rank %d: users [%d,%d), %d of %d edges), item rows owned by "
+                "range (%d per rank); per stage: all-gather of the item rows, reduce-scatter of the item partials; %s" % (
+                    self.world, lay, self.topo.G, self.rank, self.u_lo, self.u_hi, self.e_hi - self.e_lo, self.plan.E, self.plan.chunk,
+                    self.capture_mode))
 
     def working_set_bytes(self):
         N = self.U + self.plan.I_pad

@@ -9,6 +9,7 @@ TensorBoard scalar tags (:139,149-153).  Example (the reference's README smoke t
 import argparse
 import ast
 import os
+import sys
 import time
 
 import numpy as np
@@ -48,6 +49,11 @@ def createModels(args, userNum, itemNum):
     return model, lossfn, optim
 
 
+class _NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+
 def _writer(args):
     comment = "_DS:{}_M:{}_E:{}_L:{}_lr:{}_wd:{}_dp:{}_rs:{}_parallel:{}".format(
         args.dataset, args.model, args.embedSize, args.layers, args.lr, args.weight_decay, args.droprate, args.seed, args.parallel)
@@ -55,14 +61,12 @@ def _writer(args):
         from torch.utils.tensorboard import SummaryWriter
         return SummaryWriter(comment=comment)
     except Exception:
-        class _Null:
-            def add_scalar(self, *a, **k):
-                pass
-        return _Null()
+        return _NullWriter()
 
 
 def main(args):
-    summaryWriter = _writer(args)
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+    summaryWriter = _writer(args) if rank0 else _NullWriter()
     train_df, test_df, train_pos_neg, test_pos_neg, userNum, itemNum, adj = prepareData(args)
     print("adj.shape", tuple(adj.shape))
     model, lossfn, optim = createModels(args, userNum, itemNum)
@@ -71,6 +75,8 @@ def main(args):
         checkpoint = torch.load("ckpts/{}_{}_{:03d}.pkl".format(args.model, args.dataset, args.resume_from), map_location="cuda")
         model.load_state_dict(checkpoint["model"])
         optim.load_state_dict(checkpoint["optim"])
+        # the dropout stream counter resumes where the saved run stopped (one call per propagation, two per PairSampling step)
+        model._call = int(checkpoint.get("dropout_calls", 0))
         print("=> loaded checkpoint '{}'".format("ckpts/{}_{:03d}.pkl".format(args.model, args.resume_from)))
     for epoch in range(args.resume_from, args.epochs):
         t0 = time.time()
@@ -79,8 +85,10 @@ def main(args):
                               sample_seed=args.seed)
         summaryWriter.add_scalar("loss/train_loss", train_loss, epoch)
         print("------epoch:{}, train_loss:{:5f}, time consuming:{}s".format(epoch, train_loss, time.strftime("%H: %M: %S", time.gmtime(time.time() - t0))))
-        if (epoch + 1) % args.save_every == 0:
-            torch.save({"model": model.state_dict(), "optim": optim.state_dict()}, "ckpts/{}_{}_{:03d}.pkl".format(args.model, args.dataset, epoch + 1))
+        if (epoch + 1) % args.save_every == 0 and rank0:
+            # the reference's two keys (run_Gowalla.py:142-143) + the position of the dropout streams (ignored by the reference's loader)
+            torch.save({"model": model.state_dict(), "optim": optim.state_dict(), "dropout_calls": int(model._call)},
+                       "ckpts/{}_{}_{:03d}.pkl".format(args.model, args.dataset, epoch + 1))
         if (epoch + 1) % args.eval_every == 0:
             t0 = time.time()
             if args.eval_mode == "SampledNeg":        # run_Gowalla.py:155-160
@@ -117,19 +125,36 @@ def build_parser():
     p.add_argument("--seed", type=int, default=2019)
     p.add_argument("--embedSize", type=int, default=64)
     p.add_argument("--layers", type=ast.literal_eval, default=[64, 64])
-    p.add_argument("--train_mode", type=str, default="PairSampling")
-    p.add_argument("--eval_mode", type=str, default="AllNeg")
+    p.add_argument("--train_mode", type=str, default="NegSampling")       # the reference's defaults (run_Gowalla.py:179-180)
+    p.add_argument("--eval_mode", type=str, default="SampledNeg")
     p.add_argument("--parallel", type=ast.literal_eval, default=False)
     p.add_argument("--gpu_id", type=str, default="0")
     p.add_argument("--data_root", type=str, default=None, help="directory holding 1K/u.data, Gowalla/g_train.csv, ... (default ./data)")
     return p
 
 
+def init_parallel(args):
+    """--parallel True under torchrun: one process per GPU over NCCL (replaces the thread-per-GPU DataParallelModel of
+    parallel.py:94-130; run_Gowalla.py:104-112).  Launch: torchrun --nproc_per_node=N run_Gowalla.py --parallel True ..."""
+    if args.parallel and "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return True
+    os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_id
+    return False
+
+
 if __name__ == "__main__":
     args = build_parser().parse_args()
     print("----------------Parallel Mode is %s----------------" % ("enabled" if args.parallel else "disabled."))
-    os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_id
+    multi = init_parallel(args)
     torch.manual_seed(args.seed)
     torch.cuda.manual_seed_all(args.seed)
     np.random.seed(args.seed)
     main(args)
+    if multi:
+        sys.stdout.flush()
+        os._exit(0)        # NCCL teardown after graph-captured collectives can hang: leave without destroy_process_group

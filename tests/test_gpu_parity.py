@@ -754,14 +754,16 @@ def test_optimizer_hyperparameters_follow_param_groups(monkeypatch):
 # multi-GPU partition (round 2), checked on ONE GPU: every rank of the user-range partition lives in this process and the
 # collectives are applied to the ranks' buffers directly (ngacf_b200.dist.LocalCluster); the NCCL run only swaps the transport
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("world,droprate", [(2, 0.2), (3, 0.0), (4, 0.2)])
-def test_sharded_partition_equals_single_gpu(world, droprate, monkeypatch):
+@pytest.mark.parametrize("world,droprate,prop_parallel", [(2, 0.2, True), (2, 0.2, False), (3, 0.0, False), (4, 0.2, True), (4, 0.0, False),
+                                                          (6, 0.2, True)])
+def test_sharded_partition_equals_single_gpu(world, droprate, prop_parallel, monkeypatch):
     """Users range-partitioned by edge count, item rows owned by range, item rows all-gathered and item partials
-    reduce-scattered per stage: loss and EVERY gradient of one step equal the single-GPU step's (same batch, same
+    reduce-scattered per stage, optionally with the pos and the neg propagation on two groups of GPUs
+    (prop_parallel): loss and EVERY gradient of one step equal the single-GPU step's (same batch, same
     Philox dropout streams, 2e-5 relative), and the losses of further Adam steps follow the single-GPU run."""
     from ngacf_b200 import hostdata
     from ngacf_b200.data import Interactions
-    from ngacf_b200.dist import LocalCluster, ShardedTrainer, ShardPlan
+    from ngacf_b200.dist import LocalCluster, ShardedTrainer, ShardPlan, Topology
     from ngacf_b200.model import SPUIGACF
     from ngacf_b200.optim import FusedAdam
     U, I, E, batch = 1500, 2501, 60000, 512          # I is not a multiple of the world size: the last item range is ragged
@@ -781,8 +783,10 @@ def test_sharded_partition_equals_single_gpu(world, droprate, monkeypatch):
     model2, tr2 = _fused_trainer(U, I, u, i, tu, ti, su, si, sd, droprate, batch, False, monkeypatch)
     ref_losses = tr2.run_steps(4, read_loss=True)
     # the partition
-    plan = ShardPlan(u, i, U, I, world)
-    assert plan.ub[0] == 0 and plan.ub[-1] == U and plan.eb[-1] == E and plan.I_pad >= I and plan.chunk * (world - 1) < I
+    topo = Topology(0, world, prop_parallel)
+    assert topo.prop_parallel == prop_parallel and topo.G == (world // 2 if prop_parallel else world)
+    plan = ShardPlan(u, i, U, I, topo.G)
+    assert plan.ub[0] == 0 and plan.ub[-1] == U and plan.eb[-1] == E and plan.I_pad >= I and plan.chunk * (topo.G - 1) < I
     trainers = []
     for r in range(world):
         mr = SPUIGACF(U, I, 64, [64, 64], droprate)
@@ -792,7 +796,7 @@ def test_sharded_partition_equals_single_gpu(world, droprate, monkeypatch):
         dit = Interactions.from_arrays(U, I, tu, ti, su, si, device=DEV)
         opt = FusedAdam(mr.parameters(), lr=0.01, weight_decay=1e-6)
         trainers.append(ShardedTrainer(mr, dit, u, i, batch, opt, sample_seed=5, use_cuda_graph=False, transport=object(), rank=r, world=world,
-                                       plan=plan))
+                                       plan=plan, prop_parallel=prop_parallel))
     cluster = LocalCluster(trainers)
     losses = cluster.run_steps(1, read_loss=True)
     assert abs(losses[0] - ref_loss) <= 2e-6 * abs(ref_loss)
@@ -805,3 +809,43 @@ def test_sharded_partition_equals_single_gpu(world, droprate, monkeypatch):
     sd_got = cluster.gather_state()
     for k in sd_ref:
         assert rel_err(sd_got[k].cpu().numpy(), sd_ref[k]) < 5e-3, k
+
+
+# ------------------------------------------------------------------------------------------------
+# the drop-in CLI (run_Gowalla.py:118-160 of the reference): train, evaluate, save, resume
+# ------------------------------------------------------------------------------------------------
+def test_cli_run_gowalla_train_eval_save_resume(tmp_path, monkeypatch, capsys):
+    """run_Gowalla.main with the reference's flags on a small synthetic dataset: two epochs straight == one epoch + `--resume_from 1`
+    (checkpoint naming ckpts/{model}_{dataset}_{epoch:03d}.pkl with the reference's two keys; model, Adam state, sampler epoch and
+    dropout streams all resume), the printed lines keep the reference's format, the metrics dict has its keys."""
+    import run_Gowalla as R
+    monkeypatch.chdir(tmp_path)
+    flags = ["--dataset", "synth-tiny", "--model", "SPUIGACF", "--adj_type", "ui_mat", "--train_mode", "PairSampling", "--eval_mode", "AllNeg",
+             "--lr", "0.002", "--weight_decay", "0.000001", "--droprate", "0.2", "--batch_size", "2048", "--eval_every", "1", "--save_every", "1",
+             "--parallel", "False"]
+
+    def run(extra):
+        args = R.build_parser().parse_args(flags + extra)
+        torch.manual_seed(args.seed)
+        torch.cuda.manual_seed_all(args.seed)
+        np.random.seed(args.seed)
+        R.main(args)
+        return capsys.readouterr().out
+    out2 = run(["--epochs", "2"])
+    assert "------epoch:1, train_loss:" in out2 and "metrics:" in out2 and "userNum:2000, itemNum:3000" in out2
+    ck = torch.load(tmp_path / "ckpts" / "SPUIGACF_synth-tiny_002.pkl", map_location="cpu", weights_only=False)
+    assert {"model", "optim"} <= set(ck) and set(ck["model"]) >= {"uEmbd.weight", "iEmbd.weight", "gat.attention_0.W_u", "gat.out_att.a"}
+    straight = {k: v.clone() for k, v in ck["model"].items()}
+    # second process: one epoch, then resume for the second
+    (tmp_path / "ckpts" / "SPUIGACF_synth-tiny_002.pkl").unlink()
+    run(["--epochs", "1"])
+    out_r = run(["--epochs", "2", "--resume_from", "1"])
+    assert "=> loaded checkpoint" in out_r and "------epoch:1, train_loss:" in out_r and "------epoch:0," not in out_r
+    resumed = torch.load(tmp_path / "ckpts" / "SPUIGACF_synth-tiny_002.pkl", map_location="cpu", weights_only=False)["model"]
+    for k in straight:
+        assert rel_err(resumed[k].numpy(), straight[k].numpy()) < 1e-6, k
+
+    def loss_of(text, epoch):
+        line = [l for l in text.splitlines() if l.startswith("------epoch:%d," % epoch)][0]
+        return float(line.split("train_loss:")[1].split(",")[0])
+    assert abs(loss_of(out_r, 1) - loss_of(out2, 1)) < 1e-5

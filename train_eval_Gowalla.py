@@ -83,17 +83,18 @@ def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is
     triple per train row from the GPU sampler, two full propagations with independent dropout, BPR,
     backward, optimizer step.  Returns sum(batch-mean loss) / len(train_df) like the reference (:139,144).
     `epoch`/`sample_seed` select the sampler's Philox stream (the reference's sampler is unseeded)."""
-    if is_parallel:
-        raise NotImplementedError("--parallel True (single-process DataParallel, parallel.py) is replaced by one process per GPU: "
-                                  "see ngacf_b200/dist.py and bench.py --gpus N")
     m = _unwrap(model)
     model.train()
     inter = _interactions(model, train_df, train_pos_neg)
     dev = m.uEmbd.weight.device
-    adj_t = _device_adj(model, adj)
-    graph = m.graph_for(adj_t)
     if sample_seed is None:
         sample_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    if is_parallel and _world() > 1:
+        return _train_bpr_parallel(m, batch_size, inter, adj, optim, lossfn, epoch, sample_seed, max_steps)
+    # --parallel True in a single process: the reference scatters over torch.cuda.device_count() GPUs in one process
+    # (parallel.py); here the multi-GPU modes are one process per GPU (torchrun), so a lone process is the one-GPU step
+    adj_t = _device_adj(model, adj)
+    graph = m.graph_for(adj_t)
     if fused is None:
         fused = os.environ.get("NGACF_FUSED", "1") != "0"
     if fused and _fused_ok(m, optim, lossfn):
@@ -134,6 +135,34 @@ def train_bpr(model, batch_size, train_df, train_pos_neg, adj, optim, lossfn, is
     return float(total.item()) / n
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _train_bpr_parallel(m, batch_size, inter, adj, optim, lossfn, epoch, sample_seed, max_steps):
+    """--parallel True under torchrun (one process per GPU).  NGACF_PARALLEL_MODE:
+      shard   (default) users range-partitioned, item rows all-gathered / reduce-scattered per stage (ngacf_b200.dist.ShardedTrainer):
+              the SAME step as one GPU on the same batch, split over the GPUs (the tail batch of len % batch rows is dropped);
+      replica the reference's own --parallel semantics (parallel.py, train_eval_Gowalla.py:97-104,137): every GPU propagates the
+              whole graph and scores its own batch_size rows, gradients are summed (ngacf_b200.dist.ReplicaTrainer)."""
+    from ngacf_b200.dist import ReplicaTrainer, ShardedTrainer
+    if not _fused_ok(m, optim, lossfn):
+        raise NotImplementedError("--parallel True needs the fused step: SPUIGACF + BPRLoss + a single-group Adam over model.parameters()")
+    mode = os.environ.get("NGACF_PARALLEL_MODE", "shard")
+    tr = getattr(m, "_parallel_trainer", None)
+    key = (mode, id(inter), id(adj), int(batch_size), id(optim), int(sample_seed))
+    if tr is None or tr.key != key:
+        if mode == "replica":
+            tr = ReplicaTrainer(m, inter, m.graph_for(_device_adj(m, adj)), batch_size, optim, sample_seed)
+        else:
+            idx = np.asarray(adj.cpu() if torch.is_tensor(adj) else adj).reshape(2, -1)
+            tr = ShardedTrainer(m, inter, idx[0], idx[1], batch_size, optim, sample_seed)
+        tr.key = key
+        m._parallel_trainer = tr
+    return tr.train_epoch(epoch, max_steps)
+
+
 def eval_neg_all(model, batch_size, test_df, test_pos_neg, adj, itemNum, is_parallel, mode="auto"):
     """Full-ranking evaluation: every test user against every candidate item (item_pool minus the user's
     train items), top-20, precision/recall/ndcg/hit_ratio @ [1,5,10,20] averaged with the reference's
@@ -145,8 +174,15 @@ def eval_neg_all(model, batch_size, test_df, test_pos_neg, adj, itemNum, is_para
     with torch.no_grad():
         Z = m.propagate(adj_t)
         ev = getattr(m, "_evaluator", None)
-        if ev is None or ev.inter is not inter or ev.mode != mode:
-            ev = AllNegEvaluator(inter, mode)
+        world = _world() if is_parallel else 1
+        if ev is None or ev.inter is not inter or ev.mode != mode or getattr(ev, "world", 1) != world:
+            users = None
+            if world > 1:       # users sharded over the ranks; only the 16 metric sums are merged (AllNegEvaluator.metrics)
+                import torch.distributed as dist
+                from ngacf_b200.dist import shard_eval_users
+                users = shard_eval_users(inter.eval_users, dist.get_rank(), world)
+            ev = AllNegEvaluator(inter, mode, users=users)
+            ev.world = world
             m._evaluator = ev
         return ev(Z)
 
