@@ -452,13 +452,20 @@ class ShardedTrainer:
             self.props.append(p)
         self.Zb = torch.zeros((2, 2 * self.B, ops.D), **f32)           # compact batch rows of both propagations (one all-reduce)
         self.users, self.pos, self.neg = torch.zeros(self.B, **i64), torch.zeros(self.B, **i64), torch.zeros(self.B, **i64)
-        self.sc = [torch.zeros(self.B, **f32), torch.zeros(self.B, **f32)]
+        self.sc_all = torch.zeros((2, self.B), **f32)          # pair scores of both propagations (exchanged as scores when G == 1)
+        self.sc = [self.sc_all[0], self.sc_all[1]]
         self.dsc = [torch.zeros(self.B, **f32), torch.zeros(self.B, **f32)]
         self.loss = torch.zeros((), **f32)
         self.total = torch.zeros((), dtype=torch.float64, device=dev)
         self.row_dev = torch.zeros(2, **i64)
         self.call_dev = torch.zeros(1, **i64)
         self.side = torch.cuda.Stream(device=dev)
+        # G == 1 (world 2, propagation-parallel): the propagation is whole on this rank -- no partial sums, and the output stage is
+        # pruned to the batch rows exactly as in the single-GPU trainer (csrc/pruned_stage.cu)
+        import os
+        self.complete = self.topo.G == 1
+        self.prune = self.complete and os.environ.get("NGACF_PRUNE", "1") != "0" and self.stages[-1][0] == 1
+        self.active = {q: ops.ActiveRows(g) for q in self.topo.props} if self.prune else {}
         # parameters: embedding gradients stay with the owner of the row; the attention parameters are replicated and their
         # gradients (partial sums over the own rows) are summed by one small all-reduce
         m = model
@@ -545,8 +552,13 @@ class ShardedTrainer:
                 cur.wait_stream(side)
             return run
 
+        complete, prune = self.complete, self.prune
+
         def head():
             ops.sample_pairs(self.inter, 0, B, self.sample_seed, 0, self.users, self.pos, self.neg, self.row_dev)
+            for q in mine:
+                if prune:      # active rows of propagation q: stamped with its dropout call index (as in train.FusedTrainer)
+                    self.active[q].at(q, self.call_dev).mark(self.users, items[q])
         plan.append(("k", "sample", head))
 
         def masks(k):
@@ -583,23 +595,35 @@ class ShardedTrainer:
 
             def aggregate(q, k=k, H=H):
                 p = self.props[q]
-                ops.aggregate_fwd(g, p.scratch, p.counter, p.h[k], p.s[k], H, p.edgemask[k], p.scale, p.Z[k], p.norm[k], partial_from=g.T_users)
+                if prune and k == S - 1:
+                    ops.aggregate_fwd_active(g, p.scratch, p.counter, p.h[k], p.s[k], H, p.edgemask[k], p.scale, p.Z[k], p.norm[k], self.active[q])
+                else:
+                    ops.aggregate_fwd(g, p.scratch, p.counter, p.h[k], p.s[k], H, p.edgemask[k], p.scale, p.Z[k], p.norm[k],
+                                      partial_from=-1 if complete else g.T_users)
             plan.append(("k", "aggregate%d" % k, both(aggregate)))
             plan.append(("c", "reduce-scatter Z|norm items, stage %d" % k, "rs",
                          [self._items_view(t) for q in mine for t in (self.props[q].Z[k], self.props[q].norm[k])], "sub"))
 
             def finalize(q, k=k, H=H):
                 p = self.props[q]
-                if ni:
+                if ni and not complete:
                     ops.aggregate_finalize(p.Z[k][U + ilo:U + ihi], p.h[k][U + ilo:U + ihi], p.norm[k][U + ilo:U + ihi], H)
                 if k == S - 1:
-                    ops.batch_rows_gather(p.Z[k], U, self.users, items[q], (ulo, uhi), (ilo, ihi), self.Zb[q])
+                    if complete:      # every row is local: score the own propagation's pairs here, exchange SCORES instead of rows
+                        ops.score_pairs(p.Z[k], U, self.users, items[q], self.sc[q])
+                    else:
+                        ops.batch_rows_gather(p.Z[k], U, self.users, items[q], (ulo, uhi), (ilo, ihi), self.Zb[q])
             plan.append(("k", "finalize%d" % k, both(finalize)))
 
-        if len(mine) == 1:
+        if complete:
             other = 1 - mine[0]
-            plan.append(("k", "zero the other propagation's batch rows", lambda: ops.memset_zero(self.Zb[other])))
-        plan.append(("c", "all-reduce batch rows", "ar", [self.Zb], "world"))
+            plan.append(("k", "zero the other propagation's scores", lambda: ops.memset_zero(self.sc[other])))
+            plan.append(("c", "all-reduce pair scores", "ar", [self.sc_all], "world"))
+        else:
+            if len(mine) == 1:
+                other = 1 - mine[0]
+                plan.append(("k", "zero the other propagation's batch rows", lambda: ops.memset_zero(self.Zb[other])))
+            plan.append(("c", "all-reduce batch rows", "ar", [self.Zb], "world"))
 
         def score(q):
             p = self.props[q]
@@ -607,17 +631,20 @@ class ShardedTrainer:
             ops.score_pairs(p.ZS, U, self.users, items[q], self.sc[q])
 
         def loss_and_scatter():
-            both(score, [0, 1])()               # every rank scores both propagations' pairs (the loss needs both)
+            if not complete:
+                both(score, [0, 1])()           # every rank scores both propagations' pairs (the loss needs both)
             ops.bpr_loss(self.sc[0], self.sc[1], 1.0, self.loss, self.dsc[0], self.dsc[1])
 
             def scatter(q):
                 p = self.props[q]
                 G = p.G[0]
-                if nu:
-                    ops.memset_zero(G[ulo:uhi])
-                if ni:
-                    ops.memset_zero(G[U + ilo:U + ihi])
-                ops.score_pairs_bwd(p.ZS, U, self.users, items[q], self.dsc[q], G)      # rows of other owners are written and never read
+                if not prune:      # pruned: the scatter writes exactly the active rows, nothing else of G is read
+                    if nu:
+                        ops.memset_zero(G[ulo:uhi])
+                    if ni:
+                        ops.memset_zero(G[U + ilo:U + ihi])
+                # rows of other owners are written and never read
+                ops.score_pairs_bwd(p.Z[S - 1] if complete else p.ZS, U, self.users, items[q], self.dsc[q], G)
             both(scatter)()
             ops.memset_zero(self.flat_small)        # attention-parameter gradients are accumulated by every dense backward
         plan.append(("k", "scores+loss+scatter", loss_and_scatter))
@@ -630,6 +657,9 @@ class ShardedTrainer:
             def prep(q, k=k, H=H, Gi=Gi):
                 p = self.props[q]
                 G = p.G[Gi]
+                if prune and k == S - 1:
+                    ops.stage_bwd_prep_active(g, G, p.Z[k], p.h[k], p.norm[k], H, p.Ghat, p.dN[k], self.active[q])
+                    return
                 if nu:
                     ops.stage_bwd_prep(G[ulo:uhi], p.Z[k][ulo:uhi], p.h[k][ulo:uhi], p.norm[k][ulo:uhi], H, p.Ghat[ulo:uhi], p.dN[k][ulo:uhi])
                 if ni:
@@ -642,8 +672,12 @@ class ShardedTrainer:
             def edges(q, k=k, H=H, Gi=Gi):
                 p = self.props[q]
                 for mode in (0, 1):
-                    ops.stage_bwd_edges(mode, g, p.scratch, p.counter, p.G[Gi], p.Ghat, p.dN[k], p.h[k], p.s[k], H, p.edgemask[k], p.scale,
-                                        self.wtabs[k], p.ds, p.dh, p.dS[k], partial=mode)
+                    if prune and k == S - 1:
+                        ops.stage_bwd_edges_active(mode, g, p.scratch, p.counter, p.G[Gi], p.Ghat, p.dN[k], p.h[k], p.s[k], H, p.edgemask[k],
+                                                   p.scale, self.wtabs[k], p.ds, p.dh, p.dS[k], self.active[q])
+                    else:
+                        ops.stage_bwd_edges(mode, g, p.scratch, p.counter, p.G[Gi], p.Ghat, p.dN[k], p.h[k], p.s[k], H, p.edgemask[k], p.scale,
+                                            self.wtabs[k], p.ds, p.dh, p.dS[k], partial=0 if complete else mode)
             plan.append(("k", "edges%d" % k, both(edges)))
             plan.append(("c", "reduce-scatter dh|dS items, stage %d" % k, "rs",
                          [self._items_view(t) for q in mine for t in (self.props[q].dh, self.props[q].dS[k])], "sub"))
@@ -653,7 +687,7 @@ class ShardedTrainer:
 
                 def fin(q):
                     p = self.props[q]
-                    if ni:
+                    if ni and not complete:
                         ops.stage_bwd_finalize(p.dh[U + ilo:U + ihi], p.dS[k][U + ilo:U + ihi], p.G[Gi][U + ilo:U + ihi], self.wtabs[k], H, 1)
 
                 def tb(q):
