@@ -430,3 +430,15 @@ def test_build_graph_invariants(U, I, E, seed):
     cols = np.repeat(np.arange(I), np.diff(g.colptr))
     assert np.array_equal(g.eu[g.perm], g.rowidx) and np.array_equal(g.ei[g.perm], cols)
     assert np.array_equal(np.sort(g.perm), np.arange(g.E))
+
+
+def test_port_embeddings_match_reference_fixture(golden):
+    """The oracle port's propagation against the reference's own fp64 features (embeddings_medium.npz): 1e-12."""
+    gz = golden("embeddings_medium")
+    U, I = int(gz["U"]), int(gz["I"])
+    g = port.build_graph(np.stack([gz["edge_u"], gz["edge_i"]]), U, I)
+    sd = {k[3:]: torch.from_numpy(gz[k]) for k in gz.files if k.startswith("sd/")}
+    p = port.params_from_state_dict(sd, torch.float64)
+    F, _ = port.propagate(p, g)
+    ref = gz["features_f64"]
+    assert np.abs(F.numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
