@@ -295,6 +295,17 @@ int ngacf_sample_negs(const int32_t* rows_user, const int32_t* rows_item, const 
 int ngacf_bce_logits_loss(const float* scores, int64_t n, int32_t group, float* loss, float* dscore, void* stream);
 int ngacf_rank_metrics(const float* scores, int64_t n_rows, int32_t group, int32_t top_k, double* sums, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SPUIGAGPCF: GPLayer.forward = torch.sparse.mm(laplacianMat + selfLoop, features) (SPUIGACF.py:174-185) with the
+ * normalised adjacency of buildLaplacianMat (data/loadGowalla.py:197-227).  The Laplacian of the bipartite graph is symmetric and
+ * has the pattern of the unified adjacency plus a diagonal: val[E] holds one value per undirected edge (CSR edge id), diag[N]
+ * one per node (self loop included).  Y = diag (.) X + A_val X over the task list of ngacf_graph_build; the transpose (backward)
+ * is the same call.  X != Y.
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_spmm_sym(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* adj_eid,
+                   const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* val, const float* diag,
+                   const float* X, float* Y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SIGNATURES = {
     "ngacf_batch_rows_gather": (c_int32, [P, c_int32, P, P, c_int32, c_int64, c_int64, c_int64, c_int64, P, P]),
     "ngacf_batch_rows_scatter": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
     "ngacf_memset_zero": (c_int32, [P, c_size_t, P]),
+    "ngacf_spmm_sym": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, P, P, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_step_counters": (c_int32, [P, P, P, c_int64, P]),
     "ngacf_mark_active": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P, P]),

@@ -7,13 +7,19 @@
 // are flagged and recomputed by the caller through the exact CUDA-core entry point.
 // Replaces train_eval_Gowalla.py:300-341,370-385 of the reference.
 //
-// Kernel structure (one CTA = 128 users, persistent over all item tiles; two CTAs per SM overlap):
-//   warps 0-3  epilogue: thread r owns user row r = TMEM lane r; tcgen05.ld 32 columns at a time,
-//              candidate mask (item pool minus train positives), threshold test, sorted insert
+// Kernel structure (one CTA = 128 users x one SEGMENT of the item tiles; two CTAs per SM overlap):
+//   warps 0-3, 6-9  epilogue: eight warps; thread (quadrant, lane) owns user row r = TMEM lane r and one HALF of every tile's
+//              128 columns (warps 0-3 columns 0-63, warps 6-9 columns 64-127); tcgen05.ld 16 columns at a time, candidate
+//              mask (item pool minus train positives), threshold test; survivors are APPENDED to a small per-thread buffer and
+//              merged into the thread's sorted 16-entry list only when a buffer fills (round 1 inserted every survivor at once:
+//              the 32-step insertion was run by the whole warp for almost every 32-column chunk, ~200 of ~380 instructions)
 //   warp 4     producer: one 32 KB cp.async.bulk (TMA engine, 1-D) per item tile, pre-tiled in HBM in
 //              the exact UMMA shared-memory image (K-major, no swizzle) by prep_items_kernel
 //   warp 5     TMEM allocator + single-thread MMA issuer: 12 tcgen05.mma (4 k-steps x {hi.hi, hi.lo, lo.hi})
 //              per tile into a double-buffered 128x128 fp32 accumulator
+// 2-D decomposition: grid = (user blocks, S segments); S grows as the user count shrinks (a rank of an 8-GPU evaluation holds
+// 30 user blocks: without the split 30 CTAs would walk all 321 tiles serially on a 148-SM part).  Every (user, segment, column
+// half) keeps its own 16 candidates and threshold; the re-score kernel merges the 2*S lists of a user.
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -22,14 +28,18 @@ namespace tc {
 
 constexpr int TM = 128;                 // users per CTA (UMMA M)
 constexpr int TN = 128;                 // items per tile (UMMA N)
-constexpr int KP = 32;                  // approximate candidates kept per user
+constexpr int KP = 24;                  // approximate candidates kept per LIST (user x segment x column half): > 20, so that a list
+                                        // holding the whole top-20 still has its threshold below the 20th exact score
+constexpr int CBUF = 16;                // append-buffer entries per epilogue thread
+constexpr int EPI = 256;                // epilogue threads per CTA
+constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
 constexpr int K = NGACF_TOPK;
 constexpr int PANEL = TN * 16;          // bytes of one k-chunk panel: 128 rows x 16 B
 constexpr int HALF_BYTES = 8 * PANEL;   // 16 KB: one operand half (hi or lo), 8 k-chunks
 constexpr int TILE_BYTES = 2 * HALF_BYTES;   // 32 KB per item tile (hi + lo)
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
 constexpr int STAGES = 2;                // item-tile ring in shared memory
-constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + STAGES * TILE_BYTES /*B ring*/ + 32 * TM * 4 /*score staging*/ + 128 /*barriers*/ + 128 /*align*/;
+constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + STAGES * TILE_BYTES /*B ring*/ + 16 * EPI * 4 /*score staging*/ + 128 /*barriers*/ + 128 /*align*/;
 constexpr float GUARD = 1e-4f;          // |approx - exact| <= GUARD * |u| * max|i|  (bf16x3: ~6e-5 worst case)
 
 // instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128  (cute::UMMA::InstrDescriptor bit layout)
@@ -51,15 +61,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// try_wait with a suspend-time hint: the thread is parked in hardware until the phase completes (or the hint expires) instead of
+// re-issuing the test.  Without it a third of ALL issued instructions of this kernel were the spin loops of the producer thread,
+// the MMA thread and the epilogue warps (ncu source page, profiles/r2_score_topk_tc_source.txt), stealing issue slots from the
+// epilogue warps that share their schedulers.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
-        ::"r"(bar), "r"(parity) : "memory");
+        ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -89,6 +103,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -146,20 +169,25 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const float* __restrict
 __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* __restrict__ F, int U, const int* __restrict__ users,
                                                                    int n_users, const int* __restrict__ train_ptr,
                                                                    const int* __restrict__ train_items, const uint32_t* __restrict__ pool_bits,
-                                                                   const uint8_t* __restrict__ img, int n_tiles, int* __restrict__ cand_ids,
-                                                                   float* __restrict__ cand_thr) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);   // no swizzle: 16 B would do
+                                                                   const uint8_t* __restrict__ img, int n_tiles, int S,
+                                                                   float* __restrict__ gbuf_s, int* __restrict__ gbuf_i,
+                                                                   int* __restrict__ cand_ids, float* __restrict__ cand_thr) {
+    // no pointer arithmetic through integers here: the compiler must keep the shared address space (STS/LDS), the staging
+    // stores of round 1 were generic ST.E because the base pointer had been aligned by hand through uintptr_t
+    extern __shared__ __align__(128) unsigned char smem[];      // SWIZZLE_NONE operands: 16-byte alignment would do
     unsigned char* sA = smem;                                   // hi | lo, 32 KB
     unsigned char* sB = sA + 2 * HALF_BYTES;                    // STAGES x (hi | lo), 32 KB each
-    float* Vs = reinterpret_cast<float*>(sB + STAGES * TILE_BYTES);   // [32 columns][TM rows] staging of one accumulator chunk
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 32 * TM); // full[2], empty[2], tmem_full[2], tmem_empty[2]
+    float4* Vs4 = reinterpret_cast<float4*>(sB + STAGES * TILE_BYTES);   // [4 column quads][EPI threads] x float4: one accumulator piece
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs4 + 4 * EPI); // full[2], empty[2], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const uint32_t bar_full0 = smem_u32(bars + 0), bar_empty0 = smem_u32(bars + 2);
     const uint32_t bar_tfull0 = smem_u32(bars + 4), bar_tempty0 = smem_u32(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int u0 = blockIdx.x * TM;
+    const int seg = blockIdx.y;
+    const int t0 = (int)((int64_t)seg * n_tiles / S), t1 = (int)((int64_t)(seg + 1) * n_tiles / S);   // this CTA's item tiles
+    const int nt = t1 - t0;
 
     // ---- one-time setup: user rows -> bf16 hi/lo UMMA image (generic-proxy stores) ----
     for (int idx = tid; idx < TM * 8; idx += THREADS) {
@@ -184,8 +212,8 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         mbar_init(bar_empty0 + 8, 1);
         mbar_init(bar_tfull0, 1);
         mbar_init(bar_tfull0 + 8, 1);
-        mbar_init(bar_tempty0, 4);
-        mbar_init(bar_tempty0 + 8, 4);
+        mbar_init(bar_tempty0, 8);                   // eight epilogue warps drain an accumulator
+        mbar_init(bar_tempty0 + 8, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {   // TMEM: 256 columns = two 128-column fp32 accumulators
@@ -201,22 +229,22 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
     if (warp == 4) {
         // ================= producer =================
         if (lane == 0) {
-            for (int t = 0; t < n_tiles; ++t) {
-                const int st = t & 1;
-                mbar_wait(bar_empty0 + 8 * st, (uint32_t)(((t >> 1) & 1) ^ 1));   // ring slot free (MMAs of tile t-2 retired)
+            for (int lt = 0; lt < nt; ++lt) {
+                const int st = lt & 1;
+                mbar_wait(bar_empty0 + 8 * st, (uint32_t)(((lt >> 1) & 1) ^ 1));   // ring slot free (MMAs of tile lt-2 retired)
                 mbar_expect_tx(bar_full0 + 8 * st, TILE_BYTES);
-                bulk_g2s(smem_u32(sB) + st * TILE_BYTES, img + (size_t)t * TILE_BYTES, TILE_BYTES, bar_full0 + 8 * st);
+                bulk_g2s(smem_u32(sB) + st * TILE_BYTES, img + (size_t)(t0 + lt) * TILE_BYTES, TILE_BYTES, bar_full0 + 8 * st);
             }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t aH = smem_u32(sA), aL = aH + HALF_BYTES;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int buf = t & 1;
+            for (int lt = 0; lt < nt; ++lt) {
+                const int buf = lt & 1;
                 const uint32_t bH = smem_u32(sB) + buf * TILE_BYTES, bL = bH + HALF_BYTES;
-                mbar_wait(bar_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));                 // tile t landed in its ring slot
-                mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
+                mbar_wait(bar_full0 + 8 * buf, (uint32_t)((lt >> 1) & 1));                 // tile landed in its ring slot
+                mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((lt >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);
 #pragma unroll
@@ -232,76 +260,108 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             }
         }
     } else {
-        // ================= epilogue: thread = user row = TMEM lane =================
-        const int r = tid;                                    // 0..127, warp w reads TMEM lanes 32w..32w+31
+        // ================= epilogue: thread = (user row = TMEM lane, column half) =================
+        const int half = warp >= 6 ? 1 : 0;
+        const int quad = warp & 3;                            // TMEM lanes 32*quad .. 32*quad+31 are the ones this warp may read
+        const int r = quad * 32 + lane;
+        const int et = half * TM + r;                         // epilogue thread id 0..255
         const int uslot = u0 + r;
         const int user = uslot < n_users ? users[uslot] : -1;
-        int cur = user >= 0 ? train_ptr[user] : 0;
+        int cur = 0;
         const int tend = user >= 0 ? train_ptr[user + 1] : 0;
+        if (user >= 0) {                                      // first train item of this user inside the segment (lower bound)
+            int lo = train_ptr[user], hi = tend;
+            const int first_item = t0 * TN;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (train_items[mid] < first_item) lo = mid + 1; else hi = mid;
+            }
+            cur = lo;
+        }
+        int nxt = (user >= 0 && cur < tend) ? train_items[cur] : 0x7fffffff;
         // candidate list: KP (score, id) pairs sorted by descending score, entirely in registers
         float ls[KP];
         int li[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) { ls[k] = -INFINITY; li[k] = -1; }
         float thr = -INFINITY;                                // == ls[KP-1]
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
-            const int item0 = t * TN;
-            unsigned tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;      // train positives of this user inside the tile
-            while (cur < tend) {
-                const int it = train_items[cur];
-                if (it >= item0 + TN) break;
-                const int off = it - item0;
-                if (off >= 0) {
+        // append buffer of this thread (global memory, interleaved over the CTA's epilogue threads: coalesced, L1/L2 resident)
+        const size_t cta_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        float* bS = gbuf_s + cta_lin * (CBUF * EPI) + et;
+        int* bI = gbuf_i + cta_lin * (CBUF * EPI) + et;
+        int cnt = 0;
+        auto flush = [&]() {                                  // merge the buffered survivors into the sorted list
+            for (int e = 0; e < cnt; ++e) {
+                const float sc = bS[e * EPI];
+                const int id = bI[e * EPI];
+                if (sc > thr) {
+#pragma unroll
+                    for (int k = KP - 1; k > 0; --k) {
+                        const bool shift = ls[k - 1] < sc;
+                        const bool here = ls[k] < sc;
+                        li[k] = shift ? li[k - 1] : (here ? id : li[k]);
+                        ls[k] = shift ? ls[k - 1] : (here ? sc : ls[k]);
+                    }
+                    if (ls[0] < sc) { ls[0] = sc; li[0] = id; }
+                    thr = ls[KP - 1];
+                }
+            }
+            cnt = 0;
+        };
+        for (int lt = 0; lt < nt; ++lt) {
+            const int buf = lt & 1;
+            const int item0 = (t0 + lt) * TN + half * 64;     // first item of this thread's 64 columns
+            unsigned tw0 = 0, tw1 = 0;                        // train positives of this user inside those 64 columns
+            const int tile_end = (t0 + lt + 1) * TN;
+            while (nxt < tile_end) {                          // nxt = the user's next train item, loaded ahead of its tile
+                const int off = nxt - item0;
+                if (off >= 0 && off < 64) {
                     const unsigned bit = 1u << (off & 31);
-                    const int w = off >> 5;
-                    tw0 |= w == 0 ? bit : 0u; tw1 |= w == 1 ? bit : 0u; tw2 |= w == 2 ? bit : 0u; tw3 |= w == 3 ? bit : 0u;
+                    tw0 |= off < 32 ? bit : 0u;
+                    tw1 |= off >= 32 ? bit : 0u;
                 }
                 ++cur;
+                nxt = cur < tend ? train_items[cur] : 0x7fffffff;
             }
-            mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((t >> 1) & 1));
+            const unsigned pw0 = user >= 0 ? (__ldg(pool_bits + (t0 + lt) * 4 + half * 2) & ~tw0) : 0u;
+            const unsigned pw1 = user >= 0 ? (__ldg(pool_bits + (t0 + lt) * 4 + half * 2 + 1) & ~tw1) : 0u;
+            mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TN + ch * 32), v);
-                const unsigned tw = ch == 0 ? tw0 : ch == 1 ? tw1 : ch == 2 ? tw2 : tw3;
-                const unsigned allowed = user >= 0 ? (__ldg(pool_bits + t * 4 + ch) & ~tw) : 0u;
-                // threshold filter on the registers; the (rare) survivors are picked up again from a shared-memory
-                // copy so that the insertion code exists once instead of 32 times
+            for (int pc = 0; pc < 4; ++pc) {                  // four 16-column pieces of this thread's 64 columns
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + half * 64 + pc * 16), v);
+                const unsigned allowed = ((pc < 2 ? pw0 : pw1) >> ((pc & 1) * 16)) & 0xFFFFu;
+                // threshold filter on the registers; the survivors are picked up again from a shared-memory copy so that the
+                // append code exists once instead of 16 times
                 unsigned hit = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    Vs[j * TM + r] = __uint_as_float(v[j]);
-                    hit |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
-                }
+                for (int q4 = 0; q4 < 4; ++q4)               // staging: four 16-byte stores (thread stride 16 B: conflict-free)
+                    Vs4[q4 * EPI + et] = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                                                     __uint_as_float(v[4 * q4 + 3]));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hit |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
                 hit &= allowed;
-                while (hit) {                                   // lanes work on their own survivors in parallel
+                const int n = __popc(hit);                    // <= 16 = CBUF: fits after a flush
+                if (__any_sync(0xffffffffu, cnt + n > CBUF)) flush();
+                while (hit) {                                 // lanes append their own survivors in parallel
                     const int j = __ffs(hit) - 1;
                     hit &= hit - 1;
-                    const float sc = Vs[j * TM + r];
-                    const int id = item0 + ch * 32 + j;
-                    if (sc > thr) {
-#pragma unroll
-                        for (int k = KP - 1; k > 0; --k) {
-                            const bool shift = ls[k - 1] < sc;
-                            const bool here = ls[k] < sc;
-                            li[k] = shift ? li[k - 1] : (here ? id : li[k]);
-                            ls[k] = shift ? ls[k - 1] : (here ? sc : ls[k]);
-                        }
-                        if (ls[0] < sc) { ls[0] = sc; li[0] = id; }
-                        thr = ls[KP - 1];
-                    }
+                    bS[cnt * EPI] = reinterpret_cast<const float*>(Vs4 + (j >> 2) * EPI + et)[j & 3];
+                    bI[cnt * EPI] = item0 + pc * 16 + j;
+                    ++cnt;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty0 + 8 * buf);
         }
+        flush();
         if (user >= 0) {
+            const size_t list = ((size_t)uslot * S + seg) * 2 + half;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) cand_ids[(int64_t)uslot * KP + k] = li[k];
-            cand_thr[uslot] = li[KP - 1] >= 0 ? thr : -INFINITY;
+            for (int k = 0; k < KP; ++k) cand_ids[list * KP + k] = li[k];
+            cand_thr[list] = li[KP - 1] >= 0 ? thr : -INFINITY;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -324,51 +384,69 @@ __device__ __forceinline__ float dot64_tree_g(float4 a, float4 b, unsigned gm) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ F, int U, const int* __restrict__ users, int n_users,
-                                                      const int* __restrict__ cand_ids, const float* __restrict__ cand_thr,
-                                                      const unsigned int* __restrict__ maxnorm_bits, int* __restrict__ top_ids,
-                                                      float* __restrict__ top_scores, int* __restrict__ fallback) {
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    if (j >= n_users) return;
+// One 16-lane group per user: the user's 2*S candidate lists (KP entries each, disjoint item ranges) are re-scored exactly,
+// ranked under (score desc, id asc), and the top-20 is accepted only if no non-candidate can beat its last entry: a
+// non-candidate of list l has approx <= thr[l], hence exact <= thr[l] + delta.
+constexpr int RS_GROUPS = 4;            // users per CTA (64 threads; 24 KB of candidate scores / ids)
+__global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __restrict__ F, int U, const int* __restrict__ users, int n_users,
+                                                                const int* __restrict__ cand_ids, const float* __restrict__ cand_thr, int n_lists,
+                                                                const unsigned int* __restrict__ maxnorm_bits, int* __restrict__ top_ids,
+                                                                float* __restrict__ top_scores, int* __restrict__ fallback) {
+    __shared__ float sc_s[RS_GROUPS][MAX_LISTS * KP];
+    __shared__ int id_s[RS_GROUPS][MAX_LISTS * KP];
+    const int grp = threadIdx.x >> 4;
+    const int j = blockIdx.x * RS_GROUPS + grp;
+    if (j >= n_users) return;                                  // whole groups leave together; no block-level barrier below
     const int lane16 = threadIdx.x & 15;
     const unsigned gm = group_mask();
+    const int NC = n_lists * KP;
     const int64_t u = users[j];
     const float4 fu = ld_gather4(F + u * D + lane16 * 4);
     const float unorm = sqrtf(dot64_tree_g(fu, fu, gm));
-    const int id0 = cand_ids[(int64_t)j * KP + lane16], id1 = cand_ids[(int64_t)j * KP + 16 + lane16];
-    float s0 = -INFINITY, s1 = -INFINITY;
-#pragma unroll 4
-    for (int c = 0; c < KP; ++c) {
-        const int id = __shfl_sync(gm, c < 16 ? id0 : id1, c & 15, 16);
-        float s = -INFINITY;
-        if (id >= 0) {                                                   // group-uniform
-            const float4 fi = ld_gather4(F + (int64_t)(U + id) * D + lane16 * 4);
-            s = dot64_tree_g(fu, fi, gm);
+    float* scs = sc_s[grp];
+    int* ids = id_s[grp];
+    for (int c = lane16; c < NC; c += 16) ids[c] = cand_ids[(int64_t)j * NC + c];
+    __syncwarp(gm);
+    for (int c0 = 0; c0 < NC; c0 += 4) {                        // exact scores, four candidate rows in flight
+        float4 fi[4];
+        int id[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            id[q] = c0 + q < NC ? ids[c0 + q] : -1;
+            fi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id[q] >= 0) fi[q] = ld_gather4(F + (int64_t)(U + id[q]) * D + lane16 * 4);     // group-uniform
         }
-        if ((c & 15) == lane16) { if (c < 16) s0 = s; else s1 = s; }
-    }
-    // rank of my two candidates under (score desc, id asc); ids are distinct so ranks are a permutation
-    int rank0 = 0, rank1 = 0, nvalid = 0;
-#pragma unroll 4
-    for (int c = 0; c < KP; ++c) {
-        const int id = __shfl_sync(gm, c < 16 ? id0 : id1, c & 15, 16);
-        const float s = __shfl_sync(gm, c < 16 ? s0 : s1, c & 15, 16);
-        if (id >= 0) {
-            ++nvalid;
-            rank0 += (s > s0 || (s == s0 && id < id0)) ? 1 : 0;
-            rank1 += (s > s1 || (s == s1 && id < id1)) ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float sv = dot64_tree_g(fu, fi[q], gm);
+            if (lane16 == 0 && c0 + q < NC) scs[c0 + q] = id[q] >= 0 ? sv : -INFINITY;
         }
     }
-    if (id0 >= 0 && rank0 < K) { top_ids[(int64_t)j * K + rank0] = id0; top_scores[(int64_t)j * K + rank0] = s0; }
-    if (id1 >= 0 && rank1 < K) { top_ids[(int64_t)j * K + rank1] = id1; top_scores[(int64_t)j * K + rank1] = s1; }
-    for (int k = nvalid + lane16; k < K; k += 16) { top_ids[(int64_t)j * K + k] = -1; top_scores[(int64_t)j * K + k] = 0.f; }
-    // proof: every non-candidate has approx <= thr, hence exact <= thr + delta; it cannot enter if that is < tau (exact 20th)
+    __syncwarp(gm);
+    // rank of my candidates under (score desc, id asc); ids are distinct (the lists cover disjoint item ranges)
+    int nvalid = 0;
+    for (int c = 0; c < NC; ++c) nvalid += ids[c] >= 0 ? 1 : 0;
     float tau = -INFINITY;
-    if (id0 >= 0 && rank0 == K - 1) tau = s0;
-    if (id1 >= 0 && rank1 == K - 1) tau = s1;
+    for (int c = lane16; c < NC; c += 16) {
+        const int id = ids[c];
+        if (id < 0) continue;
+        const float sv = scs[c];
+        int rank = 0;
+        for (int o = 0; o < NC; ++o) {
+            const int io = ids[o];
+            const float so = scs[o];
+            rank += (io >= 0 && (so > sv || (so == sv && io < id))) ? 1 : 0;
+        }
+        if (rank < K) { top_ids[(int64_t)j * K + rank] = id; top_scores[(int64_t)j * K + rank] = sv; }
+        if (rank == K - 1) tau = sv;
+    }
+    for (int k = nvalid + lane16; k < K; k += 16) { top_ids[(int64_t)j * K + k] = -1; top_scores[(int64_t)j * K + k] = 0.f; }
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(gm, tau, o, 16));
-    const float thr = cand_thr[j];
+    float thr = -INFINITY;
+    for (int l = lane16; l < n_lists; l += 16) thr = fmaxf(thr, cand_thr[(int64_t)j * n_lists + l]);
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) thr = fmaxf(thr, __shfl_xor_sync(gm, thr, o, 16));
     const float delta = GUARD * unorm * __uint_as_float(*maxnorm_bits);
     const bool ok = (thr == -INFINITY) || (nvalid >= K && thr + delta < tau);
     if (lane16 == 0) fallback[j] = ok ? 0 : 1;
@@ -381,9 +459,23 @@ using namespace ngacf;
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
+// item-tile segments per user block: fill the 2 x 148 CTA slots when there are few user blocks (a rank of a sharded evaluation)
+static int plan_segments(int n_users, int n_tiles) {
+    const int blocks = (n_users + tc::TM - 1) / tc::TM;
+    int S = blocks > 0 ? (2 * 148) / blocks : 1;
+    if (S < 1) S = 1;
+    if (S > tc::MAX_LISTS / 2) S = tc::MAX_LISTS / 2;
+    if (S > n_tiles) S = n_tiles > 0 ? n_tiles : 1;
+    return S;
+}
+
 extern "C" size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users) {
     const size_t n_tiles = (size_t)(I + tc::TN - 1) / tc::TN;
-    return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + al256((size_t)n_users * tc::KP * 4) + al256((size_t)n_users * 4) + 1024;
+    const int S = plan_segments(n_users, (int)n_tiles);
+    const size_t lists = (size_t)n_users * 2 * S;
+    const size_t ctas = (size_t)((n_users + tc::TM - 1) / tc::TM) * S;
+    return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + al256(lists * tc::KP * 4) + al256(lists * 4) +
+           2 * al256(ctas * tc::CBUF * tc::EPI * 4) + 1024;
 }
 
 extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users, const int32_t* train_ptr,
@@ -395,21 +487,27 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     if (n_users == 0) return NGACF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (I + tc::TN - 1) / tc::TN;
+    const int S = plan_segments(n_users, n_tiles);
+    const int blocks = ceil_div(n_users, tc::TM);
+    const size_t lists = (size_t)n_users * 2 * S;
+    const size_t ctas = (size_t)blocks * S;
     char* w = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     uint8_t* img = (uint8_t*)w;                         w += al256((size_t)n_tiles * tc::TILE_BYTES);
     uint32_t* pool_bits = (uint32_t*)w;                 w += al256((size_t)n_tiles * 4 * 4);
     unsigned int* maxnorm = (unsigned int*)w;           w += 256;
-    int* cand_ids = (int*)w;                            w += al256((size_t)n_users * tc::KP * 4);
-    float* cand_thr = (float*)w;
+    int* cand_ids = (int*)w;                            w += al256(lists * tc::KP * 4);
+    float* cand_thr = (float*)w;                        w += al256(lists * 4);
+    float* gbuf_s = (float*)w;                          w += al256(ctas * tc::CBUF * tc::EPI * 4);
+    int* gbuf_i = (int*)w;
     cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
     tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
     static PerDeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
-    tc::score_topk_tc_kernel<<<ceil_div(n_users, tc::TM), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, train_ptr, train_items, pool_bits,
-                                                                                             img, n_tiles, cand_ids, cand_thr);
-    tc::rescore_kernel<<<ceil_div((int64_t)n_users * 16, 256), 256, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, maxnorm, top_ids, top_scores,
-                                                                             fallback);
+    tc::score_topk_tc_kernel<<<dim3(blocks, S), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, train_ptr, train_items, pool_bits, img,
+                                                                                  n_tiles, S, gbuf_s, gbuf_i, cand_ids, cand_thr);
+    tc::rescore_kernel<<<ceil_div(n_users, tc::RS_GROUPS), tc::RS_GROUPS * 16, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, 2 * S, maxnorm,
+                                                                                       top_ids, top_scores, fallback);
     return check_launch("score_topk_tc");
 }

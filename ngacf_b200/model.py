@@ -101,6 +101,7 @@ class SPUIGACF(nn.Module):
         self.iEmbd = nn.Embedding(itemNum, embedSize)
         # `layers` is accepted and ignored exactly as in the reference (SPUIGACF.py:7 is its only use)
         self.gat = self.GAT(nfeat=embedSize, nhid=8, nclass=embedSize, dropout=droprate, nheads=8, alpha=ALPHA)
+        self._extra_modules(embedSize, layers)      # subclasses create their modules HERE: the reference's RNG order (init after all modules)
         nn.init.normal_(self.uEmbd.weight, std=0.01)
         nn.init.normal_(self.iEmbd.weight, std=0.01)
         self.drop_seed = None       # Philox key of the dropout streams; defaults to torch.initial_seed()
@@ -108,6 +109,9 @@ class SPUIGACF(nn.Module):
         self._graph_key, self._graph = None, None
         self._eval_key, self._eval_Z = None, None
         self.injected_masks = None  # parity tests: dict(feat=[...], edge=[...]) consumed by the next call
+
+    def _extra_modules(self, embedSize, layers):
+        pass
 
     # ------------------------------------------------------------------------------------------
     def graph_for(self, mask: torch.Tensor) -> BipartiteGraph:

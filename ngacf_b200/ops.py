@@ -251,3 +251,9 @@ def bce_logits_loss(scores, group, loss, dscore=None):
 
 def rank_metrics(scores, group, top_k, sums):
     _lib.call("ngacf_rank_metrics", _p(scores), scores.numel() // int(group), int(group), int(top_k), _p(sums), _s())
+
+
+def spmm_sym(g: BipartiteGraph, scratch, counter, val, diag, X, Y):
+    """Y = diag (.) X + A_val X  (symmetric Laplacian on the unified adjacency; SPUIGAGPCF's GPLayer)"""
+    _lib.call("ngacf_spmm_sym", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid), _p(g.long_first_slot), _p(counter), _p(scratch),
+              _p(val), _p(diag), _p(X), _p(Y), _s())

@@ -931,3 +931,33 @@ def test_long_row_combine_is_deterministic_under_stress():
         for a, b in zip([Z, dU, dI] + grads, first):
             bad += (a != b).sum()
     assert int(bad.item()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f-1, second half: SPUIGAGPCF (SpUIGAT + Laplacian-propagation layers)
+# ------------------------------------------------------------------------------------------------
+def test_spuigagpcf_forward_backward_vs_reference(golden):
+    """SPUIGAGPCF.forward / backward against the reference's own fp64 run (tests/golden/gagpcf_small.npz: the reference class with the
+    reference's buildLaplacianMat 'norm_adj' Laplacian over integer ratings).  Scores and EVERY gradient -- embeddings, attention
+    parameters and the affine layers behind the Laplacian product -- to 1e-4."""
+    from graphattention.SPUIGACF import SPUIGAGPCF
+    gz = golden("gagpcf_small")
+    U, I = int(gz["U"]), int(gz["I"])
+    L = torch.sparse_coo_tensor(torch.from_numpy(np.stack([gz["lap_row"], gz["lap_col"]])), torch.from_numpy(gz["lap_val"]), (U + I, U + I))
+    model = SPUIGAGPCF(U, I, L, 64, [64, 64], 0.0)
+    model.load_state_dict(sd_from(gz, "sd/"))
+    model = model.to(DEV).train()
+    adj = torch.from_numpy(np.stack([gz["edge_u"], gz["edge_i"]])).to(DEV)
+    sc = model(torch.from_numpy(gz["users"]).to(DEV), torch.from_numpy(gz["items"]).to(DEV), adj)
+    assert rel_err(sc.detach().cpu().numpy(), gz["scores_f64"]) < 1e-4
+    (sc * torch.from_numpy(gz["w"]).float().to(DEV)).sum().backward()
+    names = [k for k, _ in model.named_parameters()]
+    assert "Affinelayers.1.bias" in names and "gat.out_att.a" in names
+    for k, v in model.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), gz["grad_f64/" + k]) < 1e-4, k
+    # the operator itself: (L + I) X against the dense product, long rows included
+    from ngacf_b200.gp import LaplacianOp
+    X = torch.randn(U + I, 64, device=DEV)
+    got = LaplacianOp(model.graph_for(adj), L)(X)
+    want = (L.to_dense().to(DEV).double() + torch.eye(U + I, device=DEV, dtype=torch.float64)) @ X.double()
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5

@@ -219,3 +219,16 @@ def test_integration_stub_matches_the_abi():
     for name in re.findall(r"`(ngacf_[a-z_0-9]+)`", text):       # every entry point the document names exists
         base = name
         assert base in _lib.SIGNATURES or any(k.startswith(base) for k in _lib.SIGNATURES), name
+
+
+def test_normalized_laplacian_matches_reference_fixture():
+    """ngacf_b200.gp.normalized_laplacian (host side of SPUIGAGPCF) == the reference's buildLaplacianMat(..., 'norm_adj')
+    + scipySP_torchSP + coalesce, whose output is stored in tests/golden/gagpcf_small.npz."""
+    from ngacf_b200.gp import normalized_laplacian
+    gz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gagpcf_small.npz"))
+    U, I = int(gz["U"]), int(gz["I"])
+    L = normalized_laplacian(U, I, gz["edge_u"], gz["edge_i"], gz["rating"], "norm_adj")
+    assert np.array_equal(L.indices()[0].numpy(), gz["lap_row"]) and np.array_equal(L.indices()[1].numpy(), gz["lap_col"])
+    assert np.allclose(L.values().numpy(), gz["lap_val"], rtol=1e-6, atol=0)
+    M = normalized_laplacian(U, I, gz["edge_u"], gz["edge_i"], None, "mean_adj").to_dense().numpy()
+    assert np.allclose(M, M.T) and np.allclose(np.diag(M), 0)
