@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--workload", default="gowalla", choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the second timing without the output-stage pruning")
     ap.add_argument("--train-mode", default="pair", choices=["pair", "neg"],
                     help="pair: PairSampling + AllNeg (the headline, SURVEY 8); neg: NegSampling + SampledNeg (8f-3, single GPU)")
     ap.add_argument("--split-bwd", action="store_true", help="dense backward as dX (on the chain) + dW/da (gradient stream)")
@@ -257,15 +258,30 @@ def main():
         torch.cuda.synchronize()
 
     if args.profile_only:      # eager, single stream: the launch list ncu sees is the step's kernel sequence
+        # ncu --profile-from-start off: only the steady-state steps (and the evaluation) between cudaProfilerStart/Stop are listed,
+        # none of the one-off allocations / graph-build launches
         trainer.side = None
-        for k in range(W + 2):
+        for k in range(W):
             trainer._step_body(B, 0, HYPER["droprate"], model._seed(), k * B, 2 * k, False)
-        torch.cuda.synchronize()
+        ev = None
         if not args.no_eval:
             model.eval()
+            ev = AllNegEvaluator(inter, args.eval_mode)
             with torch.no_grad():
-                AllNegEvaluator(inter, args.eval_mode)(model.propagate(graph))
+                ev(model.propagate(graph))
+            model.train()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for k in range(W, W + 3):
+            trainer._step_body(B, 0, HYPER["droprate"], model._seed(), k * B, 2 * k, False)
+        torch.cuda.synchronize()
+        if ev is not None:
+            model.eval()
+            with torch.no_grad():
+                model._eval_key = None
+                ev(model.propagate(graph))
             torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
 
     clocks = ClockSampler(local) if rank == 0 else None
@@ -305,6 +321,24 @@ def main():
     ms_e2e = float(np.median(blocks_e2e))
     e2e_value = units_per_step / (ms_e2e / K / 1000.0)
     clk = clocks.stop() if clocks else {}
+
+    # ---------------- the same step WITHOUT the output-stage pruning (N=1, PairSampling): reported next to the headline ----------------
+    full_prop = None
+    if world == 1 and args.train_mode == "pair" and getattr(trainer, "prune_last_stage", False) and not args.no_full:
+        os.environ["NGACF_PRUNE"] = "0"
+        try:
+            model_f = SPUIGACF(U, I, 64, [64, 64], HYPER["droprate"]).to(dev)
+            model_f.load_state_dict(model.state_dict())
+            tr_f = FusedTrainer(model_f, inter, graph, B, FusedAdam(model_f.parameters(), lr=HYPER["lr"], weight_decay=HYPER["weight_decay"]),
+                                sample_seed=0, split_dense_backward=args.split_bwd)
+            tr_f.run_steps(W)
+            bf = timed_blocks(lambda: tr_f.run_steps(K))
+            full_prop = dict(ms_per_step=float(np.median(bf)) / K, value=units_per_step / (float(np.median(bf)) / K / 1000.0), unit="edges/s",
+                             note="NGACF_PRUNE=0: the output stage is computed for every row, as the reference does (results identical up to "
+                                  "the order of additions, tests/test_gpu_parity.py::test_pruned_last_stage_equals_full)")
+            del tr_f, model_f
+        finally:
+            os.environ["NGACF_PRUNE"] = "1"
 
     # ---------------- per-kernel live timing (eager, one stream) -> roofline of the dominant kernel ----------------
     phases = trainer.profile_phases(5) if hasattr(trainer, "profile_phases") else None
@@ -367,10 +401,13 @@ def main():
                     peak_source=pk["source"], algorithmic_bytes_per_launch=top_bytes, avg_launch_ms=top_avg_ms,
                     byte_model="gather (tables > 63 MB, SURVEY 8d)" if gather else "compulsory (tables L2-resident, SURVEY 8d)",
                     share_of_step=top_ms_step / total_prof,
-                    note="Gowalla-size gather tables (18 MB) are L2-resident: the gather kernels are limited by the L2->SM path (0.37-0.61 GB of "
-                         "tex sectors per launch at 6-9 TB/s, profiles/r1e_top_kernels_ncu_full.txt), DRAM traffic <= algorithmic bytes (no "
-                         "re-reads, profiles/ncu_traffic.json); in the HBM regime (sweep-10m/30m) the same kernels reach 0.9-1.06 of the measured "
-                         "HBM peak (profiles/r1e_bench_sweep-30m.json)",
+                    note="Gowalla-size gather tables (18 MB) are L2-resident; DRAM traffic <= algorithmic bytes (no re-reads, "
+                         "profiles/ncu_traffic.json).  The gather kernels are bounded by the SM's L1TEX wavefront rate, not by L2 or HBM: a "
+                         "bare 256-byte row gather of the same visits sustains 15.7 TB/s out of L2 (scripts/probe/probe_gather.cu, "
+                         "profiles/r2_probe_gather.txt: ~2.4 cycles per 128-byte line per SM, L1 hits cost the same wavefronts, hot rows in "
+                         "shared memory do not pay), and these kernels need 3.1-4 wavefronts per visited edge (row 2 + logit 1 + mask/edge id) "
+                         "-- the compulsory byte model of SURVEY 8d cannot be reached by a kernel that must pull 2E rows through L1TEX; in the "
+                         "HBM regime (sweep-10m/30m) the same kernels reach 0.9-1.06 of the measured HBM peak",
                     step_model=dict(compulsory_bytes_per_step=step_bytes, step_ms_at_peak=step_bytes / (pk["hbm"] * 1e9) * 1e3,
                                     frac_of_step_roofline=(step_bytes / (pk["hbm"] * 1e9) * 1e3) / ms_step if world == 1 else None),
                     kernels=[dict(kernel=k, ms_per_step=round(ms, 4), launches_per_step=n) for k, ms, n in table])
@@ -476,6 +513,9 @@ def main():
                                           "PairSampling step: sampler + 2 propagations (dropout %.1f) + BPR + backward + Adam") % HYPER["droprate"],
                                 batch=B, l2="per-step working set ~%d MB > 126 MB L2, no flush" % (trainer.working_set_bytes() // 2 ** 20),
                                 parallelism=trainer.parallelism(), graph_build_ms=graph_build_ms,
+                                output_stage=("pruned to the batch rows (exact: the loss reads nothing else of it, SPUIGACF.py:49-52)"
+                                              if getattr(trainer, "prune_last_stage", getattr(trainer, "prune", False)) else "full"),
+                                full_propagation=full_prop,
                                 train_rows_per_s=B / (ms_step / 1000.0) * (world if getattr(trainer, "weak", False) else 1)),
                     roofline=roof, cpu_baseline=cpu, clocks=clk,
                     e2e=dict(value=e2e_value, unit="edges/s", h2d_bytes_per_step=B * 4, d2h_bytes_per_step=4, ms_per_step=ms_e2e / K),
