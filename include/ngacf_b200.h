@@ -306,6 +306,33 @@ int ngacf_spmm_sym(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, cons
                    const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* val, const float* diag,
                    const float* X, float* Y, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SpGraphAttentionLayer / SpGAT (graphattention/SPGA.py:330-421): one W for every node, directed logit
+ * e(n->m) = exp(-LeakyReLU(a[:out].h[n] + a[out:].h[m])), row-normalised, no residual: out[n] = sum_m drop(e) h[m] / sum_m e.
+ * The adjacency is the unified adjacency of ngacf_graph_build (symmetric bipartite pattern) plus, if self_loops, one edge n->n per
+ * node.  Directed edges are identified by adjacency position (0..n_adj-1, n_adj = 2E; self edge of n: n_adj + n): emask
+ * (uint8[n_adj (+N)], bit k = head k kept; NULL = no dropout) and pairs (float2[(n_adj (+N)) * H]) use that index; rev[p] is the
+ * position of the reverse edge.  h is produced by ngacf_transform_fwd with W_u = W_i = W in wtab ([W x H | W x H | a x H]).
+ *   node_logits:      p[n,k] = a_k[:DH].h[n,head k], q[n,k] = a_k[DH:].h[n,head k]
+ *   spgat_aggregate_fwd: Z = out (pre-ELU), norm = row sums.
+ *   spgat_bwd:        from G = dL/dZ: Ghat, pairs, dP, dQ (scratch outputs) and dh = dL/dh complete (attention terms included),
+ *                     which ngacf_transform_bwd turns into dW / dX.
+ *   node_logits_bwd:  partials[b][0:64] = sum_n dP[n,head(c)] h[n,c], partials[b][64:128] the same with dQ, over the rows block b
+ *                     owns (n_blocks blocks, fixed order); da_k = [sum_b partials[b][cols of head k] | ... dQ part].
+ * ------------------------------------------------------------------------------------------- */
+int ngacf_node_logits(const float* h, const float* const* wtab, int32_t H, int64_t N, float* p, float* q, void* stream);
+int ngacf_node_logits_bwd(const float* h, const float* dP, const float* dQ, int32_t H, int64_t N, float* partials, int32_t n_blocks,
+                          void* stream);
+int ngacf_spgat_aggregate_fwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx,
+                              const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* h, const float* p,
+                              const float* q, int32_t H, const uint8_t* emask, float scale, int32_t self_loops, int32_t n_adj,
+                              float* Z, float* norm, void* stream);
+int ngacf_spgat_bwd(const int32_t* tasks, int32_t T, const int32_t* adj_ptr, const int32_t* adj_idx, const int32_t* rev,
+                    const int32_t* long_first_slot, int32_t* long_counter, float* scratch, const float* G, const float* Z,
+                    const float* norm, const float* h, const float* p, const float* q, int32_t H, const uint8_t* emask, float scale,
+                    int32_t self_loops, int32_t n_adj, const float* const* wtab, float* Ghat, float* pairs, float* dP, float* dQ,
+                    float* dh, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

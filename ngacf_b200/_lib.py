@@ -28,6 +28,10 @@ SIGNATURES = {
     "ngacf_batch_rows_scatter": (c_int32, [P, c_int32, P, P, c_int32, P, P]),
     "ngacf_memset_zero": (c_int32, [P, c_size_t, P]),
     "ngacf_spmm_sym": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, P, P, P]),
+    "ngacf_node_logits": (c_int32, [P, P, c_int32, c_int64, P, P, P]),
+    "ngacf_node_logits_bwd": (c_int32, [P, P, P, c_int32, c_int64, P, c_int32, P]),
+    "ngacf_spgat_aggregate_fwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, c_int32, P, c_float, c_int32, c_int32, P, P, P]),
+    "ngacf_spgat_bwd": (c_int32, [P, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, c_int32, P, c_float, c_int32, c_int32, P, P, P, P, P, P, P]),
     "ngacf_counter_add": (c_int32, [P, c_int64, P]),
     "ngacf_step_counters": (c_int32, [P, P, P, c_int64, P]),
     "ngacf_mark_active": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P, P]),

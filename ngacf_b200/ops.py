@@ -257,3 +257,25 @@ def spmm_sym(g: BipartiteGraph, scratch, counter, val, diag, X, Y):
     """Y = diag (.) X + A_val X  (symmetric Laplacian on the unified adjacency; SPUIGAGPCF's GPLayer)"""
     _lib.call("ngacf_spmm_sym", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(g.adj_eid), _p(g.long_first_slot), _p(counter), _p(scratch),
               _p(val), _p(diag), _p(X), _p(Y), _s())
+
+
+# SpGraphAttentionLayer (csrc/spgat.cu); `graph` is a spgat.HomoGraph
+def node_logits(h, wtab, H, N, p, q):
+    _lib.call("ngacf_node_logits", _p(h), _p(wtab), int(H), int(N), _p(p), _p(q), _s())
+
+
+def node_logits_bwd(h, dP, dQ, H, N, partials):
+    _lib.call("ngacf_node_logits_bwd", _p(h), _p(dP), _p(dQ), int(H), int(N), _p(partials), partials.shape[0], _s())
+
+
+def spgat_aggregate_fwd(graph, scratch, counter, h, p, q, H, emask, scale, Z, norm):
+    g = graph.g
+    _lib.call("ngacf_spgat_aggregate_fwd", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(g.long_first_slot), _p(counter), _p(scratch), _p(h),
+              _p(p), _p(q), int(H), _p(emask), float(scale), int(graph.self_loops), graph.n_adj, _p(Z), _p(norm), _s())
+
+
+def spgat_bwd(graph, scratch, counter, G, Z, norm, h, p, q, H, emask, scale, wtab, Ghat, pairs, dP, dQ, dh):
+    g = graph.g
+    _lib.call("ngacf_spgat_bwd", _p(g.tasks), g.T, _p(g.adj_ptr), _p(g.adj_idx), _p(graph.rev), _p(g.long_first_slot), _p(counter), _p(scratch),
+              _p(G), _p(Z), _p(norm), _p(h), _p(p), _p(q), int(H), _p(emask), float(scale), int(graph.self_loops), graph.n_adj, _p(wtab),
+              _p(Ghat), _p(pairs), _p(dP), _p(dQ), _p(dh), _s())

@@ -114,6 +114,7 @@ def load():
     try:
         ns = {
             "SPUIGACF": importlib.import_module("graphattention.SPUIGACF"),
+            "SPGA": importlib.import_module("graphattention.SPGA"),
             "BPRLoss": importlib.import_module("graphattention.BPRLoss"),
             "metrics": importlib.import_module("graphattention.metrics"),
             "loadGowalla": importlib.import_module("data.loadGowalla"),

@@ -961,3 +961,119 @@ def test_spuigagpcf_forward_backward_vs_reference(golden):
     got = LaplacianOp(model.graph_for(adj), L)(X)
     want = (L.to_dense().to(DEV).double() + torch.eye(U + I, device=DEV, dtype=torch.float64)) @ X.double()
     assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# SpGraphAttentionLayer / SpGAT / SPGACF (the single-table layer, graphattention/SPGA.py:85-140,330-421)
+# ------------------------------------------------------------------------------------------------
+def _spgacf_masks(gz, graph):
+    """the fixture's keep masks (edge masks in adj.nonzero() order) in the kernels' directed-edge order"""
+    nzi = graph.nonzero_index().cpu().numpy()
+    return dict(feat=[torch.from_numpy(gz["drop_feat0"].view(np.int64)).to(DEV), torch.from_numpy(gz["drop_feat1"].view(np.int64)).to(DEV)],
+                edge=[torch.from_numpy(gz["drop_edge0_nz"][nzi]).to(DEV), torch.from_numpy(gz["drop_edge1_nz"][nzi]).to(DEV)])
+
+
+@pytest.mark.parametrize("name", ["spgacf_small", "spgacf_selfloops_small"])
+def test_spgacf_forward_backward_vs_reference(golden, name):
+    """SPGACF (SpGAT over the dense N x N adjacency, without and with the diagonal) against the reference's own fp64 run: scores,
+    final features and EVERY gradient to 1e-4, without dropout and with the fixture's injected keep masks (p = 0.3)."""
+    from graphattention.SPGA import SPGACF, HomoGraph
+    gz = golden(name)
+    U, I = int(gz["U"]), int(gz["I"])
+    N = U + I
+    adj = torch.zeros(N, N)
+    adj[torch.from_numpy(gz["row"]), torch.from_numpy(gz["col"])] = 1.0
+    adj = adj.to(DEV)
+    users, items = torch.from_numpy(gz["users"]).to(DEV), torch.from_numpy(gz["items"]).to(DEV)
+    w = torch.from_numpy(gz["w"]).float().to(DEV)
+    for tag, p_drop in (("f64", 0.0), ("drop_f64", float(gz["drop_p"]))):
+        model = SPGACF(U, I, None, 64, [64, 64], p_drop)
+        model.load_state_dict(sd_from(gz, "sd/"))
+        model = model.to(DEV).train()
+        graph = model.gat.graph_for(adj, U)
+        assert graph.self_loops == bool(gz["self_loops"]) and graph.n_edges == gz["row"].shape[0]
+        if p_drop > 0:
+            model.gat.injected_masks = _spgacf_masks(gz, graph)
+        sc = model(users, items, adj)
+        assert rel_err(sc.detach().cpu().numpy(), gz["scores_" + tag]) < 1e-4, tag
+        (sc * w).sum().backward()
+        names = [k for k, _ in model.named_parameters()]
+        assert "gat.attention_7.W" in names and "gat.out_att.a" in names and len(names) == 20
+        for k, v in model.named_parameters():
+            assert rel_err(v.grad.cpu().numpy(), gz["grad_%s/%s" % (tag, k)]) < 1e-4, (tag, k)
+    # eval mode: the propagated features, element-wise (sparse adjacency input, inferred user count)
+    model.eval()
+    with torch.no_grad():
+        F = model.gat(model.getFeatureMat()[2], adj.to_sparse())
+    ref = gz["features_f64"]
+    assert np.abs(F.cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    # the same graph from (user, item) pairs, no dense matrix
+    g2 = HomoGraph.from_pairs(torch.from_numpy(np.stack([gz["edge_u"], gz["edge_i"]])).to(DEV), U, I, bool(gz["self_loops"]))
+    assert torch.equal(g2.rev, graph.rev) and torch.equal(g2.g.adj_idx, graph.g.adj_idx)
+    # reverse map is an involution that swaps the endpoints
+    rev = graph.rev.long()
+    assert torch.equal(rev[rev], torch.arange(rev.numel(), device=DEV))
+
+
+def test_spgat_long_rows_philox_dropout_and_refusals():
+    """rows longer than one chunk (the combine path) against the port restatement, Philox dropout determinism, and the loud refusals
+    (non-bipartite / asymmetric pattern, node without edges)."""
+    from oracle import port
+    from graphattention.SPGA import SPGACF, HomoGraph
+    rng = np.random.default_rng(5)
+    U2, I2 = 400, 500
+    u = np.concatenate([rng.integers(0, U2, 4000), np.arange(U2), np.full(300, 3), rng.integers(0, U2, 300), rng.integers(0, U2, I2)])   # user 3 / item 7: > 128 edges
+    i = np.concatenate([rng.integers(0, I2, 4000), np.arange(U2) % I2, rng.integers(0, I2, 300), np.full(300, 7), np.arange(I2)])
+    g = port.build_graph(np.stack([u, i]), U2, I2)
+    assert np.diff(g.rowptr).max() > 128 and np.diff(g.colptr).max() > 128
+    for self_loops in (False, True):
+        torch.manual_seed(3)
+        model = SPGACF(U2, I2, None, 64, [64, 64], 0.0)
+        with torch.no_grad():
+            model.uEmbd.weight.mul_(20.0)
+            model.iEmbd.weight.mul_(20.0)
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        model = model.to(DEV).train()
+        graph = HomoGraph.from_pairs(torch.from_numpy(np.stack([g.eu, g.ei])).to(DEV), U2, I2, self_loops)
+        assert graph.g.L > 0
+        users, items = torch.from_numpy(rng.integers(0, U2, 256)).to(DEV), torch.from_numpy(rng.integers(0, I2, 256)).to(DEV)
+        w = torch.from_numpy(rng.standard_normal(256)).float().to(DEV)
+        sc = model(users, items, graph)
+        (sc * w).sum().backward()
+        p = port.spgat_params_from_state_dict({k: v.double() for k, v in sd.items()})
+        row, col = port.homo_edges(g, self_loops)
+        F, caches = port.spgat_propagate(p, row, col)
+        uu, ii, ww = users.cpu(), items.cpu(), w.cpu().double()
+        want = (F[uu] * F[ii + U2]).sum(1)
+        assert rel_err(sc.detach().cpu().numpy(), want.numpy()) < 1e-4
+        dF = torch.zeros_like(F).index_add_(0, uu, ww[:, None] * F[ii + U2]).index_add_(0, ii + U2, ww[:, None] * F[uu])
+        gr = port.spgat_propagate_backward(dF, p, row, col, caches)
+        assert rel_err(model.uEmbd.weight.grad.cpu().numpy(), gr["uEmbd"].numpy()) < 1e-4
+        assert rel_err(model.iEmbd.weight.grad.cpu().numpy(), gr["iEmbd"].numpy()) < 1e-4
+        assert rel_err(model.gat.out_att.W.grad.cpu().numpy(), gr["stages"][1]["W"][0].numpy()) < 1e-4
+        assert rel_err(model.gat.out_att.a.grad.cpu().numpy()[0], gr["stages"][1]["a"][0].numpy()) < 1e-4
+        for k in range(8):
+            assert rel_err(getattr(model.gat, "attention_%d" % k).W.grad.cpu().numpy(), gr["stages"][0]["W"][k].numpy()) < 1e-4
+            assert rel_err(getattr(model.gat, "attention_%d" % k).a.grad.cpu().numpy()[0], gr["stages"][0]["a"][k].numpy()) < 1e-4
+    # Philox dropout: same (seed, call) -> same bits; training calls advance the stream
+    model.gat.dropout = 0.3
+    model.gat.drop_seed, model.gat._call = 11, 0
+    a = model(users, items, graph).detach().clone()
+    b = model(users, items, graph).detach().clone()
+    model.gat._call = 0
+    c = model(users, items, graph).detach().clone()
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    # refusals
+    N = 6
+    bad = torch.zeros(N, N, device=DEV)
+    bad[0, 1] = bad[1, 0] = 1.0            # with userNum = 3 this is a user-user edge
+    with pytest.raises(NotImplementedError):
+        HomoGraph(bad, 3)
+    asym = torch.zeros(N, N, device=DEV)
+    asym[0, 4] = 1.0
+    with pytest.raises(NotImplementedError):
+        HomoGraph(asym, 3)
+    lonely = torch.zeros(N, N, device=DEV)
+    lonely[0, 4] = lonely[4, 0] = 1.0
+    with pytest.raises(ValueError):
+        HomoGraph(lonely, 3)

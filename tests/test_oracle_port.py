@@ -442,3 +442,33 @@ def test_port_embeddings_match_reference_fixture(golden):
     F, _ = port.propagate(p, g)
     ref = gz["features_f64"]
     assert np.abs(F.numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", ["spgacf_small", "spgacf_selfloops_small"])
+def test_port_spgat_matches_reference_fixture(golden, name):
+    """The SpGAT restatement (forward and closed-form backward) against the reference's own fp64 SPGACF run -- without dropout and
+    with the fixture's injected keep masks: scores, features and every gradient to 1e-12."""
+    gz = golden(name)
+    U = int(gz["U"])
+    g = port.build_graph(np.stack([gz["edge_u"], gz["edge_i"]]), U, int(gz["I"]))
+    row, col = port.homo_edges(g, bool(gz["self_loops"]))
+    assert (row == gz["row"]).all() and (col == gz["col"]).all()
+    p = port.spgat_params_from_state_dict({k[3:]: torch.from_numpy(gz[k]) for k in gz.files if k.startswith("sd/")}, torch.float64)
+    users, items, w = (torch.from_numpy(gz[k]) for k in ("users", "items", "w"))
+    fk = [torch.from_numpy(port.unpack_feature_mask(gz["drop_feat%d" % k])) for k in (0, 1)]
+    ek = [torch.from_numpy(port.unpack_edge_mask(gz["drop_edge%d_nz" % k], H)) for k, H in ((0, 8), (1, 1))]
+    for tag, masks, dr in (("f64", (None, None), 0.0), ("drop_f64", (fk, ek), float(gz["drop_p"]))):
+        F, caches = port.spgat_propagate(p, row, col, masks[0], masks[1], dr)
+        sc = (F[users] * F[items + U]).sum(1)
+        assert np.abs(sc.numpy() - gz["scores_" + tag]).max() <= 1e-12 * np.abs(gz["scores_" + tag]).max()
+        dF = torch.zeros_like(F).index_add_(0, users, w[:, None] * F[items + U]).index_add_(0, items + U, w[:, None] * F[users])
+        gr = port.spgat_propagate_backward(dF, p, row, col, caches)
+        got = {"uEmbd.weight": gr["uEmbd"], "iEmbd.weight": gr["iEmbd"], "gat.out_att.W": gr["stages"][1]["W"][0], "gat.out_att.a": gr["stages"][1]["a"]}
+        for k in range(8):
+            got["gat.attention_%d.W" % k] = gr["stages"][0]["W"][k]
+            got["gat.attention_%d.a" % k] = gr["stages"][0]["a"][k:k + 1]
+        for k, v in got.items():
+            ref = gz["grad_%s/%s" % (tag, k)]
+            assert np.abs(v.numpy() - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-30), (tag, k)
+    F, _ = port.spgat_propagate(p, row, col)
+    assert np.abs(F.numpy() - gz["features_f64"]).max() <= 1e-12 * np.abs(gz["features_f64"]).max()
