@@ -265,8 +265,12 @@ int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, const int32_t* 
 size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users);
 int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
                         const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
-                        int32_t* top_ids, float* top_scores, int32_t* fallback, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        int32_t* top_ids, float* top_scores, int32_t* fallback, int32_t reuse_mask, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* reuse_mask: the tc path keeps, inside the workspace, a bit matrix [item tile][user][128] of the columns a user may be ranked on
+ * (item pool minus the user's train positives, train_eval_Gowalla.py:305-318,374-378).  It depends on (users, train_ptr,
+ * train_items, in_pool) only.  0: build it in this call; 1: the caller asserts that this workspace already holds the matrix built
+ * by an earlier call with the same four arrays (every evaluation after the first one of a run). */
 /* hits + metric sums (metrics.py:10-86 via get_performance, train_eval_Gowalla.py:419-429):
  * hits uint8 [n_users][20]; sums double[16] = {precision,recall,ndcg,hit}@{1,5,10,20} summed over users
  * (the caller divides by the reference's divisor, the number of users with train data, :283). */

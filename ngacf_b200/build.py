@@ -42,6 +42,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("NGACF_NVCC_EXTRA", "").split()       # debug builds only (e.g. -DNGACF_TOPK_TRACE for scripts/probe/trace_topk.py)
     procs = []
     objs = []
     for s in srcs:

@@ -30,7 +30,7 @@ constexpr int TM = 128;                 // users per CTA (UMMA M)
 constexpr int TN = 128;                 // items per tile (UMMA N)
 constexpr int KP = 24;                  // approximate candidates kept per LIST (user x segment x column half): > 20, so that a list
                                         // holding the whole top-20 still has its threshold below the 20th exact score
-constexpr int CBUF = 16;                // append-buffer entries per epilogue thread
+constexpr int CBUF = 512;               // survivor LOG entries per epilogue thread (append-only; ~250 used on the gowalla shape; overflow -> exact fallback)
 constexpr int EPI = 256;                // epilogue threads per CTA
 constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
 constexpr int K = NGACF_TOPK;
@@ -116,6 +116,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// split form for software pipelining: the registers of an issued load are only defined after tmem_ld_wait() -- which also names
+// them, so that no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+
 __device__ __forceinline__ void split_bf16x8(const float (&x)[8], uint4& hi, uint4& lo) {
     __nv_bfloat16 h[8], l[8];
 #pragma unroll
@@ -166,12 +182,47 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// allowed-column mask matrix [tile][user slot][half] (uint64 each): pool bits of the tile, minus the user's train positives.
+// Depends on (users, train set, pool) only: built once per evaluator, reused by every evaluation (reuse_mask).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_fill_kernel(const uint32_t* __restrict__ pool_bits, int n_tiles, int n_slots, int n_users,
+                                                        uint4* __restrict__ amask) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (tile, user slot)
+    if (idx >= (int64_t)n_tiles * n_slots) return;
+    const int tile = (int)(idx / n_slots), slot = (int)(idx % n_slots);
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (slot < n_users) w = __ldg(reinterpret_cast<const uint4*>(pool_bits) + tile);
+    amask[idx] = w;
+}
+__global__ void __launch_bounds__(256) mask_clear_train_kernel(const int* __restrict__ users, int n_users, const int* __restrict__ train_ptr,
+                                                               const int* __restrict__ train_items, int n_slots, uint32_t* __restrict__ amask) {
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // one warp per user
+    if (slot >= n_users) return;
+    const int lane = threadIdx.x & 31;
+    const int u = users[slot];
+    for (int e = train_ptr[u] + lane; e < train_ptr[u + 1]; e += 32) {
+        const int item = train_items[e];
+        atomicAnd(amask + ((size_t)(item / TN) * n_slots + slot) * 4 + ((item % TN) >> 5), ~(1u << (item & 31)));
+    }
+}
+
+#ifdef NGACF_TOPK_TRACE
+// pipeline timeline of two CTAs (debug builds only): [cta slot][event][tile]
+__device__ long long g_topk_trace[2][6][512];
+__device__ long long g_topk_cta[1024][4];      // per CTA (blockIdx.y == 0): globaltimer at start / end of the epilogue of warp 0, SM id, flushes of warp 0
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int smid() { int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define TRACE(ev, lt) do { if ((blockIdx.x == 0 || blockIdx.x == 100) && blockIdx.y == 0 && (lt) < 512) g_topk_trace[blockIdx.x ? 1 : 0][ev][lt] = clock64(); } while (0)
+#else
+#define TRACE(ev, lt) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* __restrict__ F, int U, const int* __restrict__ users,
-                                                                   int n_users, const int* __restrict__ train_ptr,
-                                                                   const int* __restrict__ train_items, const uint32_t* __restrict__ pool_bits,
+                                                                   int n_users, const uint2* __restrict__ amask,
                                                                    const uint8_t* __restrict__ img, int n_tiles, int S,
-                                                                   float* __restrict__ gbuf_s, int* __restrict__ gbuf_i,
-                                                                   int* __restrict__ cand_ids, float* __restrict__ cand_thr) {
+                                                                   uint2* __restrict__ gbuf, int* __restrict__ cand_ids,
+                                                                   float* __restrict__ cand_thr) {
     // no pointer arithmetic through integers here: the compiler must keep the shared address space (STS/LDS), the staging
     // stores of round 1 were generic ST.E because the base pointer had been aligned by hand through uintptr_t
     extern __shared__ __align__(128) unsigned char smem[];      // SWIZZLE_NONE operands: 16-byte alignment would do
@@ -232,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             for (int lt = 0; lt < nt; ++lt) {
                 const int st = lt & 1;
                 mbar_wait(bar_empty0 + 8 * st, (uint32_t)(((lt >> 1) & 1) ^ 1));   // ring slot free (MMAs of tile lt-2 retired)
+                TRACE(0, lt);
                 mbar_expect_tx(bar_full0 + 8 * st, TILE_BYTES);
                 bulk_g2s(smem_u32(sB) + st * TILE_BYTES, img + (size_t)(t0 + lt) * TILE_BYTES, TILE_BYTES, bar_full0 + 8 * st);
             }
@@ -244,7 +296,9 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 const int buf = lt & 1;
                 const uint32_t bH = smem_u32(sB) + buf * TILE_BYTES, bL = bH + HALF_BYTES;
                 mbar_wait(bar_full0 + 8 * buf, (uint32_t)((lt >> 1) & 1));                 // tile landed in its ring slot
+                TRACE(1, lt);
                 mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((lt >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
+                TRACE(2, lt);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);
 #pragma unroll
@@ -257,6 +311,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 }
                 umma_commit(bar_empty0 + 8 * buf);            // ring slot reusable once these MMAs retire
                 umma_commit(bar_tfull0 + 8 * buf);            // accumulator ready for the epilogue
+                TRACE(3, lt);
             }
         }
     } else {
@@ -267,101 +322,151 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         const int et = half * TM + r;                         // epilogue thread id 0..255
         const int uslot = u0 + r;
         const int user = uslot < n_users ? users[uslot] : -1;
-        int cur = 0;
-        const int tend = user >= 0 ? train_ptr[user + 1] : 0;
-        if (user >= 0) {                                      // first train item of this user inside the segment (lower bound)
-            int lo = train_ptr[user], hi = tend;
-            const int first_item = t0 * TN;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (train_items[mid] < first_item) lo = mid + 1; else hi = mid;
-            }
-            cur = lo;
-        }
-        int nxt = (user >= 0 && cur < tend) ? train_items[cur] : 0x7fffffff;
-        // candidate list: KP (score, id) pairs sorted by descending score, entirely in registers
+        // The KP best SCORES so far, sorted descending, entirely in registers; thr = ls[KP-1] filters the accumulators.  The item ids
+        // are not carried through the sort: every survivor is appended to this thread's LOG in global memory (append-only,
+        // interleaved over the CTA's epilogue threads: a warp's entries of one index share a 256-byte segment), and the final
+        // candidates are the log entries with score >= the final threshold.
         float ls[KP];
-        int li[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) { ls[k] = -INFINITY; li[k] = -1; }
+        for (int k = 0; k < KP; ++k) ls[k] = -INFINITY;
         float thr = -INFINITY;                                // == ls[KP-1]
-        // append buffer of this thread (global memory, interleaved over the CTA's epilogue threads: coalesced, L1/L2 resident)
         const size_t cta_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        float* bS = gbuf_s + cta_lin * (CBUF * EPI) + et;
-        int* bI = gbuf_i + cta_lin * (CBUF * EPI) + et;
-        int cnt = 0;
-        auto flush = [&]() {                                  // merge the buffered survivors into the sorted list
-            for (int e = 0; e < cnt; ++e) {
-                const float sc = bS[e * EPI];
-                const int id = bI[e * EPI];
-                if (sc > thr) {
+        uint2* bE = gbuf + cta_lin * (CBUF * EPI) + et;
+        int cnt = 0, done = 0, overflow = 0;                  // log entries written / already merged into ls
+#ifdef NGACF_TOPK_TRACE
+        int n_flush = 0;
+        const long long t_begin = gtimer();
+#endif
+        // merge the log entries [done, cnt) into the sorted scores (warp-collective).  Runs on a FIXED tile schedule, the same for
+        // all eight epilogue warps of the CTA: a merge takes thousands of cycles during which the warp does not drain its part of
+        // the accumulator, i.e. the whole CTA pipeline waits -- with per-warp triggers (a lane's buffer filling up) the eight warps
+        // stalled the pipeline at eight different tiles per round (measured: 40 % of the kernel, scripts/probe/trace_topk.py).
+        auto flush = [&]() {
+#ifdef NGACF_TOPK_TRACE
+            ++n_flush;
+#endif
+            // every lane walks ITS OWN new entries (the logs of the 32 lanes drift apart by dozens of entries: a common index range
+            // was three times longer than any lane's share), eight loads in flight (the entries were written long ago: L2 latency)
+            const int nnew = cnt - done;
+            const int nmax = __reduce_max_sync(0xffffffffu, nnew);
+#pragma unroll 1
+            for (int i0 = 0; i0 < nmax; i0 += 8) {
+                float sb[8];
 #pragma unroll
-                    for (int k = KP - 1; k > 0; --k) {
-                        const bool shift = ls[k - 1] < sc;
-                        const bool here = ls[k] < sc;
-                        li[k] = shift ? li[k - 1] : (here ? id : li[k]);
-                        ls[k] = shift ? ls[k - 1] : (here ? sc : ls[k]);
+                for (int q = 0; q < 8; ++q) sb[q] = i0 + q < nnew ? __uint_as_float(bE[(size_t)(done + i0 + q) * EPI].x) : -INFINITY;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float sc = sb[q];
+                    if (__any_sync(0xffffffffu, sc > thr)) {              // most logged entries are below the threshold by now
+                        // sorted insertion without predicates: ls'[k] = max(ls[k], min(ls[k-1], sc)) -- unchanged where sc <= ls[k],
+                        // sc where ls[k] < sc <= ls[k-1], the shifted ls[k-1] above; a lane whose sc <= thr changes nothing
+#pragma unroll
+                        for (int k = KP - 1; k > 0; --k) ls[k] = fmaxf(ls[k], fminf(ls[k - 1], sc));
+                        ls[0] = fmaxf(ls[0], sc);
+                        thr = ls[KP - 1];
                     }
-                    if (ls[0] < sc) { ls[0] = sc; li[0] = id; }
-                    thr = ls[KP - 1];
                 }
             }
-            cnt = 0;
+            done = cnt;
         };
+        // allowed columns (item pool minus this user's train positives) of this thread's 64 columns: one 8-byte word per tile from
+        // the mask matrix [tile][user slot][half] (coalesced over the warp), requested one tile ahead.  Rows past n_users are zero.
+        const size_t mstride = (size_t)gridDim.x * TM * 2;
+        const uint2* mrow = amask + (size_t)uslot * 2 + half;
+        uint2 mnext = nt > 0 ? __ldg(mrow + (size_t)t0 * mstride) : make_uint2(0u, 0u);
         for (int lt = 0; lt < nt; ++lt) {
             const int buf = lt & 1;
             const int item0 = (t0 + lt) * TN + half * 64;     // first item of this thread's 64 columns
-            unsigned tw0 = 0, tw1 = 0;                        // train positives of this user inside those 64 columns
-            const int tile_end = (t0 + lt + 1) * TN;
-            while (nxt < tile_end) {                          // nxt = the user's next train item, loaded ahead of its tile
-                const int off = nxt - item0;
-                if (off >= 0 && off < 64) {
-                    const unsigned bit = 1u << (off & 31);
-                    tw0 |= off < 32 ? bit : 0u;
-                    tw1 |= off >= 32 ? bit : 0u;
-                }
-                ++cur;
-                nxt = cur < tend ? train_items[cur] : 0x7fffffff;
-            }
-            const unsigned pw0 = user >= 0 ? (__ldg(pool_bits + (t0 + lt) * 4 + half * 2) & ~tw0) : 0u;
-            const unsigned pw1 = user >= 0 ? (__ldg(pool_bits + (t0 + lt) * 4 + half * 2 + 1) & ~tw1) : 0u;
+            const unsigned pw0 = mnext.x, pw1 = mnext.y;
+            if (lt + 1 < nt) mnext = __ldg(mrow + (size_t)(t0 + lt + 1) * mstride);
+            // merge schedule: tiles 1, 2, 3, 4, 6, 8, 12, 16, 24, ... (a power of two or three times one): the threshold is at most
+            // 1.5x "stale", ~12 new survivors per lane and round
+            if (lt > 0 && ((lt & (lt - 1)) == 0 || (lt % 3 == 0 && ((lt / 3) & (lt / 3 - 1)) == 0))) flush();
             mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
+            if (warp == 0 && lane == 0) TRACE(4, lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int pc = 0; pc < 4; ++pc) {                  // four 16-column pieces of this thread's 64 columns
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + half * 64 + pc * 16), v);
-                const unsigned allowed = ((pc < 2 ? pw0 : pw1) >> ((pc & 1) * 16)) & 0xFFFFu;
-                // threshold filter on the registers; the survivors are picked up again from a shared-memory copy so that the
-                // append code exists once instead of 16 times
-                unsigned hit = 0;
+            // four 16-column pieces of this thread's 64 columns, software-pipelined: the tcgen05.ld of piece pc+1 is in flight while
+            // piece pc is filtered (the epilogue is a latency chain per warp, and the CTA pipeline waits for its slowest warp)
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + half * 64);
+            uint32_t va[16], vb[16];
+            tmem_ld16_issue(taddr0, va);
+            auto piece = [&](const uint32_t (&v)[16], int pc) {
+                // threshold filter: two instructions per accumulator (FSETP, predicated OR of the column's bit), four short chains
+                unsigned h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+#define NGACF_HIT(h, j, bit) asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, " #bit ";\n\t}" : "+r"(h) : "f"(__uint_as_float(v[j])), "f"(thr))
+                NGACF_HIT(h0, 0, 0x1); NGACF_HIT(h1, 4, 0x10); NGACF_HIT(h2, 8, 0x100); NGACF_HIT(h3, 12, 0x1000);
+                NGACF_HIT(h0, 1, 0x2); NGACF_HIT(h1, 5, 0x20); NGACF_HIT(h2, 9, 0x200); NGACF_HIT(h3, 13, 0x2000);
+                NGACF_HIT(h0, 2, 0x4); NGACF_HIT(h1, 6, 0x40); NGACF_HIT(h2, 10, 0x400); NGACF_HIT(h3, 14, 0x4000);
+                NGACF_HIT(h0, 3, 0x8); NGACF_HIT(h1, 7, 0x80); NGACF_HIT(h2, 11, 0x800); NGACF_HIT(h3, 15, 0x8000);
+#undef NGACF_HIT
+                unsigned hit = (h0 | h1) | (h2 | h3);
+                hit &= ((pc < 2 ? pw0 : pw1) >> ((pc & 1) * 16)) & 0xFFFFu;      // item pool minus this user's train positives
+                if (__any_sync(0xffffffffu, hit != 0)) {
+                    // the survivors are picked up from a shared-memory copy (own slots only: thread stride 16 B, conflict-free), so
+                    // that the append code exists once instead of 16 times and no register is indexed dynamically
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)               // staging: four 16-byte stores (thread stride 16 B: conflict-free)
-                    Vs4[q4 * EPI + et] = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
-                                                     __uint_as_float(v[4 * q4 + 3]));
-#pragma unroll
-                for (int j = 0; j < 16; ++j) hit |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
-                hit &= allowed;
-                const int n = __popc(hit);                    // <= 16 = CBUF: fits after a flush
-                if (__any_sync(0xffffffffu, cnt + n > CBUF)) flush();
-                while (hit) {                                 // lanes append their own survivors in parallel
-                    const int j = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    bS[cnt * EPI] = reinterpret_cast<const float*>(Vs4 + (j >> 2) * EPI + et)[j & 3];
-                    bI[cnt * EPI] = item0 + pc * 16 + j;
-                    ++cnt;
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        Vs4[q4 * EPI + et] = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                                                         __uint_as_float(v[4 * q4 + 3]));
+                    while (hit) {                             // lanes append their own survivors in parallel
+                        const int j = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        if (cnt < CBUF) {
+                            bE[(size_t)cnt * EPI] = make_uint2(reinterpret_cast<const uint32_t*>(Vs4 + (j >> 2) * EPI + et)[j & 3], (uint32_t)(item0 + pc * 16 + j));
+                            ++cnt;
+                        } else {
+                            overflow = 1;                     // pathological score order: this list goes to the exact fallback
+                        }
+                    }
                 }
-            }
+            };
+            tmem_ld_wait(va);
+            tmem_ld16_issue(taddr0 + 16, vb);
+            piece(va, 0);
+            tmem_ld_wait(vb);
+            tmem_ld16_issue(taddr0 + 32, va);
+            piece(vb, 1);
+            tmem_ld_wait(va);
+            tmem_ld16_issue(taddr0 + 48, vb);
+            piece(va, 2);
+            tmem_ld_wait(vb);
+            piece(vb, 3);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty0 + 8 * buf);
+            if (warp == 0 && lane == 0) TRACE(5, lt);
         }
         flush();
-        if (user >= 0) {
-            const size_t list = ((size_t)uslot * S + seg) * 2 + half;
+#ifdef NGACF_TOPK_TRACE
+        if (warp == 0 && lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
+            g_topk_cta[blockIdx.x][0] = t_begin; g_topk_cta[blockIdx.x][1] = gtimer(); g_topk_cta[blockIdx.x][2] = smid(); g_topk_cta[blockIdx.x][3] = n_flush;
+        }
+#endif
+        // candidates = the logged survivors at or above the final threshold (ties beyond KP stay out: they are <= cand_thr)
+        {
+            const size_t list = ((size_t)(user >= 0 ? uslot : 0) * S + seg) * 2 + half;
+            const int e_hi = __reduce_max_sync(0xffffffffu, cnt);
+            int emitted = 0, tie_left = KP;               // entries equal to the threshold may only fill what the larger ones leave
 #pragma unroll
-            for (int k = 0; k < KP; ++k) cand_ids[list * KP + k] = li[k];
-            cand_thr[list] = li[KP - 1] >= 0 ? thr : -INFINITY;
+            for (int k = 0; k < KP; ++k) tie_left -= ls[k] > thr ? 1 : 0;
+            uint2 n0 = 0 < cnt ? bE[0] : make_uint2(0xff800000u, 0xffffffffu);
+#pragma unroll 1
+            for (int e = 0; e < e_hi; ++e) {
+                const uint2 cur_e = n0;
+                n0 = e + 1 < cnt ? bE[(size_t)(e + 1) * EPI] : make_uint2(0xff800000u, 0xffffffffu);
+                if (user >= 0 && e < cnt && emitted < KP) {
+                    const float sc = __uint_as_float(cur_e.x);
+                    const bool tie = sc == thr && tie_left > 0;
+                    if (sc > thr || tie) {
+                        cand_ids[list * KP + emitted++] = (int)cur_e.y;
+                        tie_left -= tie ? 1 : 0;
+                    }
+                }
+            }
+            if (user >= 0) {
+                for (int k = emitted; k < KP; ++k) cand_ids[list * KP + k] = -1;
+                cand_thr[list] = overflow ? INFINITY : thr;   // list not full: thr = -inf (there is no non-candidate)
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -469,18 +574,28 @@ static int plan_segments(int n_users, int n_tiles) {
     return S;
 }
 
+#ifdef NGACF_TOPK_TRACE
+extern "C" int ngacf_debug_topk_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, tc::g_topk_trace, sizeof(tc::g_topk_trace));
+}
+extern "C" int ngacf_debug_topk_cta(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, tc::g_topk_cta, sizeof(tc::g_topk_cta));
+}
+#endif
+
 extern "C" size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users) {
     const size_t n_tiles = (size_t)(I + tc::TN - 1) / tc::TN;
     const int S = plan_segments(n_users, (int)n_tiles);
     const size_t lists = (size_t)n_users * 2 * S;
     const size_t ctas = (size_t)((n_users + tc::TM - 1) / tc::TM) * S;
+    const size_t slots = (size_t)((n_users + tc::TM - 1) / tc::TM) * tc::TM;
     return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + al256(lists * tc::KP * 4) + al256(lists * 4) +
-           2 * al256(ctas * tc::CBUF * tc::EPI * 4) + 1024;
+           al256(ctas * tc::CBUF * tc::EPI * 8) + al256(n_tiles * slots * 16) + 1024;
 }
 
 extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users, const int32_t* train_ptr,
                                    const int32_t* train_items, const uint8_t* in_pool, int32_t* top_ids, float* top_scores,
-                                   int32_t* fallback, void* workspace, size_t workspace_bytes, void* stream) {
+                                   int32_t* fallback, int32_t reuse_mask, void* workspace, size_t workspace_bytes, void* stream) {
     NGACF_REQUIRE(F && users && train_ptr && train_items && in_pool && top_ids && top_scores && fallback && workspace && U > 0 && I > 0,
                   "score_topk_tc: null/empty argument");
     if (workspace_bytes < ngacf_score_topk_tc_workspace_bytes(I, n_users)) { set_error("score_topk_tc: workspace too small"); return NGACF_ERR_WORKSPACE; }
@@ -497,16 +612,22 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     unsigned int* maxnorm = (unsigned int*)w;           w += 256;
     int* cand_ids = (int*)w;                            w += al256(lists * tc::KP * 4);
     float* cand_thr = (float*)w;                        w += al256(lists * 4);
-    float* gbuf_s = (float*)w;                          w += al256(ctas * tc::CBUF * tc::EPI * 4);
-    int* gbuf_i = (int*)w;
+    uint2* gbuf = (uint2*)w;                            w += al256(ctas * tc::CBUF * tc::EPI * 8);
+    uint4* amask = (uint4*)w;                           // [tile][user slot]: persists in the caller's workspace between calls
+    const int n_slots = blocks * tc::TM;
     cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
     tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
+    if (!reuse_mask) {
+        tc::mask_fill_kernel<<<ceil_div((int64_t)n_tiles * n_slots, 256), 256, 0, st>>>(pool_bits, n_tiles, n_slots, n_users, amask);
+        tc::mask_clear_train_kernel<<<ceil_div((int64_t)n_users * 32, 256), 256, 0, st>>>(users, n_users, train_ptr, train_items, n_slots,
+                                                                                          reinterpret_cast<uint32_t*>(amask));
+    }
     static PerDeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
-    tc::score_topk_tc_kernel<<<dim3(blocks, S), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, train_ptr, train_items, pool_bits, img,
-                                                                                  n_tiles, S, gbuf_s, gbuf_i, cand_ids, cand_thr);
+    tc::score_topk_tc_kernel<<<dim3(blocks, S), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, reinterpret_cast<const uint2*>(amask), img,
+                                                                                  n_tiles, S, gbuf, cand_ids, cand_thr);
     tc::rescore_kernel<<<ceil_div(n_users, tc::RS_GROUPS), tc::RS_GROUPS * 16, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, 2 * S, maxnorm,
                                                                                        top_ids, top_scores, fallback);
     return check_launch("score_topk_tc");

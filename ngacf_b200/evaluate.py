@@ -50,9 +50,16 @@ class AllNegEvaluator:
         if n == 0:
             return
         if self._use_tc():
+            # the workspace also carries the allowed-column matrix of (users, train set, pool): built by the first call, reused while
+            # this evaluator's users tensor and the interactions' arrays are the same objects at the same version
+            key = (self.users.data_ptr(), self.users._version, it.train_ptr.data_ptr(), it.train_ptr._version, it.train_items.data_ptr(),
+                   it.train_items._version, it.in_pool.data_ptr(), it.in_pool._version)
             if self._tc_ws is None:
                 self._tc_ws = torch.empty(ops.score_topk_tc_workspace_bytes(it.I, n), dtype=torch.uint8, device=Z.device)
-            ops.score_topk_tc(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws)
+                self._mask_key = None
+            ops.score_topk_tc(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws,
+                              reuse_mask=self._mask_key == key)
+            self._mask_key = key
             bad = torch.nonzero(self.fallback[:n]).flatten()
             if bad.numel():       # rows whose error guard failed: recompute exactly
                 users = self.users[bad].contiguous()

@@ -224,9 +224,10 @@ def score_topk_tc_workspace_bytes(I, n_users):
     return int(_lib.load().ngacf_score_topk_tc_workspace_bytes(I, n_users))
 
 
-def score_topk_tc(F, U, I, users, inter, top_ids, top_scores, fallback, ws):
+def score_topk_tc(F, U, I, users, inter, top_ids, top_scores, fallback, ws, reuse_mask=False):
+    """reuse_mask: `ws` already holds the allowed-column matrix of (users, inter) from an earlier call (include/ngacf_b200.h)"""
     _lib.call("ngacf_score_topk_tc", _p(F), U, I, _p(users), users.numel(), _p(inter.train_ptr), _p(inter.train_items),
-              _p(inter.in_pool), _p(top_ids), _p(top_scores), _p(fallback), _p(ws), ws.numel() * ws.element_size(), _s())
+              _p(inter.in_pool), _p(top_ids), _p(top_scores), _p(fallback), int(bool(reuse_mask)), _p(ws), ws.numel() * ws.element_size(), _s())
 
 
 def eval_metrics(top_ids, users, inter, hits, sums, ws):
