@@ -257,7 +257,8 @@ int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr,
  *          other item can enter the top-20; rows whose proof fails are flagged in `fallback` (the caller recomputes
  *          them through the exact entry point), so the returned ids are always the exact ones.
  * F = ELU(Z_last) (N,64) final features (ngacf_final_features).  in_pool: uint8[I].
- * top_ids int32 [n_users][20] (-1 padded), top_scores fp32 likewise.
+ * top_ids int32 [n_users][20] (-1 padded), top_scores fp32 likewise.  fallback (tc only): int32[n_users + 1], flag per user and, in
+ * the last element, the number of flagged users.
  * ------------------------------------------------------------------------------------------- */
 int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
                            const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,

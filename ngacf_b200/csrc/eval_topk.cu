@@ -3,6 +3,7 @@
 // kernel -- the (users x items) score matrix never exists in HBM.  Plus hit lists and metric sums.
 // Replaces train_eval_Gowalla.py:300-341 (64x2048 tiles through model(), D2H per tile),
 // :370-385 (heapq.nlargest over a dict per user), :419-429 + metrics.py:10-86.
+#include <cmath>
 #include "common.cuh"
 
 namespace ngacf {
@@ -144,6 +145,10 @@ __global__ void __launch_bounds__(EX_THREADS) score_topk_exact_kernel(const floa
 // ------------------------------------------------------------------------------------------------
 // hit lists + metrics (metrics.py:10-86 through get_performance, train_eval_Gowalla.py:419-429)
 // ------------------------------------------------------------------------------------------------
+// 1 / log2(k + 2), k = 0..19, in double (metrics.py:52-53: np.log2(np.arange(2, size + 2))); evaluated once on the host -- fp64
+// transcendental code was most of this kernel's time
+__constant__ double c_disc[K];
+
 __global__ void __launch_bounds__(128) eval_metrics_kernel(const int* __restrict__ top_ids, const int* __restrict__ users, int n_users,
                                                            const int* __restrict__ test_ptr, const int* __restrict__ test_items,
                                                            uint8_t* __restrict__ hits, double* __restrict__ partial /* [gridDim.x][16] */) {
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(128) eval_metrics_kernel(const int* __restrict
             int h = 0;
             double dcg = 0.0, idcg = 0.0;
             for (int k = 0; k < KK; ++k) {
-                const double disc = 1.0 / log2((double)(k + 2));
+                const double disc = c_disc[k];
                 if ((r >> k) & 1u) { ++h; dcg += disc; }
                 if (k < total_hits) idcg += disc;        // ideal = the top-20 hit list itself, sorted (metrics.py:69-73)
             }
@@ -199,12 +204,14 @@ __global__ void __launch_bounds__(128) eval_metrics_kernel(const int* __restrict
 }
 
 // fixed-order sum of the block partials
-__global__ void eval_metrics_reduce_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ sums) {
-    const int c = threadIdx.x;
-    if (c >= 16) return;
+// 16 warps, one per metric column: lane l sums blocks l, l+32, ... in order, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(512) eval_metrics_reduce_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ sums) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * 16 + c];
-    sums[c] = acc;
+    for (int b = lane; b < nblocks; b += 32) acc += partial[(int64_t)b * 16 + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sums[c] = acc;
 }
 
 }  // namespace ngacf
@@ -233,7 +240,13 @@ extern "C" int ngacf_eval_metrics(const int32_t* top_ids, const int32_t* users, 
     if (workspace_bytes < ngacf_eval_metrics_workspace_bytes(n_users)) { set_error("eval_metrics: workspace too small"); return NGACF_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n_users == 0) { cudaMemsetAsync(sums, 0, 16 * sizeof(double), st); return NGACF_OK; }
+    static PerDeviceOnce once;
+    once.run([] {
+        double disc[K];
+        for (int k = 0; k < K; ++k) disc[k] = 1.0 / std::log2((double)(k + 2));
+        cudaMemcpyToSymbol(c_disc, disc, sizeof(disc));
+    });
     eval_metrics_kernel<<<ceil_div(n_users, 128), 128, 0, st>>>(top_ids, users, n_users, test_ptr, test_items, hits, (double*)workspace);
-    eval_metrics_reduce_kernel<<<1, 32, 0, st>>>((const double*)workspace, ceil_div(n_users, 128), sums);
+    eval_metrics_reduce_kernel<<<1, 512, 0, st>>>((const double*)workspace, ceil_div(n_users, 128), sums);
     return check_launch("eval_metrics");
 }

@@ -291,10 +291,21 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t aH = smem_u32(sA), aL = aH + HALF_BYTES;
-            for (int lt = 0; lt < nt; ++lt) {
-                const int buf = lt & 1;
-                const uint32_t bH = smem_u32(sB) + buf * TILE_BYTES, bL = bH + HALF_BYTES;
+            // all 24 operand descriptors are loop invariants (two ring slots): built once, the issue loop is then 12 back-to-back
+            // MMAs -- it was ~90 cycles per MMA of descriptor arithmetic, longer than the MMA itself, and sits on the critical path
+            // accumulator drained -> MMAs issued -> accumulator full -> epilogue
+            uint64_t dA[2][4], dB[2][2][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                dA[0][ks] = smem_desc(smem_u32(sA) + ks * 2 * PANEL);
+                dA[1][ks] = smem_desc(smem_u32(sA) + HALF_BYTES + ks * 2 * PANEL);
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    dB[b][0][ks] = smem_desc(smem_u32(sB) + b * TILE_BYTES + ks * 2 * PANEL);
+                    dB[b][1][ks] = smem_desc(smem_u32(sB) + b * TILE_BYTES + HALF_BYTES + ks * 2 * PANEL);
+                }
+            }
+            auto issue = [&](int lt, const uint64_t (&bd)[2][4], int buf) {
                 mbar_wait(bar_full0 + 8 * buf, (uint32_t)((lt >> 1) & 1));                 // tile landed in its ring slot
                 TRACE(1, lt);
                 mbar_wait(bar_tempty0 + 8 * buf, (uint32_t)(((lt >> 1) & 1) ^ 1));         // accumulator drained by the epilogue
@@ -302,16 +313,18 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + (uint32_t)(buf * TN);
 #pragma unroll
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t a0 = term == 2 ? aL : aH;
-                    const uint32_t b0 = term == 1 ? bL : bH;
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dA[0][ks], bd[0][ks], ks ? 1u : 0u);      // hi . hi   (K = 16 per MMA)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)            // K = 16 per MMA = two k-chunk panels
-                        umma_bf16(d, smem_desc(a0 + ks * 2 * PANEL), smem_desc(b0 + ks * 2 * PANEL), (term | ks) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dA[0][ks], bd[1][ks], 1u);                // hi . lo
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dA[1][ks], bd[0][ks], 1u);                // lo . hi
                 umma_commit(bar_empty0 + 8 * buf);            // ring slot reusable once these MMAs retire
                 umma_commit(bar_tfull0 + 8 * buf);            // accumulator ready for the epilogue
                 TRACE(3, lt);
+            };
+            for (int lt = 0; lt < nt; lt += 2) {
+                issue(lt, dB[0], 0);
+                if (lt + 1 < nt) issue(lt + 1, dB[1], 1);
             }
         }
     } else {
@@ -330,6 +343,10 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
 #pragma unroll
         for (int k = 0; k < KP; ++k) ls[k] = -INFINITY;
         float thr = -INFINITY;                                // == ls[KP-1]
+        // FILTER threshold: max of this list's thr and that of the user's other column half (exchanged at every merge).  The KP-th
+        // best of the union of the two halves is >= either list's KP-th best, so it is a valid bound for both -- and the tighter
+        // filter logs ~40 % fewer survivors (24 ln(N/24) per user instead of twice 24 ln(N/48)).
+        float T = -INFINITY;
         const size_t cta_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
         uint2* bE = gbuf + cta_lin * (CBUF * EPI) + et;
         int cnt = 0, done = 0, overflow = 0;                  // log entries written / already merged into ls
@@ -346,16 +363,16 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             ++n_flush;
 #endif
             // every lane walks ITS OWN new entries (the logs of the 32 lanes drift apart by dozens of entries: a common index range
-            // was three times longer than any lane's share), eight loads in flight (the entries were written long ago: L2 latency)
+            // was three times longer than any lane's share), sixteen loads in flight (the entries were written long ago: L2 latency)
             const int nnew = cnt - done;
             const int nmax = __reduce_max_sync(0xffffffffu, nnew);
 #pragma unroll 1
-            for (int i0 = 0; i0 < nmax; i0 += 8) {
-                float sb[8];
+            for (int i0 = 0; i0 < nmax; i0 += 16) {
+                float sb[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) sb[q] = i0 + q < nnew ? __uint_as_float(bE[(size_t)(done + i0 + q) * EPI].x) : -INFINITY;
+                for (int q = 0; q < 16; ++q) sb[q] = i0 + q < nnew ? __uint_as_float(bE[(size_t)(done + i0 + q) * EPI].x) : -INFINITY;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 16; ++q) {
                     const float sc = sb[q];
                     if (__any_sync(0xffffffffu, sc > thr)) {              // most logged entries are below the threshold by now
                         // sorted insertion without predicates: ls'[k] = max(ls[k], min(ls[k-1], sc)) -- unchanged where sc <= ls[k],
@@ -368,6 +385,13 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 }
             }
             done = cnt;
+            // exchange with the thread that owns the other column half of this user row: through the own staging slots (nobody
+            // else touches them), between two named barriers of the 256 epilogue threads -- every epilogue warp of the CTA runs
+            // the same merge schedule, so the barrier counts match
+            reinterpret_cast<float*>(Vs4 + et)[0] = thr;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            T = fmaxf(thr, reinterpret_cast<const float*>(Vs4 + (et ^ TM))[0]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         };
         // allowed columns (item pool minus this user's train positives) of this thread's 64 columns: one 8-byte word per tile from
         // the mask matrix [tile][user slot][half] (coalesced over the warp), requested one tile ahead.  Rows past n_users are zero.
@@ -379,9 +403,9 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             const int item0 = (t0 + lt) * TN + half * 64;     // first item of this thread's 64 columns
             const unsigned pw0 = mnext.x, pw1 = mnext.y;
             if (lt + 1 < nt) mnext = __ldg(mrow + (size_t)(t0 + lt + 1) * mstride);
-            // merge schedule: tiles 1, 2, 3, 4, 6, 8, 12, 16, 24, ... (a power of two or three times one): the threshold is at most
-            // 1.5x "stale", ~12 new survivors per lane and round
-            if (lt > 0 && ((lt & (lt - 1)) == 0 || (lt % 3 == 0 && ((lt / 3) & (lt / 3 - 1)) == 0))) flush();
+            // merge schedule: tiles 1, 2, 4, 8, 16, ...: a merge costs ~10k cycles of a stalled CTA pipeline, a survivor logged
+            // because the threshold is stale ~0.3k; doubling intervals are near the optimum of that trade
+            if (lt > 0 && (lt & (lt - 1)) == 0) flush();
             mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
             if (warp == 0 && lane == 0) TRACE(4, lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -393,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             auto piece = [&](const uint32_t (&v)[16], int pc) {
                 // threshold filter: two instructions per accumulator (FSETP, predicated OR of the column's bit), four short chains
                 unsigned h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-#define NGACF_HIT(h, j, bit) asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, " #bit ";\n\t}" : "+r"(h) : "f"(__uint_as_float(v[j])), "f"(thr))
+#define NGACF_HIT(h, j, bit) asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, " #bit ";\n\t}" : "+r"(h) : "f"(__uint_as_float(v[j])), "f"(T))
                 NGACF_HIT(h0, 0, 0x1); NGACF_HIT(h1, 4, 0x10); NGACF_HIT(h2, 8, 0x100); NGACF_HIT(h3, 12, 0x1000);
                 NGACF_HIT(h0, 1, 0x2); NGACF_HIT(h1, 5, 0x20); NGACF_HIT(h2, 9, 0x200); NGACF_HIT(h3, 13, 0x2000);
                 NGACF_HIT(h0, 2, 0x4); NGACF_HIT(h1, 6, 0x40); NGACF_HIT(h2, 10, 0x400); NGACF_HIT(h3, 14, 0x4000);
@@ -442,13 +466,14 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             g_topk_cta[blockIdx.x][0] = t_begin; g_topk_cta[blockIdx.x][1] = gtimer(); g_topk_cta[blockIdx.x][2] = smid(); g_topk_cta[blockIdx.x][3] = n_flush;
         }
 #endif
-        // candidates = the logged survivors at or above the final threshold (ties beyond KP stay out: they are <= cand_thr)
+        // candidates = the logged survivors at or above the final (shared) threshold: at most KP per list, since the entries above
+        // T >= thr are part of this list's own top KP (ties beyond KP stay out: they are <= cand_thr)
         {
             const size_t list = ((size_t)(user >= 0 ? uslot : 0) * S + seg) * 2 + half;
             const int e_hi = __reduce_max_sync(0xffffffffu, cnt);
             int emitted = 0, tie_left = KP;               // entries equal to the threshold may only fill what the larger ones leave
 #pragma unroll
-            for (int k = 0; k < KP; ++k) tie_left -= ls[k] > thr ? 1 : 0;
+            for (int k = 0; k < KP; ++k) tie_left -= ls[k] > T ? 1 : 0;
             uint2 n0 = 0 < cnt ? bE[0] : make_uint2(0xff800000u, 0xffffffffu);
 #pragma unroll 1
             for (int e = 0; e < e_hi; ++e) {
@@ -456,8 +481,8 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 n0 = e + 1 < cnt ? bE[(size_t)(e + 1) * EPI] : make_uint2(0xff800000u, 0xffffffffu);
                 if (user >= 0 && e < cnt && emitted < KP) {
                     const float sc = __uint_as_float(cur_e.x);
-                    const bool tie = sc == thr && tie_left > 0;
-                    if (sc > thr || tie) {
+                    const bool tie = sc == T && tie_left > 0;
+                    if (sc > T || tie) {
                         cand_ids[list * KP + emitted++] = (int)cur_e.y;
                         tie_left -= tie ? 1 : 0;
                     }
@@ -465,7 +490,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             }
             if (user >= 0) {
                 for (int k = emitted; k < KP; ++k) cand_ids[list * KP + k] = -1;
-                cand_thr[list] = overflow ? INFINITY : thr;   // list not full: thr = -inf (there is no non-candidate)
+                cand_thr[list] = overflow ? INFINITY : T;     // neither half's list full: T = -inf (there is no non-candidate)
             }
         }
     }
@@ -504,13 +529,22 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     if (j >= n_users) return;                                  // whole groups leave together; no block-level barrier below
     const int lane16 = threadIdx.x & 15;
     const unsigned gm = group_mask();
-    const int NC = n_lists * KP;
     const int64_t u = users[j];
     const float4 fu = ld_gather4(F + u * D + lane16 * 4);
     const float unorm = sqrtf(dot64_tree_g(fu, fu, gm));
     float* scs = sc_s[grp];
     int* ids = id_s[grp];
-    for (int c = lane16; c < NC; c += 16) ids[c] = cand_ids[(int64_t)j * NC + c];
+    // the lists are mostly padding (-1): with the shared filter threshold a user's two lists hold ~24-30 candidates out of 2*KP slots;
+    // compact them first (the ranking below is quadratic in the count)
+    const int NC_all = n_lists * KP;
+    int NC = 0;
+    const int gshift = (threadIdx.x & 16);
+    for (int c0 = 0; c0 < NC_all; c0 += 16) {
+        const int id = c0 + lane16 < NC_all ? cand_ids[(int64_t)j * NC_all + c0 + lane16] : -1;
+        const unsigned m = (__ballot_sync(gm, id >= 0) >> gshift) & 0xFFFFu;
+        if (id >= 0) ids[NC + __popc(m & ((1u << lane16) - 1u))] = id;
+        NC += __popc(m);
+    }
     __syncwarp(gm);
     for (int c0 = 0; c0 < NC; c0 += 4) {                        // exact scores, four candidate rows in flight
         float4 fi[4];
@@ -554,7 +588,10 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     for (int o = 1; o < 16; o <<= 1) thr = fmaxf(thr, __shfl_xor_sync(gm, thr, o, 16));
     const float delta = GUARD * unorm * __uint_as_float(*maxnorm_bits);
     const bool ok = (thr == -INFINITY) || (nvalid >= K && thr + delta < tau);
-    if (lane16 == 0) fallback[j] = ok ? 0 : 1;
+    if (lane16 == 0) {
+        fallback[j] = ok ? 0 : 1;
+        if (!ok) atomicAdd(fallback + n_users, 1);              // number of flagged rows: the caller reads one int instead of scanning
+    }
 }
 
 }  // namespace tc
@@ -616,6 +653,7 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     uint4* amask = (uint4*)w;                           // [tile][user slot]: persists in the caller's workspace between calls
     const int n_slots = blocks * tc::TM;
     cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
+    cudaMemsetAsync(fallback + n_users, 0, sizeof(int32_t), st);
     tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
     if (!reuse_mask) {
         tc::mask_fill_kernel<<<ceil_div((int64_t)n_tiles * n_slots, 256), 256, 0, st>>>(pool_bits, n_tiles, n_slots, n_users, amask);

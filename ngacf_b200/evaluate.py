@@ -22,14 +22,15 @@ class AllNegEvaluator:
         self.users = inter.eval_users if users is None else users.to(torch.int32).contiguous()
         dev = inter.device
         n = self.users.numel()
-        self.top_ids = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
-        self.top_scores = torch.empty((max(n, 1), K), dtype=torch.float32, device=dev)
+        self._top_ids = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
+        self._top_scores = torch.empty((max(n, 1), K), dtype=torch.float32, device=dev)
         self.hits = torch.empty((max(n, 1), K), dtype=torch.uint8, device=dev)
         self.sums = torch.zeros(16, dtype=torch.float64, device=dev)
         self.metric_ws = torch.empty(max(n, 1) * 16, dtype=torch.float64, device=dev)
         self.F = None
         self._tc_ws = None
-        self.fallback = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        self.fallback = torch.zeros(max(n, 1) + 1, dtype=torch.int32, device=dev)      # flag per user + number of flagged users
+        self._pending_fallback = False
 
     def _use_tc(self):
         from . import _lib
@@ -57,26 +58,54 @@ class AllNegEvaluator:
             if self._tc_ws is None:
                 self._tc_ws = torch.empty(ops.score_topk_tc_workspace_bytes(it.I, n), dtype=torch.uint8, device=Z.device)
                 self._mask_key = None
-            ops.score_topk_tc(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores, self.fallback, self._tc_ws,
+            ops.score_topk_tc(self.F, it.U, it.I, self.users, it, self._top_ids, self._top_scores, self.fallback, self._tc_ws,
                               reuse_mask=self._mask_key == key)
             self._mask_key = key
-            bad = torch.nonzero(self.fallback[:n]).flatten()
-            if bad.numel():       # rows whose error guard failed: recompute exactly
-                users = self.users[bad].contiguous()
-                ids = torch.empty((bad.numel(), K), dtype=torch.int32, device=Z.device)
-                sc = torch.empty((bad.numel(), K), dtype=torch.float32, device=Z.device)
-                ops.score_topk_exact(self.F, it.U, it.I, users, it, ids, sc)
-                self.top_ids[bad] = ids
-                self.top_scores[bad] = sc
-            self.n_fallback = int(bad.numel())
-        else:
-            ops.score_topk_exact(self.F, it.U, it.I, self.users, it, self.top_ids, self.top_scores)
+            # rows whose error guard failed are recomputed exactly -- checked in metrics() / resolve(), together with the read-back of
+            # the result, so that ranking itself never synchronises with the host
+            self._pending_fallback = True
             self.n_fallback = 0
+        else:
+            ops.score_topk_exact(self.F, it.U, it.I, self.users, it, self._top_ids, self._top_scores)
+            self.n_fallback = 0
+
+    @property
+    def top_ids(self):
+        """(n_users, 20) int32, -1 padded; reading it finishes a pending rank() (see resolve)"""
+        self.resolve()
+        return self._top_ids
+
+    @property
+    def top_scores(self):
+        self.resolve()
+        return self._top_scores
+
+    def resolve(self):
+        """Finish rank(): recompute the flagged rows through the exact entry point (one 4-byte read-back; normally zero rows).
+        Returns True if rows were replaced."""
+        if not self._pending_fallback:
+            return False
+        self._pending_fallback = False
+        n = self.users.numel()
+        it = self.inter
+        self.n_fallback = int(self.fallback[n].item())
+        if self.n_fallback == 0:
+            return False
+        bad = torch.nonzero(self.fallback[:n]).flatten()
+        users = self.users[bad].contiguous()
+        ids = torch.empty((bad.numel(), K), dtype=torch.int32, device=self.F.device)
+        sc = torch.empty((bad.numel(), K), dtype=torch.float32, device=self.F.device)
+        ops.score_topk_exact(self.F, it.U, it.I, users, it, ids, sc)
+        self._top_ids[bad] = ids
+        self._top_scores[bad] = sc
+        return True
 
     def metrics(self):
         """dict in the reference's format (train_eval_Gowalla.py:277-278,354)."""
         it = self.inter
-        ops.eval_metrics(self.top_ids, self.users, it, self.hits, self.sums, self.metric_ws)
+        ops.eval_metrics(self._top_ids, self.users, it, self.hits, self.sums, self.metric_ws)      # queued behind rank(): no host sync yet
+        if self.resolve():
+            ops.eval_metrics(self._top_ids, self.users, it, self.hits, self.sums, self.metric_ws)
         from .dist import allreduce_sums
         allreduce_sums(self.sums)                                   # multi-GPU: users are sharded, only 16 sums are merged
         s = self.sums.cpu().numpy() / max(it.n_train_users, 1)      # divisor = users with train data (:283)
