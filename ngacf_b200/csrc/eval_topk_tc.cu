@@ -20,6 +20,7 @@
 // 2-D decomposition: grid = (user blocks, S segments); S grows as the user count shrinks (a rank of an 8-GPU evaluation holds
 // 30 user blocks: without the split 30 CTAs would walk all 321 tiles serially on a 148-SM part).  Every (user, segment, column
 // half) keeps its own 16 candidates and threshold; the re-score kernel merges the 2*S lists of a user.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -30,7 +31,7 @@ constexpr int TM = 128;                 // users per CTA (UMMA M)
 constexpr int TN = 128;                 // items per tile (UMMA N)
 constexpr int KP = 24;                  // approximate candidates kept per LIST (user x segment x column half): > 20, so that a list
                                         // holding the whole top-20 still has its threshold below the 20th exact score
-constexpr int CBUF = 512;               // survivor LOG entries per epilogue thread (append-only; ~250 used on the gowalla shape; overflow -> exact fallback)
+constexpr int CBUF = 384;               // survivor LOG entries per epilogue thread (append-only; ~150 used on the gowalla shape; overflow -> exact fallback)
 constexpr int EPI = 256;                // epilogue threads per CTA
 constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
 constexpr int K = NGACF_TOPK;
@@ -114,6 +115,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ unsigned int smid_u32() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
+// order-preserving float <-> uint (atomicMax on thresholds); 0 decodes to -inf, so a zero-filled array is "no threshold yet"
+__device__ __forceinline__ unsigned int thr_encode(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float thr_decode(unsigned int e) {
+    if (e == 0u) return -INFINITY;
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
 }
 
 // split form for software pipelining: the registers of an issued load are only defined after tmem_ld_wait() -- which also names
@@ -209,10 +222,11 @@ __global__ void __launch_bounds__(256) mask_clear_train_kernel(const int* __rest
 #ifdef NGACF_TOPK_TRACE
 // pipeline timeline of two CTAs (debug builds only): [cta slot][event][tile]
 __device__ long long g_topk_trace[2][6][512];
-__device__ long long g_topk_cta[1024][4];      // per CTA (blockIdx.y == 0): globaltimer at start / end of the epilogue of warp 0, SM id, flushes of warp 0
+__device__ long long g_topk_cta[4096][4];
+__device__ unsigned long long g_rescore_stat[4];   // sum of kept candidates, sum of listed (id >= 0) candidates, users, max kept      // per CTA: globaltimer at start / end of the epilogue of warp 0, SM id, log entries of (warp 0, lane 0)
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int smid() { int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
-#define TRACE(ev, lt) do { if ((blockIdx.x == 0 || blockIdx.x == 100) && blockIdx.y == 0 && (lt) < 512) g_topk_trace[blockIdx.x ? 1 : 0][ev][lt] = clock64(); } while (0)
+#define TRACE(ev, lt) do { if ((blockIdx.x == 0 || blockIdx.x == 200) && blockIdx.y == 0 && (lt) < 512) g_topk_trace[blockIdx.x ? 1 : 0][ev][lt] = clock64(); } while (0)
 #else
 #define TRACE(ev, lt) do { } while (0)
 #endif
@@ -220,8 +234,10 @@ __device__ __forceinline__ int smid() { int r; asm volatile("mov.u32 %0, %%smid;
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* __restrict__ F, int U, const int* __restrict__ users,
                                                                    int n_users, const uint2* __restrict__ amask,
-                                                                   const uint8_t* __restrict__ img, int n_tiles, int S,
-                                                                   uint2* __restrict__ gbuf, int* __restrict__ cand_ids,
+                                                                   const uint8_t* __restrict__ img, int tile_begin, int tile_count, int S,
+                                                                   int list_base, int lists_per_user,
+                                                                   uint2* __restrict__ gbuf, int* buf_locks, int n_bufs, unsigned int* gthr,
+                                                                   int* __restrict__ cand_ids, float* __restrict__ cand_sc,
                                                                    float* __restrict__ cand_thr) {
     // no pointer arithmetic through integers here: the compiler must keep the shared address space (STS/LDS), the staging
     // stores of round 1 were generic ST.E because the base pointer had been aligned by hand through uintptr_t
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int u0 = blockIdx.x * TM;
     const int seg = blockIdx.y;
-    const int t0 = (int)((int64_t)seg * n_tiles / S), t1 = (int)((int64_t)(seg + 1) * n_tiles / S);   // this CTA's item tiles
+    const int t0 = tile_begin + (int)((int64_t)seg * tile_count / S), t1 = tile_begin + (int)((int64_t)(seg + 1) * tile_count / S);   // this CTA's item tiles
     const int nt = t1 - t0;
 
     // ---- one-time setup: user rows -> bf16 hi/lo UMMA image (generic-proxy stores) ----
@@ -266,6 +282,13 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
         mbar_init(bar_tempty0, 8);                   // eight epilogue warps drain an accumulator
         mbar_init(bar_tempty0 + 8, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid == 32) {
+        // survivor-log buffer of this CTA: one of n_bufs (= resident CTA slots of the device), claimed for the CTA's lifetime.  The
+        // logs are only read by their own CTA, so the workspace holds one per RESIDENT CTA, not one per (user block, segment).
+        int b = (int)((smid_u32() * 2u) % (unsigned)n_bufs);
+        while (atomicCAS(buf_locks + b, 0, 1) != 0) b = b + 1 == n_bufs ? 0 : b + 1;
+        tmem_slot[1] = (uint32_t)b;
     }
     if (warp == 5) {   // TMEM: 256 columns = two 128-column fp32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
@@ -343,12 +366,15 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
 #pragma unroll
         for (int k = 0; k < KP; ++k) ls[k] = -INFINITY;
         float thr = -INFINITY;                                // == ls[KP-1]
-        // FILTER threshold: max of this list's thr and that of the user's other column half (exchanged at every merge).  The KP-th
-        // best of the union of the two halves is >= either list's KP-th best, so it is a valid bound for both -- and the tighter
-        // filter logs ~40 % fewer survivors (24 ln(N/24) per user instead of twice 24 ln(N/48)).
-        float T = -INFINITY;
-        const size_t cta_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        uint2* bE = gbuf + cta_lin * (CBUF * EPI) + et;
+        // FILTER threshold: the maximum of the thr of ALL lists of this user -- both column halves, every item segment, whichever
+        // CTA runs them -- kept in gthr[user slot] (atomicMax on an order-preserving encoding).  The KP-th best of a union is >= the
+        // KP-th best of any part, so every list's thr is a valid bound for all of them; stale reads are valid too (it only grows).
+        // A user's lists together log ~24 ln(I/24) survivors instead of that per list, and a CTA that starts late (second wave,
+        // other segment) starts with a warm threshold -- which is what makes the segment split cheap.
+        unsigned int* gT = gthr + uslot;
+        float T = thr_decode(__ldcg(gT));                     // a CTA that starts late starts warm
+        unsigned int tpre = 0u;                               // gthr value requested one tile ahead
+        uint2* bE = gbuf + (size_t)tmem_slot[1] * (CBUF * EPI) + et;
         int cnt = 0, done = 0, overflow = 0;                  // log entries written / already merged into ls
 #ifdef NGACF_TOPK_TRACE
         int n_flush = 0;
@@ -385,13 +411,7 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 }
             }
             done = cnt;
-            // exchange with the thread that owns the other column half of this user row: through the own staging slots (nobody
-            // else touches them), between two named barriers of the 256 epilogue threads -- every epilogue warp of the CTA runs
-            // the same merge schedule, so the barrier counts match
-            reinterpret_cast<float*>(Vs4 + et)[0] = thr;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            T = fmaxf(thr, reinterpret_cast<const float*>(Vs4 + (et ^ TM))[0]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (thr > -INFINITY) T = fmaxf(fmaxf(T, thr), thr_decode(atomicMax(gT, thr_encode(thr))));
         };
         // allowed columns (item pool minus this user's train positives) of this thread's 64 columns: one 8-byte word per tile from
         // the mask matrix [tile][user slot][half] (coalesced over the warp), requested one tile ahead.  Rows past n_users are zero.
@@ -403,9 +423,12 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             const int item0 = (t0 + lt) * TN + half * 64;     // first item of this thread's 64 columns
             const unsigned pw0 = mnext.x, pw1 = mnext.y;
             if (lt + 1 < nt) mnext = __ldg(mrow + (size_t)(t0 + lt + 1) * mstride);
+            T = fmaxf(T, thr_decode(tpre));                   // what the user's other lists have reached meanwhile
+            tpre = __ldcg(gT);
             // merge schedule: tiles 1, 2, 4, 8, 16, ...: a merge costs ~10k cycles of a stalled CTA pipeline, a survivor logged
             // because the threshold is stale ~0.3k; doubling intervals are near the optimum of that trade
-            if (lt > 0 && (lt & (lt - 1)) == 0) flush();
+            // -- and only when a lane has enough to merge: a list that runs under a warm shared threshold logs a handful of survivors
+            if (lt > 0 && (lt & (lt - 1)) == 0 && __reduce_max_sync(0xffffffffu, cnt - done) >= 8) flush();
             mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
             if (warp == 0 && lane == 0) TRACE(4, lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -461,29 +484,45 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             if (warp == 0 && lane == 0) TRACE(5, lt);
         }
         flush();
-#ifdef NGACF_TOPK_TRACE
-        if (warp == 0 && lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
-            g_topk_cta[blockIdx.x][0] = t_begin; g_topk_cta[blockIdx.x][1] = gtimer(); g_topk_cta[blockIdx.x][2] = smid(); g_topk_cta[blockIdx.x][3] = n_flush;
+        T = fmaxf(T, thr_decode(__ldcg(gT)));
+        // final threshold of this CTA's two lists of a user: the KP-th best of the UNION of their sorted scores (>= either thr, so
+        // every bound above still holds; >= KP items reach it).  The two threads of a row swap their KP scores through the item
+        // ring (all tiles are consumed: the ring is free), k-th of two sorted lists = max_i min(a[i-1], b[k-i-1]).
+        {
+            float* lsx = reinterpret_cast<float*>(sB);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) lsx[k * EPI + et] = ls[k];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float t_union = -INFINITY, a_prev = INFINITY;
+#pragma unroll
+            for (int i = 0; i <= KP; ++i) {                   // i scores from this list, KP - i from the other
+                const float b_last = i < KP ? lsx[(KP - i - 1) * EPI + (et ^ TM)] : INFINITY;
+                t_union = fmaxf(t_union, fminf(a_prev, b_last));
+                if (i < KP) a_prev = ls[i];
+            }
+            T = fmaxf(T, t_union);
+            if (t_union > -INFINITY) atomicMax(gT, thr_encode(t_union));
         }
-#endif
         // candidates = the logged survivors at or above the final (shared) threshold: at most KP per list, since the entries above
         // T >= thr are part of this list's own top KP (ties beyond KP stay out: they are <= cand_thr)
         {
-            const size_t list = ((size_t)(user >= 0 ? uslot : 0) * S + seg) * 2 + half;
+            const size_t list = (size_t)(user >= 0 ? uslot : 0) * lists_per_user + list_base + seg * 2 + half;
             const int e_hi = __reduce_max_sync(0xffffffffu, cnt);
             int emitted = 0, tie_left = KP;               // entries equal to the threshold may only fill what the larger ones leave
 #pragma unroll
             for (int k = 0; k < KP; ++k) tie_left -= ls[k] > T ? 1 : 0;
-            uint2 n0 = 0 < cnt ? bE[0] : make_uint2(0xff800000u, 0xffffffffu);
 #pragma unroll 1
-            for (int e = 0; e < e_hi; ++e) {
-                const uint2 cur_e = n0;
-                n0 = e + 1 < cnt ? bE[(size_t)(e + 1) * EPI] : make_uint2(0xff800000u, 0xffffffffu);
-                if (user >= 0 && e < cnt && emitted < KP) {
-                    const float sc = __uint_as_float(cur_e.x);
+            for (int e0 = 0; e0 < e_hi; e0 += 16) {           // sixteen log entries in flight (it was one: a chain of L2 round trips)
+                uint2 ent[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) ent[q] = e0 + q < cnt ? bE[(size_t)(e0 + q) * EPI] : make_uint2(0xff800000u, 0xffffffffu);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float sc = __uint_as_float(ent[q].x);
                     const bool tie = sc == T && tie_left > 0;
-                    if (sc > T || tie) {
-                        cand_ids[list * KP + emitted++] = (int)cur_e.y;
+                    if (user >= 0 && emitted < KP && (sc > T || tie)) {       // padding entries are -inf: never above T, a tie only
+                        cand_sc[list * KP + emitted] = sc;                    // while T = -inf, where their id (-1) is padding too
+                        cand_ids[list * KP + emitted++] = (int)ent[q].y;
                         tie_left -= tie ? 1 : 0;
                     }
                 }
@@ -493,9 +532,16 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 cand_thr[list] = overflow ? INFINITY : T;     // neither half's list full: T = -inf (there is no non-candidate)
             }
         }
+#ifdef NGACF_TOPK_TRACE
+        if (warp == 0 && lane == 0 && blockIdx.y * gridDim.x + blockIdx.x < 4096) {
+            const int ci = blockIdx.y * gridDim.x + blockIdx.x;
+            g_topk_cta[ci][0] = t_begin; g_topk_cta[ci][1] = gtimer(); g_topk_cta[ci][2] = smid(); g_topk_cta[ci][3] = cnt;
+        }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 32) atomicExch(buf_locks + (int)tmem_slot[1], 0);      // every log read of this CTA is behind the barrier
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
@@ -519,8 +565,9 @@ __device__ __forceinline__ float dot64_tree_g(float4 a, float4 b, unsigned gm) {
 // non-candidate of list l has approx <= thr[l], hence exact <= thr[l] + delta.
 constexpr int RS_GROUPS = 4;            // users per CTA (64 threads; 24 KB of candidate scores / ids)
 __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __restrict__ F, int U, const int* __restrict__ users, int n_users,
-                                                                const int* __restrict__ cand_ids, const float* __restrict__ cand_thr, int n_lists,
-                                                                const unsigned int* __restrict__ maxnorm_bits, int* __restrict__ top_ids,
+                                                                const int* __restrict__ cand_ids, const float* __restrict__ cand_sc,
+                                                                const float* __restrict__ cand_thr, const unsigned int* __restrict__ gthr,
+                                                                int n_lists, const unsigned int* __restrict__ maxnorm_bits, int* __restrict__ top_ids,
                                                                 float* __restrict__ top_scores, int* __restrict__ fallback) {
     __shared__ float sc_s[RS_GROUPS][MAX_LISTS * KP];
     __shared__ int id_s[RS_GROUPS][MAX_LISTS * KP];
@@ -534,18 +581,28 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     const float unorm = sqrtf(dot64_tree_g(fu, fu, gm));
     float* scs = sc_s[grp];
     int* ids = id_s[grp];
-    // the lists are mostly padding (-1): with the shared filter threshold a user's two lists hold ~24-30 candidates out of 2*KP slots;
-    // compact them first (the ranking below is quadratic in the count)
+    // Candidates = the listed items whose approximate score reaches the user's FINAL shared threshold.  A list that finished early
+    // emitted against the threshold of its time -- up to KP entries each, most of them far below the final one; everything not
+    // kept here (never logged, logged but not emitted, emitted below the final threshold) has approx <= T_final.  The lists are
+    // mostly padding (-1) as well: compact first (the ranking below is quadratic in the count).
+    const float T_final = thr_decode(gthr[j]);
     const int NC_all = n_lists * KP;
     int NC = 0;
     const int gshift = (threadIdx.x & 16);
     for (int c0 = 0; c0 < NC_all; c0 += 16) {
-        const int id = c0 + lane16 < NC_all ? cand_ids[(int64_t)j * NC_all + c0 + lane16] : -1;
+        int id = c0 + lane16 < NC_all ? cand_ids[(int64_t)j * NC_all + c0 + lane16] : -1;
+#ifdef NGACF_TOPK_TRACE
+        if (id >= 0) atomicAdd(&g_rescore_stat[1], 1ull);
+#endif
+        if (id >= 0 && cand_sc[(int64_t)j * NC_all + c0 + lane16] < T_final) id = -1;
         const unsigned m = (__ballot_sync(gm, id >= 0) >> gshift) & 0xFFFFu;
         if (id >= 0) ids[NC + __popc(m & ((1u << lane16) - 1u))] = id;
         NC += __popc(m);
     }
     __syncwarp(gm);
+#ifdef NGACF_TOPK_TRACE
+    if (lane16 == 0) { atomicAdd(&g_rescore_stat[0], (unsigned long long)NC); atomicAdd(&g_rescore_stat[2], 1ull); atomicMax(&g_rescore_stat[3], (unsigned long long)NC); }
+#endif
     for (int c0 = 0; c0 < NC; c0 += 4) {                        // exact scores, four candidate rows in flight
         float4 fi[4];
         int id[4];
@@ -582,7 +639,7 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     for (int k = nvalid + lane16; k < K; k += 16) { top_ids[(int64_t)j * K + k] = -1; top_scores[(int64_t)j * K + k] = 0.f; }
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(gm, tau, o, 16));
-    float thr = -INFINITY;
+    float thr = T_final;                                         // a list's cand_thr is <= T_final, or +inf if its log overflowed
     for (int l = lane16; l < n_lists; l += 16) thr = fmaxf(thr, cand_thr[(int64_t)j * n_lists + l]);
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) thr = fmaxf(thr, __shfl_xor_sync(gm, thr, o, 16));
@@ -602,18 +659,37 @@ using namespace ngacf;
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 // item-tile segments per user block: fill the 2 x 148 CTA slots when there are few user blocks (a rank of a sharded evaluation)
-static int plan_segments(int n_users, int n_tiles) {
+// survivor-log buffers = CTA slots that can be resident at once (two CTAs per SM: shared memory)
+static int resident_ctas() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * (sms > 0 ? sms : 148);
+}
+
+// item-tile segments per user block: fill the 2 x 148 CTA slots when there are few user blocks (a rank of a sharded evaluation).
+// More segments than that do not pay: a user's lists share their filter threshold (gthr), but each list's own threshold is the
+// KP-th best of ITS columns only, so the shared value loosens with the number of lists (measured: 43 candidates per user reach the
+// re-score kernel with 4 lists, 143 with 10), and every CTA pays its pipeline fill and its merges again.
+struct TopkPlan { int S, lists_per_user; };
+static TopkPlan plan_topk(int n_users, int n_tiles) {
+    TopkPlan p;
     const int blocks = (n_users + tc::TM - 1) / tc::TM;
     int S = blocks > 0 ? (2 * 148) / blocks : 1;
+    if (S > n_tiles / 16) S = n_tiles / 16;
     if (S < 1) S = 1;
     if (S > tc::MAX_LISTS / 2) S = tc::MAX_LISTS / 2;
-    if (S > n_tiles) S = n_tiles > 0 ? n_tiles : 1;
-    return S;
+    p.S = S;
+    p.lists_per_user = 2 * S;
+    return p;
 }
 
 #ifdef NGACF_TOPK_TRACE
 extern "C" int ngacf_debug_topk_trace(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, tc::g_topk_trace, sizeof(tc::g_topk_trace));
+}
+extern "C" int ngacf_debug_rescore_stat(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, tc::g_rescore_stat, sizeof(tc::g_rescore_stat));
 }
 extern "C" int ngacf_debug_topk_cta(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, tc::g_topk_cta, sizeof(tc::g_topk_cta));
@@ -622,12 +698,12 @@ extern "C" int ngacf_debug_topk_cta(long long* host_out) {
 
 extern "C" size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users) {
     const size_t n_tiles = (size_t)(I + tc::TN - 1) / tc::TN;
-    const int S = plan_segments(n_users, (int)n_tiles);
-    const size_t lists = (size_t)n_users * 2 * S;
-    const size_t ctas = (size_t)((n_users + tc::TM - 1) / tc::TM) * S;
+    const TopkPlan plan = plan_topk(n_users, (int)n_tiles);
+    const size_t lists = (size_t)n_users * plan.lists_per_user;
     const size_t slots = (size_t)((n_users + tc::TM - 1) / tc::TM) * tc::TM;
-    return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + al256(lists * tc::KP * 4) + al256(lists * 4) +
-           al256(ctas * tc::CBUF * tc::EPI * 8) + al256(n_tiles * slots * 16) + 1024;
+    return al256(n_tiles * tc::TILE_BYTES) + al256(n_tiles * 4 * 4) + 256 + 2 * al256(lists * tc::KP * 4) + al256(lists * 4) +
+           al256((size_t)resident_ctas() * tc::CBUF * tc::EPI * 8) + al256((size_t)resident_ctas() * 4) + al256(slots * 4) +
+           al256(n_tiles * slots * 16) + 1024;
 }
 
 extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users, const int32_t* train_ptr,
@@ -639,21 +715,25 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     if (n_users == 0) return NGACF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (I + tc::TN - 1) / tc::TN;
-    const int S = plan_segments(n_users, n_tiles);
+    const TopkPlan plan = plan_topk(n_users, n_tiles);
     const int blocks = ceil_div(n_users, tc::TM);
-    const size_t lists = (size_t)n_users * 2 * S;
-    const size_t ctas = (size_t)blocks * S;
+    const size_t lists = (size_t)n_users * plan.lists_per_user;
     char* w = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     uint8_t* img = (uint8_t*)w;                         w += al256((size_t)n_tiles * tc::TILE_BYTES);
     uint32_t* pool_bits = (uint32_t*)w;                 w += al256((size_t)n_tiles * 4 * 4);
     unsigned int* maxnorm = (unsigned int*)w;           w += 256;
     int* cand_ids = (int*)w;                            w += al256(lists * tc::KP * 4);
+    float* cand_sc = (float*)w;                         w += al256(lists * tc::KP * 4);
     float* cand_thr = (float*)w;                        w += al256(lists * 4);
-    uint2* gbuf = (uint2*)w;                            w += al256(ctas * tc::CBUF * tc::EPI * 8);
+    const int n_bufs = resident_ctas();
+    uint2* gbuf = (uint2*)w;                            w += al256((size_t)n_bufs * tc::CBUF * tc::EPI * 8);
+    int* buf_locks = (int*)w;                           w += al256((size_t)n_bufs * 4);
+    unsigned int* gthr = (unsigned int*)w;              w += al256((size_t)blocks * tc::TM * 4);
     uint4* amask = (uint4*)w;                           // [tile][user slot]: persists in the caller's workspace between calls
     const int n_slots = blocks * tc::TM;
     cudaMemsetAsync(pool_bits, 0, (size_t)n_tiles * 4 * 4 + 256 + 256, st);     // pool bits + max norm (contiguous)
     cudaMemsetAsync(fallback + n_users, 0, sizeof(int32_t), st);
+    cudaMemsetAsync(buf_locks, 0, al256((size_t)n_bufs * 4) + (size_t)blocks * tc::TM * 4, st);   // free buffers; "no threshold yet" for every user
     tc::prep_items_kernel<<<ceil_div((int64_t)n_tiles * tc::TN * 8, 256), 256, 0, st>>>(F, U, I, in_pool, img, pool_bits, maxnorm, n_tiles);
     if (!reuse_mask) {
         tc::mask_fill_kernel<<<ceil_div((int64_t)n_tiles * n_slots, 256), 256, 0, st>>>(pool_bits, n_tiles, n_slots, n_users, amask);
@@ -664,9 +744,10 @@ extern "C" int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const i
     once.run([] {
         cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
-    tc::score_topk_tc_kernel<<<dim3(blocks, S), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, reinterpret_cast<const uint2*>(amask), img,
-                                                                                  n_tiles, S, gbuf, cand_ids, cand_thr);
-    tc::rescore_kernel<<<ceil_div(n_users, tc::RS_GROUPS), tc::RS_GROUPS * 16, 0, st>>>(F, U, users, n_users, cand_ids, cand_thr, 2 * S, maxnorm,
+    tc::score_topk_tc_kernel<<<dim3(blocks, plan.S), tc::THREADS, tc::SMEM_BYTES, st>>>(F, U, users, n_users, reinterpret_cast<const uint2*>(amask), img,
+                                                                                       0, n_tiles, plan.S, 0, plan.lists_per_user, gbuf, buf_locks,
+                                                                                       n_bufs, gthr, cand_ids, cand_sc, cand_thr);
+    tc::rescore_kernel<<<ceil_div(n_users, tc::RS_GROUPS), tc::RS_GROUPS * 16, 0, st>>>(F, U, users, n_users, cand_ids, cand_sc, cand_thr, gthr, plan.lists_per_user, maxnorm,
                                                                                        top_ids, top_scores, fallback);
     return check_launch("score_topk_tc");
 }

@@ -39,37 +39,45 @@ lib = _lib.load()
 buf = np.zeros((2, 6, 512), np.int64)
 rc = lib.ngacf_debug_topk_trace(ctypes.c_void_p(buf.ctypes.data))
 assert rc == 0, rc
-cta = np.zeros((1024, 4), np.int64)
+rs = np.zeros(4, np.uint64)
+assert lib.ngacf_debug_rescore_stat(ctypes.c_void_p(rs.ctypes.data)) == 0
+print("rescore: kept candidates per user %.1f (max %d), listed per user %.1f" % (rs[0] / max(rs[2], 1), rs[3], rs[1] / max(rs[2], 1)))
+cta = np.zeros((4096, 4), np.int64)
 assert lib.ngacf_debug_topk_cta(ctypes.c_void_p(cta.ctypes.data)) == 0
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/topk_trace.npy", buf)
 np.save("gpurun_out/topk_cta.npy", cta)
-nb = (inter.eval_users.numel() + 127) // 128
-c = cta[:nb]
+c = cta[cta[:, 1] > 0]
+nb = c.shape[0]
 t0g = c[:, 0].min()
 dur = (c[:, 1] - c[:, 0]) / 1000.0
 print("CTAs %d: epilogue duration us min %.0f median %.0f max %.0f; last end at %.0f us; starts spread %.0f us" % (nb, dur.min(), np.median(dur), dur.max(), (c[:, 1].max() - t0g) / 1000.0, (c[:, 0].max() - t0g) / 1000.0))
 sm_count = np.bincount(c[:, 2].astype(int), minlength=148)
 shared = sm_count[c[:, 2].astype(int)] > 1
 print("  CTAs sharing an SM: %d, median dur %.0f us; alone: %d, median dur %.0f us" % (shared.sum(), np.median(dur[shared]), (~shared).sum(), np.median(dur[~shared])))
-print("  flushes (warp 0) min/median/max", c[:, 3].min(), np.median(c[:, 3]), c[:, 3].max())
+print("  log entries of (warp 0, lane 0) min/median/max", c[:, 3].min(), np.median(c[:, 3]), c[:, 3].max())
+print("  kernel span %.0f us; sum of CTA durations / (2 x 148 slots) = %.0f us" % ((c[:, 1].max() - t0g) / 1000.0, dur.sum() / 296))
 order = np.argsort(-dur)[:8]
 print("  slowest CTAs:", [(int(k), round(float(dur[k])), int(c[k, 2]), int(c[k, 3])) for k in order])
 names = ["tma_issue", "mma_full_ok", "mma_tempty_ok", "mma_issued", "epi_tfull_ok", "epi_done"]
-nt = 321
 for c in range(2):
-    t = buf[c][:, :nt].astype(np.float64)
-    t0 = t[0, 0]
-    print("CTA slot %d: total %.0f cycles for %d tiles = %.0f cycles/tile" % (c, t[5, nt - 1] - t0, nt, (t[5, nt - 1] - t0) / nt))
-    for lt in list(range(0, 6)) + list(range(150, 156)):
-        print("  tile %3d " % lt + "  ".join("%s %7.0f" % (n, t[k, lt] - t0) for k, n in enumerate(names)))
-    mid = slice(20, nt - 5)
-    print("  steady-state means (cycles):")
-    print("    TMA issue -> full seen by MMA      %7.0f" % np.mean(t[1, mid] - t[0, mid]))
-    print("    MMA wait for tempty after full     %7.0f" % np.mean(t[2, mid] - t[1, mid]))
-    print("    MMA issue (12 MMAs + commits)      %7.0f" % np.mean(t[3, mid] - t[2, mid]))
-    print("    MMA issued -> tfull seen by epi    %7.0f" % np.mean(t[4, mid] - t[3, mid]))
-    print("    epilogue (tfull -> done)           %7.0f" % np.mean(t[5, mid] - t[4, mid]))
-    print("    epi done(t) -> MMA tempty ok(t+2)  %7.0f" % np.mean(t[2, 22:nt - 3] - t[5, 20:nt - 5]))
-    print("    MMA issued(t) -> TMA issue(t+2)    %7.0f" % np.mean(t[0, 22:nt - 3] - t[3, 20:nt - 5]))
-    print("    tile period (epi done deltas)      %7.0f" % np.mean(np.diff(t[5, mid])))
+    x = buf[c].astype(np.float64)
+    nt = int(np.count_nonzero(x[5]))
+    if nt < 8:
+        continue
+    x = x[:, :nt]
+    epi = x[5] - x[4]
+    print("traced CTA %d: %d tiles, %.0f cycles (%.0f/tile)" % (c, nt, x[5, nt - 1] - x[0, 0], (x[5, nt - 1] - x[0, 0]) / nt))
+    for lt in range(0, 4):
+        print("   tile %d " % lt + "  ".join("%s %7.0f" % (n, x[k, lt] - x[0, 0]) for k, n in enumerate(names)))
+    edges = [0, 4, 8, 16, 32, 64, 128, 192, 256, 100000]
+    for a, b in zip(edges[:-1], edges[1:]):
+        b = min(b, nt)
+        if a >= b:
+            break
+        el = x[5, b - 1] - (x[5, a - 1] if a > 0 else x[0, 0])
+        print("   tiles %3d-%3d: %8.0f cycles (%6.0f/tile)  epilogue mean %6.0f max %6.0f   epi_done(t-1)->tfull_ok(t) mean %6.0f" % (
+            a, b, el, el / (b - a), epi[a:b].mean(), epi[a:b].max(), np.mean(x[4, max(a, 1):b] - x[5, max(a, 1) - 1:b - 1])))
+    gap = x[4, 1:] - x[5, :-1]
+    big = np.argsort(-gap)[:8]
+    print("   largest epi_done(t-1)->tfull_ok(t):", sorted([(int(k) + 1, int(gap[k])) for k in big]))
