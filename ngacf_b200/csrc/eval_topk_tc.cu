@@ -1,25 +1,34 @@
 // AllNeg evaluation, tensor-core path: users x items score contraction on the 5th-gen tensor cores
 // (tcgen05.mma, bf16 hi/lo split = "bf16x3", fp32 accumulators in TMEM) with the per-row top-K fused
 // on the accumulators as they are read back with tcgen05.ld -- the (users x items) score matrix never
-// touches shared memory or HBM.  The kernel keeps K'=32 approximate candidates per user; a second
-// kernel re-scores them exactly (fp32, specified summation tree), orders them (score desc, id asc),
+// touches shared memory or HBM.  The kernel hands ~24 approximate candidates per user to a second
+// kernel, which re-scores them exactly (fp32, specified summation tree), orders them (score desc, id asc),
 // and proves with an error bound that no non-candidate can enter the top-20; rows that fail the proof
 // are flagged and recomputed by the caller through the exact CUDA-core entry point.
 // Replaces train_eval_Gowalla.py:300-341,370-385 of the reference.
 //
 // Kernel structure (one CTA = 128 users x one SEGMENT of the item tiles; two CTAs per SM overlap):
 //   warps 0-3, 6-9  epilogue: eight warps; thread (quadrant, lane) owns user row r = TMEM lane r and one HALF of every tile's
-//              128 columns (warps 0-3 columns 0-63, warps 6-9 columns 64-127); tcgen05.ld 16 columns at a time, candidate
-//              mask (item pool minus train positives), threshold test; survivors are APPENDED to a small per-thread buffer and
-//              merged into the thread's sorted 16-entry list only when a buffer fills (round 1 inserted every survivor at once:
-//              the 32-step insertion was run by the whole warp for almost every 32-column chunk, ~200 of ~380 instructions)
+//              128 columns (warps 0-3 columns 0-63, warps 6-9 columns 64-127) = one LIST.  Per 16 columns: tcgen05.ld (the next
+//              piece's load in flight), threshold test (2 instructions per accumulator), allowed-column word (item pool minus
+//              the user's train positives, from a bit matrix built once per evaluator), survivors appended to the list's LOG
+//              in global memory.  A list keeps the KP best SCORES sorted in registers (no ids: they stay in the log); the log
+//              is merged into them on a fixed tile schedule (1, 2, 4, 8, ...), the same for all eight warps, because a merge
+//              stalls the CTA's whole TMA -> MMA -> epilogue chain.  The filter threshold is shared by all lists of a user
+//              through gthr[user] (atomicMax; a union's KP-th best bounds every part's).  At the end the two lists of a row
+//              cut their logs at the KP-th best of their union.
 //   warp 4     producer: one 32 KB cp.async.bulk (TMA engine, 1-D) per item tile, pre-tiled in HBM in
 //              the exact UMMA shared-memory image (K-major, no swizzle) by prep_items_kernel
 //   warp 5     TMEM allocator + single-thread MMA issuer: 12 tcgen05.mma (4 k-steps x {hi.hi, hi.lo, lo.hi})
-//              per tile into a double-buffered 128x128 fp32 accumulator
+//              per tile into a double-buffered 128x128 fp32 accumulator; descriptors precomputed
 // 2-D decomposition: grid = (user blocks, S segments); S grows as the user count shrinks (a rank of an 8-GPU evaluation holds
-// 30 user blocks: without the split 30 CTAs would walk all 321 tiles serially on a 148-SM part).  Every (user, segment, column
-// half) keeps its own 16 candidates and threshold; the re-score kernel merges the 2*S lists of a user.
+// 30 user blocks: without the split 30 CTAs would walk all 321 tiles serially on a 148-SM part).
+// History of the epilogue (scripts/probe/trace_topk.py prints the pipeline timeline of a debug build): round 1 inserted every
+// survivor into a sorted (score, id) list at once; round 2a buffered survivors per thread and merged when a lane's buffer filled --
+// eight warps stalling the pipeline at eight different tiles, 40 % of the kernel; the train-positive walk was a chain of dependent
+// global loads per tile (users with 1000 train items: +0.3 ms for their CTA).  Tried and dropped: more segments than CTA slots
+// (every list's own threshold is the KP-th best of its columns only: 143 candidates per user reach the re-score kernel with ten
+// lists), N = 64 MMA groups with a hand-over per column half (the single issuing thread becomes the bottleneck: +7 %).
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
