@@ -40,6 +40,8 @@ constexpr int TM = 128;                 // users per CTA (UMMA M)
 constexpr int TN = 128;                 // items per tile (UMMA N)
 constexpr int KP = 24;                  // approximate candidates kept per LIST (user x segment x column half): > 20, so that a list
                                         // holding the whole top-20 still has its threshold below the 20th exact score
+constexpr int KU = 24;                  // rank of the shared filter threshold inside the union of a row's two sorted lists (<= 2 KP; KP is the
+                                        // tightest choice and the one measured fastest: 0.72 ms against 0.76 ms with 32; no fallback rows either way)
 constexpr int CBUF = 384;               // survivor LOG entries per epilogue thread (append-only; ~150 used on the gowalla shape; overflow -> exact fallback)
 constexpr int EPI = 256;                // epilogue threads per CTA
 constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
@@ -420,7 +422,41 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
                 }
             }
             done = cnt;
-            if (thr > -INFINITY) T = fmaxf(fmaxf(T, thr), thr_decode(atomicMax(gT, thr_encode(thr))));
+        };
+        // After a scheduled merge the two lists of a user row (same CTA, warps w and w + 6 - ...) swap their KP sorted scores through
+        // shared memory and both take the KU-th best of the UNION as filter threshold: max(thr0, thr1) is the
+        // ~2 KP-th best of the row -- about half the survivors to log and merge afterwards.  All eight epilogue
+        // warps run this at the same tiles (named barrier 1).
+        auto exchange = [&]() {
+            // through the staging area: a thread owns 16 floats there (nobody else touches them), so the KP scores go in two rounds;
+            // the second barrier of a round keeps the partner from overwriting what is still being read
+            float b[KP];
+            static_assert(KP <= 32 && KP > 16, "two rounds of 16 floats");
+#pragma unroll
+            for (int r0 = 0; r0 < KP; r0 += 16) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    if (r0 + 4 * q4 < KP) Vs4[q4 * EPI + et] = make_float4(ls[r0 + 4 * q4], ls[r0 + 4 * q4 + 1], ls[r0 + 4 * q4 + 2], ls[r0 + 4 * q4 + 3]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    if (r0 + 4 * q4 < KP) {
+                        const float4 o = Vs4[q4 * EPI + (et ^ TM)];
+                        b[r0 + 4 * q4] = o.x; b[r0 + 4 * q4 + 1] = o.y; b[r0 + 4 * q4 + 2] = o.z; b[r0 + 4 * q4 + 3] = o.w;
+                    }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            // KU-th of the union of two sorted lists = max_i min(a[i-1], b[KU-i-1]), i scores from this list and KU - i from the
+            // other (both <= KP: the lists are truncated, which can only lower the value -- still a valid bound)
+            float t_union = -INFINITY;
+#pragma unroll
+            for (int i = (KU > KP ? KU - KP : 0); i <= (KP < KU ? KP : KU); ++i)
+                t_union = fmaxf(t_union, fminf(i > 0 ? ls[i > 0 ? i - 1 : 0] : INFINITY, i < KU ? b[i < KU ? KU - i - 1 : 0] : INFINITY));
+            // (own thr as well: T >= thr keeps "at most KP log entries above T" true for the final cut; with evenly mixed halves
+            // thr is the row's ~2 KP-th best, below t_union)
+            t_union = fmaxf(t_union, thr);
+            T = fmaxf(T, t_union);
+            if (t_union > -INFINITY) T = fmaxf(T, thr_decode(atomicMax(gT, thr_encode(t_union))));
         };
         // allowed columns (item pool minus this user's train positives) of this thread's 64 columns: one 8-byte word per tile from
         // the mask matrix [tile][user slot][half] (coalesced over the warp), requested one tile ahead.  Rows past n_users are zero.
@@ -437,7 +473,10 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             // merge schedule: tiles 1, 2, 4, 8, 16, ...: a merge costs ~10k cycles of a stalled CTA pipeline, a survivor logged
             // because the threshold is stale ~0.3k; doubling intervals are near the optimum of that trade
             // -- and only when a lane has enough to merge: a list that runs under a warm shared threshold logs a handful of survivors
-            if (lt > 0 && (lt & (lt - 1)) == 0 && __reduce_max_sync(0xffffffffu, cnt - done) >= 8) flush();
+            if (lt > 0 && (lt & (lt - 1)) == 0) {
+                if (__reduce_max_sync(0xffffffffu, cnt - done) >= 8) flush();
+                exchange();
+            }
             mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
             if (warp == 0 && lane == 0) TRACE(4, lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -492,26 +531,11 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             if (lane == 0) mbar_arrive(bar_tempty0 + 8 * buf);
             if (warp == 0 && lane == 0) TRACE(5, lt);
         }
+        // final threshold of this CTA's two lists of a user: the KU-th best of the UNION of their sorted scores (at least KU
+        // items reach it)
         flush();
+        exchange();
         T = fmaxf(T, thr_decode(__ldcg(gT)));
-        // final threshold of this CTA's two lists of a user: the KP-th best of the UNION of their sorted scores (>= either thr, so
-        // every bound above still holds; >= KP items reach it).  The two threads of a row swap their KP scores through the item
-        // ring (all tiles are consumed: the ring is free), k-th of two sorted lists = max_i min(a[i-1], b[k-i-1]).
-        {
-            float* lsx = reinterpret_cast<float*>(sB);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) lsx[k * EPI + et] = ls[k];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float t_union = -INFINITY, a_prev = INFINITY;
-#pragma unroll
-            for (int i = 0; i <= KP; ++i) {                   // i scores from this list, KP - i from the other
-                const float b_last = i < KP ? lsx[(KP - i - 1) * EPI + (et ^ TM)] : INFINITY;
-                t_union = fmaxf(t_union, fminf(a_prev, b_last));
-                if (i < KP) a_prev = ls[i];
-            }
-            T = fmaxf(T, t_union);
-            if (t_union > -INFINITY) atomicMax(gT, thr_encode(t_union));
-        }
         // candidates = the logged survivors at or above the final (shared) threshold: at most KP per list, since the entries above
         // T >= thr are part of this list's own top KP (ties beyond KP stay out: they are <= cand_thr)
         {
@@ -600,9 +624,6 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     const int gshift = (threadIdx.x & 16);
     for (int c0 = 0; c0 < NC_all; c0 += 16) {
         int id = c0 + lane16 < NC_all ? cand_ids[(int64_t)j * NC_all + c0 + lane16] : -1;
-#ifdef NGACF_TOPK_TRACE
-        if (id >= 0) atomicAdd(&g_rescore_stat[1], 1ull);
-#endif
         if (id >= 0 && cand_sc[(int64_t)j * NC_all + c0 + lane16] < T_final) id = -1;
         const unsigned m = (__ballot_sync(gm, id >= 0) >> gshift) & 0xFFFFu;
         if (id >= 0) ids[NC + __popc(m & ((1u << lane16) - 1u))] = id;
@@ -610,7 +631,7 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     }
     __syncwarp(gm);
 #ifdef NGACF_TOPK_TRACE
-    if (lane16 == 0) { atomicAdd(&g_rescore_stat[0], (unsigned long long)NC); atomicAdd(&g_rescore_stat[2], 1ull); atomicMax(&g_rescore_stat[3], (unsigned long long)NC); }
+    if (lane16 == 0) { atomicAdd(&g_rescore_stat[0], (unsigned long long)NC); atomicAdd(&g_rescore_stat[2], 1ull); }
 #endif
     for (int c0 = 0; c0 < NC; c0 += 4) {                        // exact scores, four candidate rows in flight
         float4 fi[4];
@@ -654,6 +675,12 @@ __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __
     for (int o = 1; o < 16; o <<= 1) thr = fmaxf(thr, __shfl_xor_sync(gm, thr, o, 16));
     const float delta = GUARD * unorm * __uint_as_float(*maxnorm_bits);
     const bool ok = (thr == -INFINITY) || (nvalid >= K && thr + delta < tau);
+#ifdef NGACF_TOPK_TRACE
+    if (lane16 == 0 && !ok) {
+        if (nvalid < K) atomicAdd(&g_rescore_stat[1], 1ull); else atomicAdd(&g_rescore_stat[3], 1ull);
+        if (j < 4) printf("user slot %d: NC %d nvalid %d T_final %g thr %g tau %g delta %g\n", j, NC, nvalid, T_final, thr, tau, delta);
+    }
+#endif
     if (lane16 == 0) {
         fallback[j] = ok ? 0 : 1;
         if (!ok) atomicAdd(fallback + n_users, 1);              // number of flagged rows: the caller reads one int instead of scanning

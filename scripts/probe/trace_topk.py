@@ -41,7 +41,7 @@ rc = lib.ngacf_debug_topk_trace(ctypes.c_void_p(buf.ctypes.data))
 assert rc == 0, rc
 rs = np.zeros(4, np.uint64)
 assert lib.ngacf_debug_rescore_stat(ctypes.c_void_p(rs.ctypes.data)) == 0
-print("rescore: kept candidates per user %.1f (max %d), listed per user %.1f" % (rs[0] / max(rs[2], 1), rs[3], rs[1] / max(rs[2], 1)))
+print("rescore: kept candidates per user %.1f; proof failures over all calls: %d with fewer than K candidates, %d on the margin (of %d user evaluations)" % (rs[0] / max(rs[2], 1), rs[1], rs[3], rs[2]))
 cta = np.zeros((4096, 4), np.int64)
 assert lib.ngacf_debug_topk_cta(ctypes.c_void_p(cta.ctypes.data)) == 0
 os.makedirs("gpurun_out", exist_ok=True)
