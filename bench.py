@@ -475,7 +475,8 @@ def main():
         with torch.no_grad():
             ev.rank(model.propagate(graph))
         torch.cuda.synchronize()
-        sc_ms = [e0_.elapsed_time(e1_) for n_, a_, e0_, e1_ in _lib.PROFILE if n_.startswith("ngacf_score_topk")]
+        ev.resolve()                                          # (sets n_fallback: rank() alone leaves the flagged rows pending)
+        sc_ms = [e0_.elapsed_time(e1_) for n_, a_, e0_, e1_ in _lib.PROFILE if n_.startswith("ngacf_score_topk_tc")]
         _lib.PROFILE = None
         sc_ms = float(sum(sc_ms)) if sc_ms else ms_eval
         n_local = int(ev.users.numel())
@@ -483,7 +484,9 @@ def main():
                        achieved=roofline.eval_flops(n_local, I) / (sc_ms / 1000.0) / 1e12, peak=pk["bf16"], unit="TFLOP/s",
                        frac=roofline.eval_flops(n_local, I) / (sc_ms / 1000.0) / 1e12 / pk["bf16"], traffic=None, launch_ms=sc_ms,
                        note="algorithmic FLOP 2*U*I*64 (the bf16x3 split issues 3x that on the tensor pipe); K=64 makes the kernel "
-                            "epilogue-bound: every accumulator is inspected once by the fused top-K (SURVEY 7 hard part 1)")
+                            "epilogue-bound: every accumulator is inspected once by the fused top-K (SURVEY 7 hard part 1); the chain accumulator "
+                            "drained -> 12 MMAs -> accumulator full -> epilogue runs at ~2.6k cycles per 128x128 tile and CTA against 0.8k of "
+                            "tensor time (DESIGN 7, scripts/probe/trace_topk.py)")
         ev_out = dict(metric="allneg_eval_users_per_s", value=n_eval / (ms_eval / 1000.0), unit="users/s", ms=ms_eval, users=n_eval,
                       e2e=dict(value=n_eval / (ms_eval_e2e / 1000.0), unit="users/s", d2h_bytes=n_eval * 20 * 4 + 128),
                       mode=("tc" if ev._use_tc() else "exact"), fallback_rows=getattr(ev, "n_fallback", 0),

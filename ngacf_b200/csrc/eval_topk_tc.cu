@@ -40,8 +40,11 @@ constexpr int TM = 128;                 // users per CTA (UMMA M)
 constexpr int TN = 128;                 // items per tile (UMMA N)
 constexpr int KP = 24;                  // approximate candidates kept per LIST (user x segment x column half): > 20, so that a list
                                         // holding the whole top-20 still has its threshold below the 20th exact score
-constexpr int KU = 24;                  // rank of the shared filter threshold inside the union of a row's two sorted lists (<= 2 KP; KP is the
-                                        // tightest choice and the one measured fastest: 0.72 ms against 0.76 ms with 32; no fallback rows either way)
+constexpr int KU = 32;                  // rank of the shared filter threshold inside the union of a row's two sorted lists (KP..2 KP).  It is also
+                                        // the rank of the final candidate cut, i.e. the proof's margin: the K-th EXACT score must clear the KU-th
+                                        // approximate one by the bf16x3 error bound.  KU = KP = 24 is 5 % faster (0.72 vs 0.76 ms) but leaves four
+                                        // ranks of margin: 1 of 52,639 amazon-book-shape users failed the proof -- and one fallback row costs 6 ms
+                                        // in the exact kernel.  With 12 ranks the failure probability falls by ~(delta/gap)^8 (none observed).
 constexpr int CBUF = 384;               // survivor LOG entries per epilogue thread (append-only; ~150 used on the gowalla shape; overflow -> exact fallback)
 constexpr int EPI = 256;                // epilogue threads per CTA
 constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
