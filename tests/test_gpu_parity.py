@@ -1077,3 +1077,43 @@ def test_spgat_long_rows_philox_dropout_and_refusals():
     lonely[0, 4] = lonely[4, 0] = 1.0
     with pytest.raises(ValueError):
         HomoGraph(lonely, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# AllNeg tensor-core scorer: the state it keeps between calls and its escape hatch
+# ------------------------------------------------------------------------------------------------
+def test_eval_tc_mask_reuse_rebuild_and_fallback():
+    """(1) the allowed-column matrix in the workspace is reused by the second evaluation and REBUILT when the pool changes (in-place
+    edit of `in_pool`: the evaluator keys it on the tensors' versions); (2) rows whose proof fails -- here every row: all item
+    embeddings equal, so every score ties -- are counted by the library, recomputed through the exact entry point when the result
+    is read, and come out identical to the exact evaluator."""
+    from ngacf_b200.evaluate import AllNegEvaluator
+    U, I = 300, 1000
+    it, dit, Zt, Fn = _eval_case(U, I, 9000, 5)
+    ev_tc, ev_ex = AllNegEvaluator(dit, "tc"), AllNegEvaluator(dit, "exact")
+    r1 = ev_tc(Zt)
+    assert ev_tc._mask_key is not None
+    key = ev_tc._mask_key
+    r2 = ev_tc(Zt)                                   # second call: reuse_mask = 1
+    assert ev_tc._mask_key == key
+    rx = ev_ex(Zt)
+    assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and ev_tc.n_fallback == 0
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        assert np.array_equal(r1[k], r2[k]) and np.allclose(r1[k], rx[k], rtol=0, atol=1e-12)
+    # take the 50 best-scored items of user 0 out of the pool, in place
+    best = torch.topk(torch.from_numpy(Fn[U:] @ Fn[int(dit.eval_users[0])]), 50).indices.to(DEV)
+    dit.in_pool[best] = 0
+    ev_tc(Zt)
+    assert ev_tc._mask_key != key                    # rebuilt
+    ev_ex(Zt)
+    assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
+    assert not bool(torch.isin(ev_tc.top_ids[0].long(), best).any())
+    # all item rows equal -> all scores of a user tie -> no margin for the proof -> every row goes through the fallback
+    Zt2 = Zt.clone()
+    Zt2[U:] = Zt2[U:U + 1]
+    ev_tc.rank(Zt2)
+    assert ev_tc._pending_fallback
+    ids = ev_tc.top_ids                              # reading the result resolves the flagged rows
+    assert ev_tc.n_fallback == dit.eval_users.numel() and not ev_tc._pending_fallback
+    ev_ex.rank(Zt2)
+    assert torch.equal(ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
