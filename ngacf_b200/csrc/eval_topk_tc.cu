@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) mask_clear_train_kernel(const int* __rest
 
 #ifdef NGACF_TOPK_TRACE
 // pipeline timeline of two CTAs (debug builds only): [cta slot][event][tile]
-__device__ long long g_topk_trace[2][6][512];
+__device__ long long g_topk_trace[2][8][512];
 __device__ long long g_topk_cta[4096][4];
 __device__ unsigned long long g_rescore_stat[4];   // sum of kept candidates, sum of listed (id >= 0) candidates, users, max kept      // per CTA: globaltimer at start / end of the epilogue of warp 0, SM id, log entries of (warp 0, lane 0)
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(THREADS, 2) score_topk_tc_kernel(const float* 
             // -- and only when a lane has enough to merge: a list that runs under a warm shared threshold logs a handful of survivors
             if (lt > 0 && (lt & (lt - 1)) == 0) {
                 if (__reduce_max_sync(0xffffffffu, cnt - done) >= 8) flush();
+                if (warp == 0 && lane == 0) TRACE(6, lt);
                 exchange();
+                if (warp == 0 && lane == 0) TRACE(7, lt);
             }
             mbar_wait(bar_tfull0 + 8 * buf, (uint32_t)((lt >> 1) & 1));
             if (warp == 0 && lane == 0) TRACE(4, lt);

@@ -36,7 +36,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
 print("rank(): %.3f ms" % (e0.elapsed_time(e1) / 5))
 lib = _lib.load()
-buf = np.zeros((2, 6, 512), np.int64)
+buf = np.zeros((2, 8, 512), np.int64)
 rc = lib.ngacf_debug_topk_trace(ctypes.c_void_p(buf.ctypes.data))
 assert rc == 0, rc
 rs = np.zeros(4, np.uint64)
@@ -81,3 +81,6 @@ for c in range(2):
     gap = x[4, 1:] - x[5, :-1]
     big = np.argsort(-gap)[:8]
     print("   largest epi_done(t-1)->tfull_ok(t):", sorted([(int(k) + 1, int(gap[k])) for k in big]))
+    sched = [t for t in range(1, nt) if t & (t - 1) == 0]
+    print("   scheduled merges (tile: merge, exchange incl. barrier waits, then wait for the accumulator):",
+          [(t, int(x[6, t] - x[5, t - 1]), int(x[7, t] - x[6, t]), int(x[4, t] - x[7, t])) for t in sched])
