@@ -263,6 +263,12 @@ int ngacf_sample_pairs(const int32_t* train_rows_user, const int32_t* train_ptr,
 int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
                            const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
                            int32_t* top_ids, float* top_scores, void* stream);
+/* the same result for FEW users (the rows the tc path flags): the item range is split over several CTAs per 16 users and the
+ * partial lists are merged -- one CTA walking all items alone takes 6 ms at 92 K items, whatever the user count. */
+size_t ngacf_score_topk_exact_split_workspace_bytes(int32_t I, int32_t n_users);
+int ngacf_score_topk_exact_split(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
+                                 const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,
+                                 int32_t* top_ids, float* top_scores, void* workspace, size_t workspace_bytes, void* stream);
 size_t ngacf_score_topk_tc_workspace_bytes(int32_t I, int32_t n_users);
 int ngacf_score_topk_tc(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users,
                         const int32_t* train_ptr, const int32_t* train_items, const uint8_t* in_pool,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "ngacf_adam_step_dev": (c_int32, [P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
     "ngacf_sample_pairs": (c_int32, [P, P, P, P, P, c_int32, c_int64, c_int64, P, c_uint64, c_uint32, P, P, P, P]),
     "ngacf_score_topk_exact": (c_int32, [P, c_int32, c_int32, P, c_int32, P, P, P, P, P, P]),
+    "ngacf_score_topk_exact_split_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "ngacf_score_topk_exact_split": (c_int32, [P, c_int32, c_int32, P, c_int32, P, P, P, P, P, P, c_size_t, P]),
     "ngacf_score_topk_tc_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "ngacf_score_topk_tc": (c_int32, [P, c_int32, c_int32, P, c_int32, P, P, P, P, P, P, c_int32, P, c_size_t, P]),
     "ngacf_eval_metrics_workspace_bytes": (c_size_t, [c_int32]),

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(EX_THREADS) score_topk_exact_kernel(const floa
                                                                       int n_users, const int* __restrict__ train_ptr,
                                                                       const int* __restrict__ train_items, const uint8_t* __restrict__ in_pool,
                                                                       int* __restrict__ top_ids, float* __restrict__ top_scores) {
+    // gridDim.y > 1 (few users, ngacf_score_topk_exact_split): CTA (x, y) ranks its 16 users on item slice y only and writes the
+    // slice's top-K to row (uslot * gridDim.y + y) of the outputs, which then are partial lists merged by merge_partial_topk_kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* It = reinterpret_cast<float*>(smem_raw);                 // [64 d][64 items]
     float* Us = It + 64 * EX_ITEMS;                                 // [16 users][64]
@@ -51,13 +53,23 @@ __global__ void __launch_bounds__(EX_THREADS) score_topk_exact_kernel(const floa
         Us[idx] = us < n_users ? F[(int64_t)users[us] * D + (idx & 63)] : 0.f;
     }
     for (int k = 0; k < K; ++k) { Ls[k * EX_THREADS + tid] = -INFINITY; Li[k * EX_THREADS + tid] = -1; }
-    if (il == 0) cursor[ul] = user >= 0 ? train_ptr[user] : 0;
+    const int tiles_all = (I + EX_ITEMS - 1) / EX_ITEMS;
+    const int i_begin = (int)((int64_t)blockIdx.y * tiles_all / gridDim.y) * EX_ITEMS;
+    const int i_end = min(I, (int)((int64_t)(blockIdx.y + 1) * tiles_all / gridDim.y) * EX_ITEMS);
+    if (il == 0) {            // first train item of the user inside the slice (sorted list)
+        int lo = user >= 0 ? train_ptr[user] : 0, hi = user >= 0 ? train_ptr[user + 1] : 0;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (train_items[mid] < i_begin) lo = mid + 1; else hi = mid;
+        }
+        cursor[ul] = lo;
+    }
     float thr = -INFINITY;    // score of this thread's current K-th entry
     int cnt = 0;
     __syncthreads();
     const int tend = user >= 0 ? train_ptr[user + 1] : 0;
 
-    for (int i0 = 0; i0 < I; i0 += EX_ITEMS) {
+    for (int i0 = i_begin; i0 < i_end; i0 += EX_ITEMS) {
         __syncthreads();
         // item tile, transposed: It[d][j] = F[U+i0+j][d]
         for (int idx = tid; idx < EX_ITEMS * 16; idx += EX_THREADS) {
@@ -132,13 +144,40 @@ __global__ void __launch_bounds__(EX_THREADS) score_topk_exact_kernel(const floa
                     if (id >= 0 && (bi < 0 || better(s, id, bs, bi))) { bs = s; bi = id; bl = l; }
                 }
             }
-            top_ids[(int64_t)uslot * K + k] = bi;
-            top_scores[(int64_t)uslot * K + k] = bi >= 0 ? bs : 0.f;
+            const int64_t orow = (int64_t)uslot * gridDim.y + blockIdx.y;
+            top_ids[orow * K + k] = bi;
+            top_scores[orow * K + k] = bi >= 0 ? bs : 0.f;
             if (bl >= 0) {
 #pragma unroll
                 for (int l = 0; l < 16; ++l) if (l == bl) ++head[l];
             }
         }
+    }
+}
+
+// P sorted partial lists of a user (disjoint item slices, ascending) -> its top-K under (score desc, id asc); one thread per user
+__global__ void __launch_bounds__(64) merge_partial_topk_kernel(const int* __restrict__ part_ids, const float* __restrict__ part_scores, int n_users, int P,
+                                                               int* __restrict__ top_ids, float* __restrict__ top_scores) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_users) return;
+    const int* ids = part_ids + (int64_t)j * P * K;
+    const float* scs = part_scores + (int64_t)j * P * K;
+    float last_s = INFINITY;
+    int last_i = -1;
+    for (int k = 0; k < K; ++k) {          // k-th pick: the best entry that comes after the previous pick in the order
+        float bs = -INFINITY;
+        int bi = -1;
+        for (int e = 0; e < P * K; ++e) {
+            const int id = ids[e];
+            const float sv = scs[e];
+            if (id < 0) continue;
+            const bool after = last_i < 0 || sv < last_s || (sv == last_s && id > last_i);
+            if (after && (bi < 0 || better(sv, id, bs, bi))) { bs = sv; bi = id; }
+        }
+        top_ids[(int64_t)j * K + k] = bi;
+        top_scores[(int64_t)j * K + k] = bi >= 0 ? bs : 0.f;
+        if (bi < 0) { for (int r = k + 1; r < K; ++r) { top_ids[(int64_t)j * K + r] = -1; top_scores[(int64_t)j * K + r] = 0.f; } break; }
+        last_s = bs; last_i = bi;
     }
 }
 
@@ -230,6 +269,45 @@ extern "C" int ngacf_score_topk_exact(const float* F, int32_t U, int32_t I, cons
     score_topk_exact_kernel<<<ceil_div(n_users, EX_USERS), EX_THREADS, EX_SMEM, (cudaStream_t)stream>>>(F, U, I, users, n_users, train_ptr,
                                                                                                          train_items, in_pool, top_ids, top_scores);
     return check_launch("score_topk_exact");
+}
+
+// few users (the rows the tensor-core path flags): one CTA per 16 users would walk all items alone (6 ms at 92 K items for a single
+// row); the item range is split over P CTAs per user group and the P partial lists are merged
+static int exact_split_parts(int n_users, int I) {
+    const int groups = (n_users + EX_USERS - 1) / EX_USERS;
+    int P = groups > 0 ? (2 * 148) / groups : 1;
+    const int tiles = (I + EX_ITEMS - 1) / EX_ITEMS;
+    if (P > tiles / 8) P = tiles / 8;
+    if (P > 64) P = 64;
+    if (P < 1) P = 1;
+    return P;
+}
+
+extern "C" size_t ngacf_score_topk_exact_split_workspace_bytes(int32_t I, int32_t n_users) {
+    return (size_t)(n_users > 0 ? n_users : 1) * exact_split_parts(n_users, I) * K * 8 + 256;
+}
+
+extern "C" int ngacf_score_topk_exact_split(const float* F, int32_t U, int32_t I, const int32_t* users, int32_t n_users, const int32_t* train_ptr,
+                                            const int32_t* train_items, const uint8_t* in_pool, int32_t* top_ids, float* top_scores,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    NGACF_REQUIRE(F && users && train_ptr && train_items && in_pool && top_ids && top_scores && workspace && U > 0 && I > 0 && n_users >= 0,
+                  "score_topk_exact_split: null/empty argument");
+    if (workspace_bytes < ngacf_score_topk_exact_split_workspace_bytes(I, n_users)) { set_error("score_topk_exact_split: workspace too small"); return NGACF_ERR_WORKSPACE; }
+    if (n_users == 0) return NGACF_OK;
+    const int P = exact_split_parts(n_users, I);
+    if (P == 1) return ngacf_score_topk_exact(F, U, I, users, n_users, train_ptr, train_items, in_pool, top_ids, top_scores, stream);
+    static PerDeviceOnce once;
+    once.run([] {
+        cudaFuncSetAttribute(score_topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EX_SMEM);
+    });
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int* part_ids = (int*)w;
+    float* part_scores = (float*)(w + (size_t)n_users * P * K * 4);
+    score_topk_exact_kernel<<<dim3(ceil_div(n_users, EX_USERS), P), EX_THREADS, EX_SMEM, st>>>(F, U, I, users, n_users, train_ptr, train_items, in_pool,
+                                                                                              part_ids, part_scores);
+    merge_partial_topk_kernel<<<ceil_div(n_users, 64), 64, 0, st>>>(part_ids, part_scores, n_users, P, top_ids, top_scores);
+    return check_launch("score_topk_exact_split");
 }
 
 extern "C" size_t ngacf_eval_metrics_workspace_bytes(int32_t n_users) { return (size_t)(n_users > 0 ? n_users : 1) * 16 * sizeof(double); }

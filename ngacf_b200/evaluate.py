@@ -95,7 +95,7 @@ class AllNegEvaluator:
         users = self.users[bad].contiguous()
         ids = torch.empty((bad.numel(), K), dtype=torch.int32, device=self.F.device)
         sc = torch.empty((bad.numel(), K), dtype=torch.float32, device=self.F.device)
-        ops.score_topk_exact(self.F, it.U, it.I, users, it, ids, sc)
+        ops.score_topk_exact_split(self.F, it.U, it.I, users, it, ids, sc)
         self._top_ids[bad] = ids
         self._top_scores[bad] = sc
         return True

@@ -220,6 +220,14 @@ def score_topk_exact(F, U, I, users, inter, top_ids, top_scores):
               _p(inter.in_pool), _p(top_ids), _p(top_scores), _s())
 
 
+def score_topk_exact_split(F, U, I, users, inter, top_ids, top_scores):
+    """score_topk_exact for few users: item range split over CTAs (workspace allocated here: this is the rare fallback path)"""
+    n = users.numel()
+    ws = torch.empty(int(_lib.load().ngacf_score_topk_exact_split_workspace_bytes(I, n)), dtype=torch.uint8, device=F.device)
+    _lib.call("ngacf_score_topk_exact_split", _p(F), U, I, _p(users), n, _p(inter.train_ptr), _p(inter.train_items),
+              _p(inter.in_pool), _p(top_ids), _p(top_scores), _p(ws), ws.numel(), _s())
+
+
 def score_topk_tc_workspace_bytes(I, n_users):
     return int(_lib.load().ngacf_score_topk_tc_workspace_bytes(I, n_users))
 

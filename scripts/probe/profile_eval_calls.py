@@ -43,3 +43,19 @@ with torch.no_grad():
         print("  %-34s %8.3f ms" % (name, a.elapsed_time(b)))
     _lib.PROFILE = None
     print("fallback rows", ev.n_fallback)
+
+# cost of the exact fallback for a handful of flagged rows: one CTA per 16 users over all items vs the item-split entry point
+from ngacf_b200 import ops  # noqa: E402
+for n in (1, 16, 64):
+    users = inter.eval_users[:n].contiguous()
+    ids = torch.empty((n, 20), dtype=torch.int32, device=DEV)
+    sc = torch.empty((n, 20), dtype=torch.float32, device=DEV)
+    for name, fn in (("score_topk_exact", ops.score_topk_exact), ("score_topk_exact_split", ops.score_topk_exact_split)):
+        fn(ev.F, U, I, users, inter, ids, sc)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn(ev.F, U, I, users, inter, ids, sc)
+        e1.record()
+        torch.cuda.synchronize()
+        print("%-24s %3d users: %.3f ms" % (name, n, e0.elapsed_time(e1) / 5))

@@ -1117,3 +1117,31 @@ def test_eval_tc_mask_reuse_rebuild_and_fallback():
     assert ev_tc.n_fallback == dit.eval_users.numel() and not ev_tc._pending_fallback
     ev_ex.rank(Zt2)
     assert torch.equal(ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
+
+
+def test_eval_exact_split_equals_exact():
+    """ngacf_score_topk_exact_split (the fallback for the few rows the tc path flags: item range split over CTAs + merge of the
+    partial lists) returns exactly what ngacf_score_topk_exact returns -- ids, scores, ties by lowest id, -1 padding."""
+    from ngacf_b200 import ops
+    U, I = 1000, 3000
+    it, dit, Zt, Fn = _eval_case(U, I, 40000, 3, 300)          # 300 duplicated item rows: exact score ties
+    F = torch.empty_like(Zt)
+    ops.final_features(Zt, F)
+    for n in (1, 5, 37):
+        users = dit.eval_users[torch.randperm(dit.eval_users.numel(), generator=torch.Generator().manual_seed(n))[:n].to(DEV)].contiguous()
+        a_ids = torch.empty((n, 20), dtype=torch.int32, device=DEV)
+        a_sc = torch.empty((n, 20), dtype=torch.float32, device=DEV)
+        b_ids, b_sc = torch.full_like(a_ids, -7), torch.full_like(a_sc, -7.0)
+        ops.score_topk_exact(F, U, I, users, dit, a_ids, a_sc)
+        ops.score_topk_exact_split(F, U, I, users, dit, b_ids, b_sc)
+        assert torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc), n
+    # a pool of 12 items: fewer than 20 candidates -> -1 padding survives the merge
+    dit.in_pool[:] = 0
+    dit.in_pool[torch.arange(0, I, I // 12, device=DEV)[:12]] = 1
+    users = dit.eval_users[:3].contiguous()
+    a_ids = torch.empty((3, 20), dtype=torch.int32, device=DEV)
+    a_sc = torch.empty((3, 20), dtype=torch.float32, device=DEV)
+    b_ids, b_sc = torch.full_like(a_ids, -7), torch.full_like(a_sc, -7.0)
+    ops.score_topk_exact(F, U, I, users, dit, a_ids, a_sc)
+    ops.score_topk_exact_split(F, U, I, users, dit, b_ids, b_sc)
+    assert torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc) and bool((a_ids[:, 12:] == -1).all())
