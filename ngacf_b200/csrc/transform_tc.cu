@@ -97,6 +97,15 @@ __device__ __forceinline__ void tile_rows(int warp, int lane, int it, int& r, in
     q = 4 * (it & 3) + (lane >> 3);
 }
 
+#ifdef NGACF_DENSE_TRACE
+// phase timeline of CTA 0 and CTA 150 of the forward kernel (debug builds): [cta][event]; events: 0 start, 1 prologue done,
+// then per tile (up to 4): 2+5t image stored, 3+5t MMAs issued, 4+5t accumulator ready, 5+5t epilogue math done, 6+5t stores issued
+__device__ long long g_dense_trace[2][32];
+#define DTRACE(ev) do { if ((blockIdx.x == 0 || blockIdx.x == 150) && threadIdx.x == 0 && (ev) < 32) g_dense_trace[blockIdx.x ? 1 : 0][ev] = clock64(); } while (0)
+#else
+#define DTRACE(ev) do { } while (0)
+#endif
+
 // MODE 0: forward (A = drop(act(X)), B[n][k] = Wcat[k][n], epilogue h, s)
 // MODE 1: backward dX (A = dh, B[n][k] = Wcat[n][k], epilogue mask/ELU'/accumulate)
 template <int H, int MODE>
@@ -129,6 +138,8 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
     const int64_t node_off = item_side ? U : 0;
     const int tiles = (rows_side + TM - 1) / TM;
 
+    DTRACE(0);
+    int tcount = 0;
     // ---- first tile's rows are requested before anything else ----
     float4 v[8];
     uint64_t mw[2] = {0ull, 0ull};
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         }
     };
     if (bs < tiles) request(bs);
+    DTRACE(27);
 
     // ---- one-time: barrier, TMEM, operand B (the side's 64x64 weight block, split) ----
     if (tid == 0) {
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    DTRACE(28);
     {
         const float* const* wptr = wtab + (item_side ? H : 0);
         float4 w[4];
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
             const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
             w[j] = __ldg(reinterpret_cast<const float4*>(wptr[c / DH] + k * DH + (c % DH)));     // Wcat[k][c..c+3]
         }
+        DTRACE(29);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
@@ -187,11 +201,13 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         }
         if (MODE == 0 && tid < 64) av[tid] = __ldg(wtab[2 * H + tid / DH] + (item_side ? DH : 0) + tid % DH);
     }
+    DTRACE(30);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     uint32_t phase = 0;
+    DTRACE(1);
     const uint64_t dAhi = smem_desc(smem_u32(sAhi), PANEL_A), dAlo = smem_desc(smem_u32(sAlo), PANEL_A);
     const uint64_t dBhi = smem_desc(smem_u32(sBhi), PANEL_B), dBlo = smem_desc(smem_u32(sBlo), PANEL_B);
     const int quarter = warp & 3, half = warp >> 2;      // TMEM lanes 32*quarter.., accumulator columns 32*half..
@@ -222,6 +238,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        DTRACE(2 + 5 * tcount);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -234,6 +251,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
                     umma_tf32(tmem_base, a0 + (uint64_t)(ks * 2 * PANEL_A / 16), b0 + (uint64_t)(ks * 2 * PANEL_B / 16), (term | ks) ? 1u : 0u);
             }
             umma_commit(smem_u32(bar));
+            DTRACE(3 + 5 * tcount);
         }
         // the next tile's rows -- and what this tile's epilogue needs from global memory -- travel while the tensor core works
         if (tile + nbs < tiles) request(tile + nbs);
@@ -251,6 +269,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         mbar_wait(smem_u32(bar), phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        DTRACE(4 + 5 * tcount);
 
         // ---- epilogue: thread = (row = TMEM lane 32*quarter + lane, 32 accumulator columns 32*half..) ----
         float acc[32];
@@ -282,6 +301,7 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         }
         // stage this warp's 32 rows x 128 bytes through its slice of the (retired) A-hi image: row r at r*128, 16-byte chunk c at
         // slot c ^ (r & 7) -> conflict-free for the row-per-thread writes and the 4-rows-per-instruction reads
+        DTRACE(5 + 5 * tcount);
         uint8_t* stg = sAhi + warp * 4096;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -316,6 +336,8 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         // the staging reads and the TMEM reads of this tile must retire before the next tile's image / MMAs overwrite them
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        DTRACE(6 + 5 * tcount);
+        ++tcount;
         if (MODE == 0 && H == 1 && tid < nrows) s[node_off + row0 + tid] = sp[tid] + sp[TM + tid];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -325,6 +347,16 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
+
+}  // namespace tcx
+}  // namespace ngacf
+#ifdef NGACF_DENSE_TRACE
+extern "C" int ngacf_debug_dense_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, ngacf::tcx::g_dense_trace, sizeof(ngacf::tcx::g_dense_trace));
+}
+#endif
+namespace ngacf {
+namespace tcx {
 
 static void side_grid(int U, int I, int* nb_u, int* nb_i) {
     const int tiles_u = ceil_div(U, TM), tiles_i = ceil_div(I, TM);
