@@ -92,6 +92,7 @@ __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
 
 // coalesced-enough tile load: warp w (of 8) owns rows 16w..16w+15; one instruction = 8 rows x 4 chunks (64-byte row segments in
 // global memory, 4 x 128 contiguous bytes in the operand image: no bank conflicts)
+__device__ __forceinline__ bool item_side_of(unsigned block, int nb_u) { return (int)block >= nb_u; }
 __device__ __forceinline__ void tile_rows(int warp, int lane, int it, int& r, int& q) {
     r = 16 * warp + 8 * (it >> 2) + (lane & 7);
     q = 4 * (it & 3) + (lane >> 3);
@@ -140,7 +141,18 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
 
     DTRACE(0);
     int tcount = 0;
-    // ---- first tile's rows are requested before anything else ----
+    // ---- the weight block sits behind the pointer table: two dependent round trips, so the pointers go first ----
+    const float* wp[4];
+    {
+        const float* const* wptr = wtab + (item_side_of(blockIdx.x, nb_u) ? H : 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = threadIdx.x + j * THREADS;
+            const int col = MODE == 0 ? (idx & 63) : (idx & 15) * 4;
+            wp[j] = wptr[col / (D / H)];
+        }
+    }
+    // ---- then the first tile's rows ----
     float4 v[8];
     uint64_t mw[2] = {0ull, 0ull};
     auto request = [&](int tile) {
@@ -174,26 +186,41 @@ __global__ void __launch_bounds__(THREADS, 2) transform_tc_kernel(const float* _
     }
     DTRACE(28);
     {
-        const float* const* wptr = wtab + (item_side ? H : 0);
-        float4 w[4];
+        if (MODE == 0) {
+            // B[n][kk = k] = Wcat[k][n]: one item = (column n, four consecutive k) = one 16-byte slot of the K-major image, so the
+            // transposed image is written with conflict-free 16-byte stores (it was 32 scalar stores per thread, 8-way conflicts);
+            // the four scalar loads of an item are coalesced over n
+            float wv[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
-            w[j] = __ldg(reinterpret_cast<const float4*>(wptr[c / DH] + k * DH + (c % DH)));     // Wcat[k][c..c+3]
-        }
-        DTRACE(29);
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + j * THREADS, n = idx & 63, kg = idx >> 6;
+                const float* src = wp[j] + (4 * kg) * DH + (n % DH);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
-            float4 hi, lo;
-            split4(w[j], hi, lo);
-            if (MODE == 0) {   // B[n = c+i][kk = k]
-                const uint32_t o = (uint32_t)(k >> 2) * PANEL_B + (uint32_t)(k & 3) * 4;
-                *reinterpret_cast<float*>(sBhi + o + (c + 0) * 16) = hi.x; *reinterpret_cast<float*>(sBlo + o + (c + 0) * 16) = lo.x;
-                *reinterpret_cast<float*>(sBhi + o + (c + 1) * 16) = hi.y; *reinterpret_cast<float*>(sBlo + o + (c + 1) * 16) = lo.y;
-                *reinterpret_cast<float*>(sBhi + o + (c + 2) * 16) = hi.z; *reinterpret_cast<float*>(sBlo + o + (c + 2) * 16) = lo.z;
-                *reinterpret_cast<float*>(sBhi + o + (c + 3) * 16) = hi.w; *reinterpret_cast<float*>(sBlo + o + (c + 3) * 16) = lo.w;
-            } else {           // B[n = k][kk = c..c+3]
+                for (int i = 0; i < 4; ++i) wv[j][i] = __ldg(src + i * DH);
+            }
+            DTRACE(29);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + j * THREADS, n = idx & 63, kg = idx >> 6;
+                float4 hi, lo;
+                split4(make_float4(wv[j][0], wv[j][1], wv[j][2], wv[j][3]), hi, lo);
+                const uint32_t o = (uint32_t)kg * PANEL_B + (uint32_t)n * 16;
+                *reinterpret_cast<float4*>(sBhi + o) = hi;
+                *reinterpret_cast<float4*>(sBlo + o) = lo;
+            }
+        } else {
+            float4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
+                w[j] = __ldg(reinterpret_cast<const float4*>(wp[j] + k * DH + (c % DH)));     // Wcat[k][c..c+3]
+            }
+            DTRACE(29);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {           // B[n = k][kk = c..c+3]
+                const int idx = tid + j * THREADS, k = idx >> 4, c = (idx & 15) * 4;
+                float4 hi, lo;
+                split4(w[j], hi, lo);
                 const uint32_t o = (uint32_t)(c >> 2) * PANEL_B + (uint32_t)k * 16;
                 *reinterpret_cast<float4*>(sBhi + o) = hi;
                 *reinterpret_cast<float4*>(sBlo + o) = lo;
