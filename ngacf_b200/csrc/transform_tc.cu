@@ -507,6 +507,15 @@ __device__ __forceinline__ uint32_t stage_off(int r, int q) {
     return (uint32_t)((quarter + 4 * cq) * 2048 + rr * 64 + ((qq ^ ((rr >> 1) & 3)) * 16));
 }
 
+#ifdef NGACF_DENSE_TRACE
+// phase timeline of CTA 0 and CTA 100 of the fused backward kernel: 0 start, 1 prologue done, per tile t (up to 6): 2+4t images stored,
+// 3+4t MMAs issued, 4+4t accumulators ready, 5+4t epilogue done; 30 = partials written
+__device__ long long g_dense_bwd_trace[2][32];
+#define BTRACE(ev) do { if ((blockIdx.x == 0 || blockIdx.x == 100) && threadIdx.x == 0 && (ev) < 32) g_dense_bwd_trace[blockIdx.x ? 1 : 0][ev] = clock64(); } while (0)
+#else
+#define BTRACE(ev) do { } while (0)
+#endif
+
 template <int H>
 __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const float* __restrict__ dh, const float* __restrict__ dS,
                                                                       const float* __restrict__ Xu, const float* __restrict__ Xi, int apply_elu,
@@ -514,6 +523,8 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
                                                                       const float* const* __restrict__ wtab, int U, int I, int nb_u,
                                                                       float* __restrict__ dXu, float* __restrict__ dXi, int accumulate_dx,
                                                                       float* __restrict__ partials) {
+    BTRACE(0);
+    int tcount = 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* sDH = base + OFF_DH;
@@ -535,6 +546,8 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
     const int64_t node_off = item_side ? U : 0;
     const int tiles = (rows_side + TM - 1) / TM;
 
+    // the weight block sits behind the pointer table (two dependent round trips): its pointer is requested before anything else
+    const float* wsrc = (wtab + (item_side ? H : 0))[((tid & 7) * 8) / DH_];
     // tile loads: warp w (of 16) owns rows 8w..8w+7; item `it` = those 8 rows x feature chunks (8 floats) 4it..4it+3
     const int lr = 8 * warp + (lane & 7);            // this thread's row within the tile (fixed)
     float4 vd[4], vx[4], vs0 = make_float4(0.f, 0.f, 0.f, 0.f), vs1 = vs0;
@@ -576,9 +589,8 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {   // W image of the dX product: B[n = k][kk = c] = Wcat[k][c], one (row k, 8-feature chunk) item per thread
-        const float* const* wptr = wtab + (item_side ? H : 0);
         const int k = tid >> 3, c = (tid & 7) * 8;
-        const float* src = wptr[c / DH_] + k * DH_ + (c % DH_);       // DH is 8 or 64: the 8 values are contiguous
+        const float* src = wsrc + k * DH_ + (c % DH_);               // DH is 8 or 64: the 8 values are contiguous
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(src)), w1 = __ldg(reinterpret_cast<const float4*>(src + 4));
         uint4 h, m, l;
         split3x8(w0, w1, h, m, l);
@@ -601,6 +613,7 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
     const int quarter = warp & 3, cq = warp >> 2;     // epilogue: TMEM lanes 32*quarter.., D1 columns 16*cq..
     const float sc = featmask ? scale : 1.f;
     bool first = true;
+    BTRACE(1);
 
     for (int tile = bs; tile < tiles; tile += nbs) {
         const int row0 = tile * TM;
@@ -649,6 +662,9 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        BTRACE(2 + 4 * tcount);
+        // (two issuing threads with accumulators of their own were measured: no gain -- the 72 MMAs of a tile are tensor-pipe time,
+        // ~59 cycles each, not issue time)
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // the six term pairs (a, b) with a + b <= 2 (0 = h, 1 = m, 2 = l), smallest products first: every accumulation rounds at
@@ -675,12 +691,14 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
                          (!first || ((pr != 0 && pr != 5) | ks)) ? 1u : 0u);
             }
             umma_commit(smem_u32(bar));
+            BTRACE(3 + 4 * tcount);
         }
         first = false;
         if (tile + nbs < tiles) request(tile + nbs);
         mbar_wait(smem_u32(bar), phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        BTRACE(4 + 4 * tcount);
 
         // ---- dX epilogue: thread = (row = TMEM lane 32*quarter + lane, 16 columns 16*cq..) ----
         float acc[16];
@@ -708,6 +726,8 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        BTRACE(5 + 4 * tcount);
+        ++tcount;
     }
 
     // ---- CTA partial: dW[k][c] (lanes 0..63 of D2, columns 0..63) and da through Q (columns 64..71) ----
@@ -751,11 +771,24 @@ __global__ void __launch_bounds__(THREADS, 1) transform_bwd_tc_kernel(const floa
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    BTRACE(30);
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
+
+}  // namespace bwd
+}  // namespace tcx
+}  // namespace ngacf
+#ifdef NGACF_DENSE_TRACE
+extern "C" int ngacf_debug_dense_bwd_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, ngacf::tcx::bwd::g_dense_bwd_trace, sizeof(ngacf::tcx::bwd::g_dense_bwd_trace));
+}
+#endif
+namespace ngacf {
+namespace tcx {
+namespace bwd {
 
 static void side_grid1(int U, int I, int* nb_u, int* nb_i) {
     const int tiles_u = ceil_div(U, TM), tiles_i = ceil_div(I, TM);

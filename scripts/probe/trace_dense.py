@@ -52,3 +52,46 @@ for k, H in ((0, 8), (1, 1)):
             print("    tile %d: image %.0f, MMA issue %.0f, MMA wait %.0f, epilogue math %.0f, staging+stores+sync %.0f   (end at %.0f)" % (
                 k2, t[b] - prev, t[b + 1] - t[b], t[b + 2] - t[b + 1], t[b + 3] - t[b + 2], t[b + 4] - t[b + 3], t[b + 4] - t0))
             k2 += 1
+
+# ---- fused backward kernel (dX, dW, da): one 512-thread CTA per SM, persistent over ~3.7 tiles ----
+from ngacf_b200.graph import BipartiteGraph  # noqa: E402,F401
+N = U + I
+dh = torch.randn((N, 64), device=DEV)
+dS = torch.randn((N, 8), device=DEV)
+X = torch.randn((N, 64), device=DEV)
+dX = torch.empty((N, 64), device=DEV)
+ws = torch.empty(ops.transform_bwd_workspace_bytes(U, I) // 4, device=DEV)
+for k, H in ((0, 8), (1, 1)):
+    grads = [torch.empty_like(p_) for p_ in sp[k]]
+    gt = ops.pointer_table(grads)
+    fn = lambda: ops.transform_bwd(dh, dS, None, X, X[U:], 1, None, 1.0, wt[k], gt, H, U, I, dX, dX[U:], 0, 0, ws)
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print("transform_bwd H=%d: %.2f us per call incl. the partial reduction (20 back to back in a graph)" % (H, e0.elapsed_time(e1) / 20 * 1000))
+    fn()
+    torch.cuda.synchronize()
+    buf = np.zeros((2, 32), np.int64)
+    assert _lib.load().ngacf_debug_dense_bwd_trace(ctypes.c_void_p(buf.ctypes.data)) == 0
+    for c in range(2):
+        t = buf[c].astype(np.float64)
+        t0 = t[0]
+        print("  CTA %d: prologue %.0f cycles, whole CTA %.0f" % (c, t[1] - t0, t[30] - t0))
+        k2 = 0
+        while 5 + 4 * k2 < 30 and t[5 + 4 * k2] > t0:
+            b = 2 + 4 * k2
+            prev = t[1] if k2 == 0 else t[b - 1]
+            print("    tile %d: images %.0f, MMA issue (72) %.0f, MMA wait %.0f, epilogue + stores + sync %.0f" % (
+                k2, t[b] - prev, t[b + 1] - t[b], t[b + 2] - t[b + 1], t[b + 3] - t[b + 2]))
+            k2 += 1
+        print("    partials + teardown %.0f" % (t[30] - t[5 + 4 * (k2 - 1)]))
