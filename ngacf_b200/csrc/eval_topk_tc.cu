@@ -55,6 +55,8 @@ constexpr int TILE_BYTES = 2 * HALF_BYTES;   // 32 KB per item tile (hi + lo)
 constexpr int THREADS = 320;
 constexpr int STAGES = 2;                // item-tile ring in shared memory
 constexpr size_t SMEM_BYTES = 2 * HALF_BYTES /*A*/ + STAGES * TILE_BYTES /*B ring*/ + 16 * EPI * 4 /*score staging*/ + 128 /*barriers*/ + 128 /*align*/;
+// the survivor-log pool (resident_ctas()) holds two buffers per SM: a third resident CTA would spin for a buffer forever
+static_assert(3 * SMEM_BYTES > 228 * 1024, "at most two CTAs of score_topk_tc_kernel may be resident per SM");
 constexpr float GUARD = 1e-4f;          // |approx - exact| <= GUARD * |u| * max|i|  (bf16x3: ~6e-5 worst case)
 
 // instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128  (cute::UMMA::InstrDescriptor bit layout)
