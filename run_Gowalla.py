@@ -41,7 +41,9 @@ def prepareData(args):
 
 def createModels(args, userNum, itemNum):
     if args.model not in ("SPUIGACF", "SPUIMultiGACF"):
-        raise NotImplementedError("--model SPUIGACF (in scope) and SPUIMultiGACF (SURVEY.md 8f-1) are built; SPUIGAGPCF is not")
+        raise NotImplementedError("--model SPUIGACF and SPUIMultiGACF are wired to the CLI.  SPUIGAGPCF exists as a class "
+                                  "(graphattention.SPUIGACF.SPUIGAGPCF, needs the Laplacian as `adj`); the reference's own CLI branch "
+                                  "for it reads an undefined name (run_Gowalla.py:102) and its evaluators rank 64-wide features")
     cls = SPUIGACF if args.model == "SPUIGACF" else SPUIMultiGACF
     model = cls(userNum, itemNum, embedSize=args.embedSize, layers=args.layers, droprate=args.droprate).cuda()
     lossfn = BPRLoss() if args.train_mode == "PairSampling" else torch.nn.BCEWithLogitsLoss()      # run_Gowalla.py:104-110

@@ -232,3 +232,24 @@ def test_normalized_laplacian_matches_reference_fixture():
     assert np.allclose(L.values().numpy(), gz["lap_val"], rtol=1e-6, atol=0)
     M = normalized_laplacian(U, I, gz["edge_u"], gz["edge_i"], None, "mean_adj").to_dense().numpy()
     assert np.allclose(M, M.T) and np.allclose(np.diag(M), 0)
+
+
+def test_fused_paths_take_exact_model_types_only():
+    """A subclass with layers behind the propagation (SPUIGAGPCF) is an SPUIGACF instance, but the captured training steps and the
+    evaluators work on the 64-wide SpUIGAT features alone: they must refuse it instead of silently training / ranking its base."""
+    import torch
+    import train_eval_Gowalla as te
+    from graphattention.BPRLoss import BPRLoss
+    from graphattention.SPUIGACF import SPUIGACF, SPUIGAGPCF, SPUIMultiGACF
+    U, I = 12, 15
+    L = torch.sparse_coo_tensor(torch.tensor([[0, U], [U, 0]]), torch.tensor([0.5, 0.5]), (U + I, U + I))
+    for cls, ok in ((SPUIGACF, True), (SPUIMultiGACF, True)):
+        m = cls(U, I, 64, [64, 64], 0.1, useCuda=False)
+        opt = torch.optim.Adam(m.parameters(), lr=0.01)
+        assert te._fused_ok(m, opt, BPRLoss()) is ok
+        assert te._plain_gat_model(m)
+    m = SPUIGAGPCF(U, I, L, 64, [64, 64], 0.1, useCuda=False)
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+    assert isinstance(m, SPUIGACF) and not te._fused_ok(m, opt, BPRLoss()) and not te._plain_gat_model(m)
+    with pytest.raises(NotImplementedError):
+        te._require_plain(m, "eval_neg_all")

@@ -60,12 +60,24 @@ def _device_adj(model, adj):
     return t
 
 
+def _plain_gat_model(m):
+    """True for the models whose final features ARE the SpUIGAT propagation (what the captured steps and the evaluators use)."""
+    from ngacf_b200.model import SPUIGACF, SPUIMultiGACF
+    return type(m) in (SPUIGACF, SPUIMultiGACF)
+
+
+def _require_plain(m, what):
+    if not _plain_gat_model(m):
+        raise NotImplementedError("%s ranks on the 64-wide SpUIGAT features of SPUIGACF / SPUIMultiGACF; %s scores through "
+                                  "model(userIdx, itemIdx, adj) only" % (what, type(m).__name__))
+
+
 def _fused_ok(m, optim, lossfn, loss_type=None):
     from ngacf_b200.loss import BPRLoss
-    from ngacf_b200.model import SPUIGACF
     from ngacf_b200.optim import FusedAdam
     loss_type = BPRLoss if loss_type is None else loss_type
-    if not isinstance(m, SPUIGACF) or not isinstance(lossfn, loss_type) or len(optim.param_groups) != 1:
+    # exact types: a subclass with more layers behind the propagation (SPUIGAGPCF) must not be trained as its base class
+    if not _plain_gat_model(m) or not isinstance(lossfn, loss_type) or len(optim.param_groups) != 1:
         return False
     if loss_type is torch.nn.BCEWithLogitsLoss and (lossfn.reduction != "mean" or lossfn.weight is not None or lossfn.pos_weight is not None):
         return False
@@ -169,6 +181,7 @@ def eval_neg_all(model, batch_size, test_df, test_pos_neg, adj, itemNum, is_para
     divisor (train_eval_Gowalla.py:283).  Returns the reference's result dict (:277-278,354)."""
     m = _unwrap(model)
     model.eval()
+    _require_plain(m, "eval_neg_all")
     inter = _interactions(model, None, test_pos_neg, test_df)
     adj_t = _device_adj(model, adj)
     with torch.no_grad():
@@ -255,6 +268,7 @@ def eval_neg_sample(model, batch_size, test_df, test_pos_neg, adj, top_k, is_par
     averaged over the test rows.  All rows are scored against one propagation.  Returns (HR, NDCG)."""
     m = _unwrap(model)
     model.eval()
+    _require_plain(m, "eval_neg_sample")
     inter = _neg_interactions(model, test_pos_neg, test_df=test_df)
     adj_t = _device_adj(model, adj)
     from ngacf_b200.negsampling import SampledNegEvaluator
