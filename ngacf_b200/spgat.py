@@ -117,13 +117,17 @@ class SpGraphAttentionLayer(nn.Module):
         nn.init.xavier_normal_(self.W.data, gain=1.414)
         self.a = nn.Parameter(torch.zeros(size=(1, 2 * out_features)))
         nn.init.xavier_normal_(self.a.data, gain=1.414)
+        self._call = 0              # one dropout stream per training-mode call of a stand-alone layer
 
     def forward(self, input, adj, userNum=None):
         if self.in_features != D or self.out_features != D:
             raise NotImplementedError("a stand-alone layer runs for 64 -> 64 only; the 8-wide heads are evaluated batched by SpGAT.forward")
         graph = adj if isinstance(adj, HomoGraph) else HomoGraph(adj, userNum)
         drop = self.p if self.training else 0.0
-        Z = SpGATFn.apply(graph, drop, int(torch.initial_seed()), 0, None, ((1, D),), False, input, self.W, self.a)
+        call = self._call
+        if drop > 0:
+            self._call += 1
+        Z = SpGATFn.apply(graph, drop, int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, call, None, ((1, D),), False, input, self.W, self.a)
         return torch.nn.functional.elu(Z) if self.concat else Z
 
     def __repr__(self):
