@@ -194,7 +194,8 @@ def _stage_lists(params, stages):
 
 
 class SpGATFn(torch.autograd.Function):
-    """Z_last = SpGAT stages on x (N,64).  elu_between: ELU on the concatenated head outputs (SPGA.py:413), always true for SpGAT."""
+    """Z_last = SpGAT stages on x (N,64).  elu_between: the SpGAT composition (dropout on every stage input, ELU on the concatenated
+    head outputs, SPGA.py:352-357); False: one layer on its own (edge dropout only)."""
 
     @staticmethod
     def forward(ctx, graph: HomoGraph, droprate, seed, call, injected, stages, elu_between, x, *params):
@@ -214,11 +215,13 @@ class SpGATFn(torch.autograd.Function):
                 featmask = [m.contiguous() for m in injected["feat"]]
                 edgemask = [m.contiguous() for m in injected["edge"]]
             else:
-                featmask = [torch.empty(N, dtype=torch.int64, device=dev) for _ in range(S)]
                 edgemask = [torch.empty(graph.n_edges, dtype=torch.uint8, device=dev) for _ in range(S)]
                 for k, (H, _) in enumerate(stages):
-                    ops.feature_mask(featmask[k], seed, call, k, droprate)
                     ops.edge_mask(edgemask[k], H, seed, call, k, droprate)
+                if elu_between:         # SpGAT.forward drops its stage inputs (SPGA.py:353,355); a layer on its own only its edges (:398)
+                    featmask = [torch.empty(N, dtype=torch.int64, device=dev) for _ in range(S)]
+                    for k in range(S):
+                        ops.feature_mask(featmask[k], seed, call, k, droprate)
         scratch, counter = g.scratch("spgat")
         h = [torch.empty((N, D), **f32) for _ in stages]
         Z = [torch.empty((N, D), **f32) for _ in stages]

@@ -1145,3 +1145,34 @@ def test_eval_exact_split_equals_exact():
     ops.score_topk_exact(F, U, I, users, dit, a_ids, a_sc)
     ops.score_topk_exact_split(F, U, I, users, dit, b_ids, b_sc)
     assert torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc) and bool((a_ids[:, 12:] == -1).all())
+
+
+def test_spgraphattentionlayer_standalone_64x64():
+    """One SpGraphAttentionLayer(64 -> 64) called on its own (SPGA.py:375-417) against the port restatement: output, d input, dW, da;
+    and a fresh dropout stream per training call."""
+    from oracle import port
+    from graphattention.SPGA import HomoGraph, SpGraphAttentionLayer
+    U, I = 70, 110
+    u, i = port.synth_bipartite(U, I, 900, 11)
+    g = port.build_graph(np.stack([u, i]), U, I)
+    row, col = port.homo_edges(g, True)
+    graph = HomoGraph.from_pairs(torch.from_numpy(np.stack([g.eu, g.ei])).to(DEV), U, I, True)
+    torch.manual_seed(4)
+    layer = SpGraphAttentionLayer(64, 64, 0.0, 0.2, concat=True).to(DEV).train()
+    x = (torch.randn(U + I, 64) * 0.5)
+    w = torch.randn(U + I, 64)
+    xd = x.to(DEV).requires_grad_(True)
+    out = layer(xd, graph)
+    (out * w.to(DEV)).sum().backward()
+    st = dict(W=layer.W.detach().cpu().double()[None], a=layer.a.detach().cpu().double())
+    c = port.spgat_stage_forward(x.double(), st, row, col)
+    ref = torch.where(c["Z"] > 0, c["Z"], torch.expm1(c["Z"]))
+    assert rel_err(out.detach().cpu().numpy(), ref.numpy()) < 1e-4
+    G = w.double() * torch.where(c["Z"] > 0, torch.ones_like(c["Z"]), torch.exp(c["Z"]))
+    dX, gs = port.spgat_stage_backward(G, c, st, row, col)
+    assert rel_err(xd.grad.cpu().numpy(), dX.numpy()) < 1e-4
+    assert rel_err(layer.W.grad.cpu().numpy(), gs["W"][0].numpy()) < 1e-4
+    assert rel_err(layer.a.grad.cpu().numpy(), gs["a"].numpy()) < 1e-4
+    layer.p = 0.4
+    a, b = layer(xd, graph).detach(), layer(xd, graph).detach()
+    assert not torch.equal(a, b) and layer._call == 2
