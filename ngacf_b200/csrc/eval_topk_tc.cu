@@ -701,7 +701,12 @@ using namespace ngacf;
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-// item-tile segments per user block: fill the 2 x 148 CTA slots when there are few user blocks (a rank of a sharded evaluation)
+// item-tile segments per user block, for the few user blocks of a rank of a sharded evaluation: about one CTA per SM, at most four
+// segments.  Filling all 2 x 148 CTA slots does not pay: a user's lists share their filter threshold (gthr), but each list's own
+// threshold is the KP-th best of ITS columns only, so the shared value loosens with the number of lists (143 candidates per user reach
+// the re-score kernel with ten lists, 43 with four), and every CTA pays its pipeline fill and merges again.  Measured on the shard of
+// an 8-GPU evaluation (scripts/probe/shard_eval.py): 30 user blocks S = 9 -> 0.45 ms, S = 4 -> 0.29 ms; 52 blocks S = 5 -> 0.60,
+// S = 2 -> 0.58.
 // survivor-log buffers = CTA slots that can be resident at once (two CTAs per SM: shared memory)
 static int resident_ctas() {
     int dev = 0, sms = 148;
@@ -710,15 +715,13 @@ static int resident_ctas() {
     return 2 * (sms > 0 ? sms : 148);
 }
 
-// item-tile segments per user block: fill the 2 x 148 CTA slots when there are few user blocks (a rank of a sharded evaluation).
-// More segments than that do not pay: a user's lists share their filter threshold (gthr), but each list's own threshold is the
-// KP-th best of ITS columns only, so the shared value loosens with the number of lists (measured: 43 candidates per user reach the
-// re-score kernel with 4 lists, 143 with 10), and every CTA pays its pipeline fill and its merges again.
 struct TopkPlan { int S, lists_per_user; };
 static TopkPlan plan_topk(int n_users, int n_tiles) {
     TopkPlan p;
     const int blocks = (n_users + tc::TM - 1) / tc::TM;
-    int S = blocks > 0 ? (2 * 148) / blocks : 1;
+    int S = blocks > 0 ? 128 / blocks : 1;
+    if (S > 4) S = 4;
+    if (const char* v = getenv("NGACF_TOPK_SEGMENTS")) { if (*v) S = atoi(v); }     // tuning knob (scripts/probe/shard_eval.py)
     if (S > n_tiles / 16) S = n_tiles / 16;
     if (S < 1) S = 1;
     if (S > tc::MAX_LISTS / 2) S = tc::MAX_LISTS / 2;

@@ -1176,3 +1176,17 @@ def test_spgraphattentionlayer_standalone_64x64():
     layer.p = 0.4
     a, b = layer(xd, graph).detach(), layer(xd, graph).detach()
     assert not torch.equal(a, b) and layer._call == 2
+
+
+def test_eval_tc_segmented_user_shard_equals_exact():
+    """A small user shard of a large item set (a rank of a multi-GPU evaluation): the tensor-core scorer splits the item tiles into
+    S = 4 segments per user block, i.e. eight lists per user sharing one threshold -- ids and scores must equal the exact path."""
+    from ngacf_b200.evaluate import AllNegEvaluator
+    U, I = 2000, 12000                      # 94 item tiles -> S = 4 for 3 user blocks
+    it, dit, Zt, Fn = _eval_case(U, I, 60000, 9, 500)
+    users = dit.eval_users[:300].contiguous()
+    ev_tc, ev_ex = AllNegEvaluator(dit, "tc", users=users), AllNegEvaluator(dit, "exact", users=users)
+    ev_tc.rank(Zt)
+    ev_ex.rank(Zt)
+    assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
+    assert ev_tc.n_fallback <= 3
