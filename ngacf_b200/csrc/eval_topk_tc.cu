@@ -47,7 +47,7 @@ constexpr int KU = 32;                  // rank of the shared filter threshold i
                                         // in the exact kernel.  With 12 ranks the failure probability falls by ~(delta/gap)^8 (none observed).
 constexpr int CBUF = 384;               // survivor LOG entries per epilogue thread (append-only; ~150 used on the gowalla shape; overflow -> exact fallback)
 constexpr int EPI = 256;                // epilogue threads per CTA
-constexpr int MAX_LISTS = 32;           // 2 * S <= 32 lists per user
+constexpr int MAX_LISTS = 8;            // 2 * S <= 8 lists per user (plan_topk: at most four segments); sizes the re-score kernel's shared arrays
 constexpr int K = NGACF_TOPK;
 constexpr int PANEL = TN * 16;          // bytes of one k-chunk panel: 128 rows x 16 B
 constexpr int HALF_BYTES = 8 * PANEL;   // 16 KB: one operand half (hi or lo), 8 k-chunks
@@ -603,7 +603,7 @@ __device__ __forceinline__ float dot64_tree_g(float4 a, float4 b, unsigned gm) {
 // One 16-lane group per user: the user's 2*S candidate lists (KP entries each, disjoint item ranges) are re-scored exactly,
 // ranked under (score desc, id asc), and the top-20 is accepted only if no non-candidate can beat its last entry: a
 // non-candidate of list l has approx <= thr[l], hence exact <= thr[l] + delta.
-constexpr int RS_GROUPS = 4;            // users per CTA (64 threads; 24 KB of candidate scores / ids)
+constexpr int RS_GROUPS = 4;            // users per CTA (64 threads; 6 KB of candidate scores / ids)
 __global__ void __launch_bounds__(RS_GROUPS * 16) rescore_kernel(const float* __restrict__ F, int U, const int* __restrict__ users, int n_users,
                                                                 const int* __restrict__ cand_ids, const float* __restrict__ cand_sc,
                                                                 const float* __restrict__ cand_thr, const unsigned int* __restrict__ gthr,
