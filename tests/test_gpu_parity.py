@@ -1190,3 +1190,21 @@ def test_eval_tc_segmented_user_shard_equals_exact():
     ev_ex.rank(Zt)
     assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
     assert ev_tc.n_fallback <= 3
+
+
+def test_eval_tc_log_overflow_goes_to_exact_fallback():
+    """Adversarial score order: every item scores higher than all items before it, so every accumulator passes every threshold and a
+    list's survivor log (384 entries) overflows after six tiles.  The overflowing lists must be flagged (never truncated silently)
+    and the rows come back exact through the fallback."""
+    from ngacf_b200.evaluate import AllNegEvaluator
+    U, I = 200, 2500
+    it, dit, Zt, Fn = _eval_case(U, I, 6000, 12)
+    v = torch.randn(64, device=DEV).abs() + 0.1
+    Zt = Zt.clone()
+    Zt[:U] = v                                                   # every user = v (ELU keeps positive values)
+    Zt[U:] = v[None, :] * torch.linspace(0.5, 3.0, I, device=DEV)[:, None]      # item i = c_i v with c_i increasing
+    ev_tc, ev_ex = AllNegEvaluator(dit, "tc"), AllNegEvaluator(dit, "exact")
+    ev_tc.rank(Zt)
+    ev_ex.rank(Zt)
+    assert torch.equal(ev_tc.top_ids, ev_ex.top_ids) and torch.equal(ev_tc.top_scores, ev_ex.top_scores)
+    assert ev_tc.n_fallback == dit.eval_users.numel()           # every row overflowed
