@@ -253,3 +253,32 @@ def test_fused_paths_take_exact_model_types_only():
     assert isinstance(m, SPUIGACF) and not te._fused_ok(m, opt, BPRLoss()) and not te._plain_gat_model(m)
     with pytest.raises(NotImplementedError):
         te._require_plain(m, "eval_neg_all")
+
+
+def test_homograph_nonzero_index_matches_adj_nonzero_order():
+    """HomoGraph.nonzero_index (kernel order of the directed edges -> index into adj.nonzero(), the order in which the reference
+    draws its edge dropout, SPGA.py:379,398) against the dense adjacency, with and without the diagonal.  Runs on CPU tensors: the
+    method is pure index arithmetic over the unified adjacency."""
+    import types
+    import torch
+    from oracle import port
+    from ngacf_b200.spgat import HomoGraph
+    U, I = 17, 23
+    u, i = port.synth_bipartite(U, I, 160, 3)
+    g = port.build_graph(np.stack([u, i]), U, I)
+    N, E = U + I, g.E
+    adj_ptr = np.concatenate([g.rowptr.astype(np.int64), E + g.colptr[1:].astype(np.int64)])
+    adj_idx = np.concatenate([g.colidx.astype(np.int64) + U, g.rowidx.astype(np.int64)])        # neighbour node of every position
+    node = np.repeat(np.arange(N), np.diff(adj_ptr))
+    fake = types.SimpleNamespace(adj_ptr=torch.from_numpy(adj_ptr), N=N, U=U, E=E, device=torch.device("cpu"))
+    for self_loops in (False, True):
+        row, col = port.homo_edges(g, self_loops)
+        dense = torch.zeros(N, N)
+        dense[torch.from_numpy(row), torch.from_numpy(col)] = 1
+        nz = dense.nonzero().numpy()
+        assert (nz[:, 0] == row).all() and (nz[:, 1] == col).all()          # the port's edge order IS adj.nonzero()
+        idx = HomoGraph.nonzero_index(types.SimpleNamespace(g=fake, self_loops=self_loops)).numpy()
+        assert idx.shape[0] == 2 * E + (N if self_loops else 0) and len(set(idx.tolist())) == idx.shape[0]
+        assert (row[idx[:2 * E]] == node).all() and (col[idx[:2 * E]] == adj_idx).all()
+        if self_loops:
+            assert (row[idx[2 * E:]] == np.arange(N)).all() and (col[idx[2 * E:]] == np.arange(N)).all()
